@@ -1,0 +1,207 @@
+// pipeline.cpp -- the GPU batch dispatcher that replaces the reference's per-query worker
+// (map.c:264 worker_for -> map.c:143 mp_map), and the file-level driver around it (map.c:273-343).
+//
+// The reference maps one protein at a time, start to finish, on one CPU thread.  Here a whole mini-batch
+// moves through the same steps together, so that each compute step is ONE device stage over all proteins:
+//
+//   S1  seed_chain   sketch + index lookup + anchor sort + pre-chain + chain          (map.c:155-195)
+//   H1  regions      chains -> regions, order, primary/secondary, ext budgets          (map.c:196-208)
+//   S2  refine       per region: window 5-mers x protein 5-mers -> base-level chain   (map.c:32-111)
+//   H2  re-rank, seed filter, DP work list                                              (map.c:217-226, align.c)
+//   S3  nasw waves   wave 1 (extensions + inner fills), 1' (io_end retries), 2 (spans) (align.c:280-333)
+//   H3  statistics, final ranking                                                       (map.c:233-236)
+//
+// Results per protein are identical to mp_map() (no state crosses proteins: SURVEY 8b "determinism contract").
+#include <stdio.h>
+#include <algorithm>
+#include "internal.hpp"
+#include "align.hpp"
+#include "fastx.hpp"
+
+namespace mpb {
+
+namespace {
+
+struct QueryState {
+	mp_reg1_t *reg = 0;
+	int32_t n_reg = 0;
+	std::vector<uint64_t> anchors; // collated refined anchors of all regions (map.c:217 mp_collate_a)
+	std::vector<uint64_t> ext;
+};
+
+} // namespace
+
+void map_batch(Stages *st, const mp_idx_t *mi, const mp_mapopt_t *opt, const Batch &b, int32_t *n_reg_out, mp_reg1_t **reg_out)
+{
+	const int32_t n = b.n, kmer = mi->opt.kmer;
+	std::vector<QueryState> qs((size_t)n);
+
+	// ---- S1
+	ChainSet cs;
+	st->seed_chain(mi, opt, b, cs);
+
+	// ---- H1 + S2 work list
+	std::vector<RefineJob> rjobs;
+	std::vector<int32_t> rjob_first((size_t)n + 1, 0);
+	for (int32_t q = 0; q < n; ++q) {
+		QueryState &Q = qs[(size_t)q];
+		const int32_t n_u = (int32_t)(cs.u_off[(size_t)q + 1] - cs.u_off[(size_t)q]);
+		const uint64_t *u = cs.u.data() + cs.u_off[(size_t)q], *a = cs.a.data() + cs.a_off[(size_t)q];
+		Q.reg = regs_from_chains(mi, n_u, u, a, &Q.n_reg);
+		regs_sort(&Q.n_reg, Q.reg);
+		regs_set_parent(opt->mask_level, opt->mask_len, Q.n_reg, Q.reg, kmer, 0);
+		regs_select_sub(opt->pri_ratio * opt->pri_ratio, kmer * 2, opt->best_n, &Q.n_reg, Q.reg);
+		regs_max_ext(0, Q.n_reg, Q.reg, a, 100, opt->max_ext, Q.ext);
+		rjob_first[(size_t)q] = (int32_t)rjobs.size();
+		for (int32_t i = 0; i < Q.n_reg; ++i) { // window of map.c:41-42
+			const mp_reg1_t *r = &Q.reg[i];
+			const int64_t ctg_len = mi->nt->ctg[r->vid >> 1].len;
+			const int32_t extl = (int32_t)(Q.ext[(size_t)i] >> 32), extr = (int32_t)Q.ext[(size_t)i];
+			RefineJob j;
+			j.qid = q, j.vid = r->vid;
+			j.as = r->vs > extl ? r->vs - extl : 0;
+			j.ae = r->ve + extr < ctg_len ? r->ve + extr : ctg_len;
+			rjobs.push_back(j);
+		}
+	}
+	rjob_first[(size_t)n] = (int32_t)rjobs.size();
+	cs = ChainSet(); // first-round anchors are not needed any more
+
+	// ---- S2
+	RefineSet rs;
+	st->refine(mi, opt, b, rjobs, rs);
+
+	// ---- H2: adopt refined chains (map.c:83-109), re-rank (map.c:217-221)
+	const int32_t k2 = opt->kmer2;
+	for (int32_t q = 0; q < n; ++q) {
+		QueryState &Q = qs[(size_t)q];
+		int32_t kept = 0;
+		std::vector<int64_t> offs;
+		Q.anchors.clear();
+		for (int32_t i = 0; i < Q.n_reg; ++i) {
+			const size_t jb = (size_t)(rjob_first[(size_t)q] + i);
+			const int64_t na = rs.off[jb + 1] - rs.off[jb];
+			if (na == 0) continue;
+			mp_reg1_t r = Q.reg[i];
+			const uint64_t *ra = rs.a.data() + rs.off[jb];
+			const int64_t as = rjobs[jb].as;
+			r.chn_sc = rs.sc[jb];
+			r.cnt = (int32_t)na, r.off = (int32_t)Q.anchors.size();
+			r.qs = (int32_t)(uint32_t)ra[0] - (k2 - 1);
+			r.qe = (int32_t)(uint32_t)ra[na - 1] + 1;
+			r.vs = as + (int64_t)(ra[0] >> 32) + 1 - 3 * k2;
+			r.ve = as + (int64_t)(ra[na - 1] >> 32) + 1;
+			for (int64_t t = 0; t < na; ++t)
+				Q.anchors.push_back(((ra[t] >> 32) + (uint64_t)(as - r.vs)) << 32 | (ra[t] & 0xffffffffULL));
+			r.chn_sc_ungap = chain_score_ungapped(r.cnt, Q.anchors.data() + r.off, k2);
+			Q.reg[kept++] = r;
+		}
+		Q.n_reg = kept;
+		for (int32_t i = 0; i < Q.n_reg; ++i) Q.reg[i].a = Q.anchors.data() + Q.reg[i].off;
+		regs_sort(&Q.n_reg, Q.reg);
+		regs_set_parent(opt->mask_level, opt->mask_len, Q.n_reg, Q.reg, kmer, 0);
+		regs_select_sub(opt->pri_ratio * opt->pri_ratio, kmer * 2, opt->best_n, &Q.n_reg, Q.reg);
+	}
+	rs = RefineSet();
+
+	// ---- S3: alignment in three waves
+	if (!(opt->flag & MP_F_NO_ALIGN)) {
+		ns_opt_t nso;
+		make_ns_opt(opt, &nso);
+		std::vector<RegionPlan> plans;
+		std::vector<DpJob> w1, w1r, w2;
+		DpSet o1, o1r, o2;
+		for (int32_t q = 0; q < n; ++q) {
+			QueryState &Q = qs[(size_t)q];
+			regs_max_ext(mi->nt, Q.n_reg, Q.reg, Q.anchors.data(), 100, opt->max_intron / 2, Q.ext);
+			for (int32_t i = 0; i < Q.n_reg; ++i) {
+				RegionPlan p;
+				if (p.plan(mi, opt, q, b.len[q], b.seq[q], &Q.reg[i], (int32_t)(Q.ext[(size_t)i] >> 32), (int32_t)Q.ext[(size_t)i], w1))
+					plans.push_back(std::move(p));
+			}
+		}
+		st->nasw(mi, &nso, b, w1, o1);
+		for (RegionPlan &p : plans) p.after_wave1(opt, o1, w1r);
+		st->nasw(mi, &nso, b, w1r, o1r);
+		for (RegionPlan &p : plans) p.after_retry(mi, opt, b.seq[p.qid], o1r, w2);
+		st->nasw(mi, &nso, b, w2, o2);
+		for (RegionPlan &p : plans) p.finish(mi, opt, b.seq[p.qid], o1, o2);
+		// ---- H3 (map.c:228-236)
+		for (int32_t q = 0; q < n; ++q) {
+			QueryState &Q = qs[(size_t)q];
+			int32_t k = 0;
+			for (int32_t i = 0; i < Q.n_reg; ++i) if (Q.reg[i].p) Q.reg[k++] = Q.reg[i];
+			Q.n_reg = k;
+			regs_sort(&Q.n_reg, Q.reg);
+			regs_select_multi_exon(Q.n_reg, Q.reg, opt->io);
+			regs_set_parent(opt->mask_level, opt->mask_len, Q.n_reg, Q.reg, kmer, 0);
+			regs_select_sub(opt->pri_ratio, kmer * 2, opt->best_n, &Q.n_reg, Q.reg);
+		}
+	}
+	for (int32_t q = 0; q < n; ++q) {
+		QueryState &Q = qs[(size_t)q];
+		for (int32_t i = 0; i < Q.n_reg; ++i) Q.reg[i].a = 0; // the anchor store dies with this call
+		n_reg_out[q] = Q.n_reg, reg_out[q] = Q.reg;
+	}
+}
+
+// map.c:293-326: per protein, hits in rank order subject to --outn / --outs / --outc; unmapped line with -u
+static void write_batch(FILE *out, Str &buf, const mp_idx_t *mi, const mp_mapopt_t *opt, const Batch &b, const int32_t *n_reg, mp_reg1_t *const *reg)
+{
+	for (int32_t q = 0; q < b.n; ++q) {
+		int32_t best = -1, n_out = 0;
+		buf.l = 0;
+		if (n_reg[q] > 0) best = reg[q][0].p ? reg[q][0].p->dp_max : reg[q][0].chn_sc;
+		for (int32_t j = 0; j < n_reg[q] && j < opt->out_n; ++j) {
+			const mp_reg1_t *r = &reg[q][j];
+			const int32_t sc = r->p ? r->p->dp_max : r->chn_sc;
+			if (sc <= 0 || sc < (double)best * opt->out_sim) continue;
+			if (r->qe - r->qs < (double)b.len[q] * opt->out_cov) continue;
+			if (!(opt->flag & MP_F_NO_PAF)) format_hit(buf, mi, opt, b.name[q], b.len[q], b.seq[q], r);
+			++n_out;
+		}
+		if (n_out == 0 && (opt->flag & MP_F_SHOW_UNMAP)) format_hit(buf, mi, opt, b.name[q], b.len[q], b.seq[q], 0);
+		if (buf.l) fwrite(buf.s, 1, (size_t)buf.l, out);
+	}
+}
+
+int32_t map_file(Stages *st, const mp_idx_t *mi, const char *fn, const mp_mapopt_t *opt, FILE *out)
+{
+	FastxReader rd(fn);
+	if (!rd.fp) return -1;
+	if (opt->flag & (MP_F_GFF | MP_F_GTF | MP_F_SHOW_RESIDUE | MP_F_SHOW_TRANS))
+		fprintf(stderr, "[WARNING] GFF/GTF/--aln/--trans output is not produced by miniprot_b200 in this round; writing PAF only\n");
+	std::vector<std::string> names, seqs;
+	std::string name, seq;
+	Str buf;
+	bool more = true;
+	int64_t n_done = 0;
+	while (more) {
+		int64_t residues = 0;
+		names.clear(), seqs.clear();
+		while (residues < opt->mini_batch_size && (more = rd.next(name, seq))) { // bseq.c:53-74
+			names.push_back(name), seqs.push_back(seq);
+			residues += (int64_t)seq.size();
+		}
+		if (seqs.empty()) break;
+		const int32_t n = (int32_t)seqs.size();
+		std::vector<const char*> sp((size_t)n), np((size_t)n);
+		std::vector<int32_t> len((size_t)n), n_reg((size_t)n);
+		std::vector<mp_reg1_t*> reg((size_t)n);
+		for (int32_t i = 0; i < n; ++i) sp[(size_t)i] = seqs[(size_t)i].c_str(), np[(size_t)i] = names[(size_t)i].c_str(), len[(size_t)i] = (int32_t)seqs[(size_t)i].size();
+		Batch b;
+		b.n = n, b.seq = sp.data(), b.len = len.data(), b.name = np.data();
+		map_batch(st, mi, opt, b, n_reg.data(), reg.data());
+		write_batch(out, buf, mi, opt, b, n_reg.data(), reg.data());
+		for (int32_t i = 0; i < n; ++i) {
+			for (int32_t j = 0; j < n_reg[(size_t)i]; ++j) free(reg[(size_t)i][j].feat), free(reg[(size_t)i][j].p);
+			free(reg[(size_t)i]);
+		}
+		n_done += n;
+		if (mp_verbose >= 3) fprintf(stderr, "[M::%s::%.3f*%.2f] mapped %d sequences\n", __func__, mp_realtime(), mp_cputime() / mp_realtime(), n);
+	}
+	free(buf.s);
+	return 0;
+}
+
+} // namespace mpb
