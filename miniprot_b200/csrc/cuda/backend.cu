@@ -1,0 +1,296 @@
+// backend.cu -- the CUDA implementation of the stage interface (mpb::Stages) and the C ABI of the batch API.
+// This is the ONLY implementation of the stages in the product: there is no CPU fallback.
+#include <stdio.h>
+#include <mutex>
+#include "ctx.hpp"
+#include "stages_dev.hpp"
+#include "../align.hpp"
+
+using namespace mpb;
+using namespace mpb::cuda;
+
+namespace {
+
+// device job from a pipeline job: where DP row 0 sits in the packed genome and which way rows walk
+DpDev make_dev_job(const mp_idx_t *mi, const DpJob &j, int32_t aa_base)
+{
+	DpDev d;
+	memset(&d, 0, sizeof(d));
+	const mp_ctg_t *c = &mi->nt->ctg[j.vid >> 1];
+	const bool rev = j.vid & 1, left = j.flag & NS_F_EXT_LEFT;
+	if (!left) {
+		d.g_start = rev ? c->off + c->len - 1 - j.nt_st : c->off + j.nt_st;
+		d.dir = rev ? -1 : 1;
+	} else { // rows run from the anchor outwards, i.e. against the strand
+		d.g_start = rev ? c->off + c->len - j.nt_st - j.nl : c->off + j.nt_st + j.nl - 1;
+		d.dir = rev ? 1 : -1;
+	}
+	d.comp = rev ? 1 : 0;
+	d.nl = j.nl, d.al = j.al, d.aa_off = aa_base + j.aa_st, d.flag = j.flag, d.io = j.io;
+	return d;
+}
+
+struct CudaStages : Stages {
+	mpb_ctx_s *ctx;
+	explicit CudaStages(mpb_ctx_s *c) : ctx(c) {}
+
+	void need_index(const mp_idx_t *mi)
+	{
+		if (ctx->mi != mi || !ctx->d_seq) {
+			if (mpb_idx_upload(ctx, mi) != 0) { fprintf(stderr, "[miniprot_b200] index upload failed\n"); abort(); }
+		}
+	}
+	// residues of the whole batch, concatenated, resident for the duration of the call
+	const char *upload_residues(const Batch &b, std::vector<int32_t> &off)
+	{
+		off.assign((size_t)b.n + 1, 0);
+		for (int32_t i = 0; i < b.n; ++i) off[(size_t)i + 1] = off[(size_t)i] + b.len[i];
+		const size_t tot = (size_t)off[(size_t)b.n];
+		ctx->b_aa.reserve(tot + 16);
+		ctx->h_c[0].reserve(tot + 16);
+		char *h = ctx->h_c[0].as<char>();
+		for (int32_t i = 0; i < b.n; ++i) memcpy(h + off[(size_t)i], b.seq[i], (size_t)b.len[i]);
+		MPB_CUDA_OK(cudaMemcpyAsync(ctx->b_aa.p, h, tot, cudaMemcpyHostToDevice, ctx->stream));
+		MPB_CUDA_OK(cudaStreamSynchronize(ctx->stream)); // staging buffer is reused
+		ctx->stats.h2d_bytes += (int64_t)tot;
+		return ctx->b_aa.as<char>();
+	}
+
+	void seed_chain(const mp_idx_t *mi, const mp_mapopt_t *opt, const Batch &b, ChainSet &out) override
+	{
+		need_index(mi);
+		std::vector<int32_t> off;
+		const char *d_aa = upload_residues(b, off);
+		seed_chain_run(ctx, mi, opt, b, off, d_aa, out);
+	}
+	void refine(const mp_idx_t *mi, const mp_mapopt_t *opt, const Batch &b, const std::vector<RefineJob> &jobs, RefineSet &out) override
+	{
+		need_index(mi);
+		std::vector<int32_t> off;
+		const char *d_aa = upload_residues(b, off);
+		refine_run(ctx, mi, opt, b, off, d_aa, jobs, out);
+	}
+	void nasw(const mp_idx_t *mi, const ns_opt_t *base, const Batch &b, const std::vector<DpJob> &jobs, DpSet &out) override
+	{
+		need_index(mi);
+		std::vector<int32_t> off;
+		const char *d_aa = upload_residues(b, off);
+		std::vector<DpDev> dj(jobs.size());
+		for (size_t k = 0; k < jobs.size(); ++k) dj[k] = make_dev_job(mi, jobs[k], off[(size_t)jobs[k].qid]);
+		nasw_run(ctx, ctx->d_seq, d_aa, base, dj, out);
+	}
+};
+
+std::mutex g_default_mu;
+mpb_ctx_t *g_default_ctx = 0;
+
+} // namespace
+
+extern "C" {
+
+mpb_ctx_t *mpb_ctx_create(int device)
+{
+	int n_dev = 0;
+	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+		fprintf(stderr, "[miniprot_b200] no CUDA device: the mapping stages exist only as sm_100a kernels (no CPU fallback)\n");
+		return 0;
+	}
+	if (device < 0 || device >= n_dev) { fprintf(stderr, "[miniprot_b200] bad device %d (have %d)\n", device, n_dev); return 0; }
+	MPB_CUDA_OK(cudaSetDevice(device));
+	mpb_ctx_s *c = new mpb_ctx_s();
+	c->device = device;
+	MPB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	MPB_CUDA_OK(cudaEventCreate(&c->ev0));
+	MPB_CUDA_OK(cudaEventCreate(&c->ev1));
+	memset(&c->stats, 0, sizeof(c->stats));
+	c->stages = new CudaStages(c);
+	if (ns_tab_aa20[(uint8_t)'X'] != 21) mp_start();
+	return c;
+}
+
+void mpb_ctx_destroy(mpb_ctx_t *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	DevBuf *bufs[] = { &c->own_ki, &c->own_kb, &c->own_seq, &c->own_bo, &c->own_ctg, &c->b_jobs, &c->b_order, &c->b_chunks, &c->b_rw, &c->b_aa, &c->b_out,
+	                   &c->b_carry, &c->b_tb, &c->b_cigar, &c->b_packed };
+	for (DevBuf *b : bufs) b->release();
+	for (DevBuf &b : c->b_c) b.release();
+	c->h_out.release(), c->h_cigar.release();
+	for (PinBuf &b : c->h_c) b.release();
+	cudaEventDestroy(c->ev0), cudaEventDestroy(c->ev1);
+	cudaStreamDestroy(c->stream);
+	delete c->stages;
+	delete c;
+}
+
+mpb_ctx_t *mpb_ctx_default(void)
+{
+	std::lock_guard<std::mutex> lk(g_default_mu);
+	if (!g_default_ctx) {
+		int dev = 0;
+		if (const char *e = getenv("LOCAL_RANK")) dev = atoi(e);
+		g_default_ctx = mpb_ctx_create(dev);
+		if (!g_default_ctx) { fprintf(stderr, "[miniprot_b200] cannot run without a GPU\n"); abort(); }
+	}
+	return g_default_ctx;
+}
+
+static void upload_meta(mpb_ctx_s *c, const mp_idx_t *mi)
+{
+	const int32_t n_ctg = mi->nt->n_ctg;
+	c->own_bo.reserve(sizeof(uint32_t) * (size_t)(2 * n_ctg + 1));
+	MPB_CUDA_OK(cudaMemcpy(c->own_bo.p, mi->bo, sizeof(uint32_t) * (size_t)(2 * n_ctg + 1), cudaMemcpyHostToDevice));
+	std::vector<int64_t> ctg((size_t)n_ctg * 2);
+	for (int32_t i = 0; i < n_ctg; ++i) ctg[(size_t)i * 2] = mi->nt->ctg[i].off, ctg[(size_t)i * 2 + 1] = mi->nt->ctg[i].len;
+	c->own_ctg.reserve(sizeof(int64_t) * ctg.size() + 16);
+	MPB_CUDA_OK(cudaMemcpy(c->own_ctg.p, ctg.data(), sizeof(int64_t) * ctg.size(), cudaMemcpyHostToDevice));
+	c->d_bo = c->own_bo.as<uint32_t>(), c->d_ctg = c->own_ctg.as<int64_t>();
+}
+
+int mpb_idx_upload(mpb_ctx_t *c, const mp_idx_t *mi)
+{
+	if (!c || !mi) return -1;
+	MPB_CUDA_OK(cudaSetDevice(c->device));
+	const size_t nb = idx_n_bucket(&mi->opt), seq_bytes = (size_t)((mi->nt->l_seq + 1) >> 1);
+	c->own_ki.reserve(sizeof(int64_t) * (nb + 1));
+	c->own_kb.reserve(sizeof(uint32_t) * (size_t)(mi->n_kb + 1));
+	c->own_seq.reserve(seq_bytes + 16);
+	MPB_CUDA_OK(cudaMemcpy(c->own_ki.p, mi->ki, sizeof(int64_t) * nb, cudaMemcpyHostToDevice));
+	MPB_CUDA_OK(cudaMemcpy(c->own_ki.as<int64_t>() + nb, &mi->n_kb, sizeof(int64_t), cudaMemcpyHostToDevice)); // sentinel: end of the last bucket
+	MPB_CUDA_OK(cudaMemcpy(c->own_kb.p, mi->kb, sizeof(uint32_t) * (size_t)mi->n_kb, cudaMemcpyHostToDevice));
+	MPB_CUDA_OK(cudaMemcpy(c->own_seq.p, mi->nt->seq, seq_bytes, cudaMemcpyHostToDevice));
+	c->d_ki = c->own_ki.as<int64_t>(), c->d_kb = c->own_kb.as<uint32_t>(), c->d_seq = c->own_seq.as<uint8_t>();
+	upload_meta(c, mi);
+	c->mi = mi, c->own_index = true;
+	c->stats.h2d_bytes += (int64_t)(sizeof(int64_t) * nb + sizeof(uint32_t) * (size_t)mi->n_kb + seq_bytes);
+	return 0;
+}
+
+int mpb_idx_attach_device(mpb_ctx_t *c, const mp_idx_t *mi, void *d_ki, void *d_kb, void *d_seq)
+{
+	if (!c || !mi || !d_ki || !d_kb || !d_seq) return -1;
+	MPB_CUDA_OK(cudaSetDevice(c->device));
+	c->d_ki = (int64_t*)d_ki, c->d_kb = (uint32_t*)d_kb, c->d_seq = (uint8_t*)d_seq;
+	upload_meta(c, mi);
+	c->mi = mi, c->own_index = false;
+	return 0;
+}
+
+int mpb_map_batch(mpb_ctx_t *c, const mp_idx_t *mi, const mp_mapopt_t *opt, int32_t n_seq, const char *const *seqs, const int32_t *lens,
+                  const char *const *names, int32_t *n_reg_out, mp_reg1_t **reg_out)
+{
+	if (!c) return -1;
+	MPB_CUDA_OK(cudaSetDevice(c->device));
+	Batch b;
+	b.n = n_seq, b.seq = seqs, b.len = lens, b.name = names;
+	map_batch(c->stages, mi, opt, b, n_reg_out, reg_out);
+	return 0;
+}
+
+int32_t mpb_map_file(mpb_ctx_t *c, const mp_idx_t *mi, const char *fn, const mp_mapopt_t *opt, FILE *out)
+{
+	if (!c) return -1;
+	MPB_CUDA_OK(cudaSetDevice(c->device));
+	return map_file(c->stages, mi, fn, opt, out);
+}
+
+int32_t mpb_map_file_path(mpb_ctx_t *c, const mp_idx_t *mi, const char *fn, const mp_mapopt_t *opt, const char *out_path)
+{
+	FILE *fp = fopen(out_path, "wb");
+	if (!fp) return -2;
+	int32_t rc = mpb_map_file(c, mi, fn, opt, fp);
+	fclose(fp);
+	return rc;
+}
+
+mp_reg1_t *mp_map(const mp_idx_t *mi, int qlen, const char *seq, int *n_reg, mp_tbuf_t *, const mp_mapopt_t *opt, const char *qname)
+{
+	mp_reg1_t *reg = 0;
+	int32_t len = qlen, nr = 0;
+	mpb_map_batch(mpb_ctx_default(), mi, opt, 1, &seq, &len, &qname, &nr, &reg);
+	*n_reg = nr;
+	return reg;
+}
+
+int32_t mp_map_file(const mp_idx_t *mi, const char *fn, const mp_mapopt_t *opt, int)
+{
+	return mpb_map_file(mpb_ctx_default(), mi, fn, opt, stdout);
+}
+
+int64_t mpb_format_paf(const mp_idx_t *mi, const mp_mapopt_t *opt, const char *qname, int32_t qlen, const char *qseq, const mp_reg1_t *r, char **buf,
+                       int64_t *len, int64_t *cap)
+{
+	Str s;
+	s.s = *buf, s.l = *len, s.m = *cap;
+	format_hit(s, mi, opt, qname, qlen, qseq, r);
+	*buf = s.s, *len = s.l, *cap = s.m;
+	return s.l;
+}
+
+int mpb_nasw_batch(mpb_ctx_t *c, const ns_opt_t *opt, int32_t n, const mpb_dp_problem_t *prob, mpb_dp_result_t *rst)
+{
+	if (!c) return -1;
+	MPB_CUDA_OK(cudaSetDevice(c->device));
+	// pack the host sequences the way the genome is stored, so that the same kernels serve both paths
+	int64_t nt_tot = 0, aa_tot = 0;
+	for (int32_t i = 0; i < n; ++i) {
+		if (prob[i].ss) { fprintf(stderr, "[miniprot_b200] splice-score bytes (ss) are not supported on the device yet\n"); return -2; }
+		nt_tot += prob[i].nl + 2, aa_tot += prob[i].al;
+	}
+	std::vector<uint8_t> packed((size_t)(nt_tot / 2 + 2), 0);
+	std::vector<char> aa((size_t)aa_tot + 1);
+	std::vector<DpDev> jobs((size_t)n);
+	int64_t g = 0, a = 0;
+	for (int32_t i = 0; i < n; ++i) {
+		const mpb_dp_problem_t &p = prob[i];
+		for (int32_t k = 0; k < p.nl; ++k) packed[(size_t)((g + k) >> 1)] |= (uint8_t)(ns_tab_nt4[p.nt[k]] << (((g + k) & 1) * 4));
+		memcpy(aa.data() + a, p.aa, (size_t)p.al);
+		DpDev &d = jobs[(size_t)i];
+		memset(&d, 0, sizeof(d));
+		const bool left = p.flag & NS_F_EXT_LEFT;
+		d.g_start = left ? g + p.nl - 1 : g, d.dir = left ? -1 : 1, d.comp = 0;
+		d.nl = p.nl, d.al = p.al, d.aa_off = (int32_t)a, d.flag = p.flag, d.io = p.io;
+		g += p.nl + 2, a += p.al;
+	}
+	c->b_packed.reserve(packed.size() + 16);
+	c->b_aa.reserve(aa.size() + 16);
+	MPB_CUDA_OK(cudaMemcpyAsync(c->b_packed.p, packed.data(), packed.size(), cudaMemcpyHostToDevice, c->stream));
+	MPB_CUDA_OK(cudaMemcpyAsync(c->b_aa.p, aa.data(), aa.size(), cudaMemcpyHostToDevice, c->stream));
+	MPB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	c->stats.h2d_bytes += (int64_t)(packed.size() + aa.size());
+	DpSet out;
+	nasw_run(c, c->b_packed.as<uint8_t>(), c->b_aa.as<char>(), opt, jobs, out);
+	for (int32_t i = 0; i < n; ++i) {
+		rst[i].score = out.score[(size_t)i], rst[i].nt_len = out.nt_len[(size_t)i], rst[i].aa_len = out.aa_len[(size_t)i];
+		const int64_t nc = out.cig_off[(size_t)i + 1] - out.cig_off[(size_t)i];
+		rst[i].n_cigar = (int32_t)nc, rst[i].cigar = 0;
+		if (nc > 0) {
+			rst[i].cigar = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)nc);
+			memcpy(rst[i].cigar, out.cig.data() + out.cig_off[(size_t)i], sizeof(uint32_t) * (size_t)nc);
+		}
+	}
+	return 0;
+}
+
+void ns_global_gs16b(void *, const char *ns, int32_t nl, const char *as, int32_t al, const ns_opt_t *opt, const uint8_t *ss, ns_rst_t *r)
+{
+	mpb_dp_problem_t p;
+	mpb_dp_result_t o;
+	p.nt = (const uint8_t*)ns, p.aa = as, p.ss = ss, p.nl = nl, p.al = al, p.flag = opt->flag, p.io = opt->io;
+	if (mpb_nasw_batch(mpb_ctx_default(), opt, 1, &p, &o) != 0) abort();
+	r->score = o.score, r->nt_len = o.nt_len, r->aa_len = o.aa_len;
+	r->n_cigar = r->m_cigar = o.n_cigar, r->cigar = o.cigar;
+	if (!(opt->flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT))) r->nt_len = nl, r->aa_len = al;
+}
+
+void ns_global_gs16(void *km, const char *ns, int32_t nl, const char *as, int32_t al, const ns_opt_t *opt, ns_rst_t *r)
+{
+	ns_global_gs16b(km, ns, nl, as, al, opt, 0, r);
+}
+
+void mpb_get_stats(const mpb_ctx_t *c, mpb_stats_t *st) { *st = c->stats; }
+void mpb_reset_stats(mpb_ctx_t *c) { memset(&c->stats, 0, sizeof(c->stats)); }
+
+} // extern "C"

@@ -1,0 +1,195 @@
+// chain_core.cuh -- anchor chaining (reference chain.c) as host+device building blocks.
+//
+// The chaining kernels (chain_kernels.cu) use one warp per chaining problem for the score fill and one thread
+// per problem for the inherently sequential backtrack; everything below is the arithmetic and the sequential
+// logic they share with the CPU lock-step emulation in tests/hostcheck (test infrastructure only).
+//
+//   pair_score()      chain.c:112-151  gap-aware score of linking anchor j -> i (FP32 penalties, truncated)
+//   resolve_chunk()   chain.c:191-205  the order-dependent part of the predecessor scan for 32 candidates at once:
+//                                      records (new maxima), the max_skip counter and the early break
+//   backtrack_compact() chain.c:26-110 ends sorted by score with the reference's tie order, best-first peeling,
+//                                      chains reversed and ordered by target start
+#pragma once
+#include <stdint.h>
+#include "../flagsort.hpp"
+
+#ifdef __CUDACC__
+#define CHN_HD __host__ __device__ __forceinline__
+#else
+#define CHN_HD inline
+#endif
+
+namespace chn {
+
+struct Par { int32_t max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc; float chn_coef_log; int32_t is_spliced, kmer, bbit; };
+
+// chain.c:160-174: parameter fix-ups done once per mp_chain call
+CHN_HD Par normalise(Par p)
+{
+	if (p.max_dist_x < p.bw) p.max_dist_x = p.bw;
+	if (p.max_dist_y < p.bw && !p.is_spliced) p.max_dist_y = p.bw;
+	return p;
+}
+
+// mppriv.h:91-99, every FP32 operation rounded separately (the reference is built without FMA contraction)
+CHN_HD float log2_approx(float x)
+{
+	union { float f; uint32_t i; } z;
+	z.f = x;
+	float r = (float)((int)((z.i >> 23) & 255) - 128);
+	z.i &= ~(255u << 23);
+	z.i += 127u << 23;
+#ifdef __CUDA_ARCH__
+	float q = __fadd_rn(__fmul_rn(-0.34484843f, z.f), 2.02466578f);
+	q = __fsub_rn(__fmul_rn(q, z.f), 0.67487759f);
+	return __fadd_rn(r, q);
+#else
+	volatile float q = -0.34484843f * z.f;
+	q = q + 2.02466578f;
+	q = q * z.f;
+	q = q - 0.67487759f;
+	volatile float s = r + q;
+	return s;
+#endif
+}
+
+CHN_HD int32_t pair_score(const Par &p, uint64_t ai, uint64_t aj)
+{
+	const int32_t dq = (int32_t)ai - (int32_t)aj, dq3 = dq * 3;
+	int32_t dr3, dd, dds = 0, sc;
+	if (dq <= 0 || dq3 > p.max_dist_x || dq > p.max_dist_y) return INT32_MIN;
+	if (p.bbit > 0) {
+		const int32_t bs = 1 << p.bbit;
+		dr3 = (int32_t)(((ai >> 32) - (aj >> 32)) << p.bbit);
+		if (dq3 < dr3 - bs) dd = dr3 - bs - dq3, dds = -dd;
+		else if (dq3 > dr3 + bs) dd = dq3 - (dr3 + bs), dds = dd;
+		else dd = 0;
+	} else {
+		dr3 = (int32_t)((ai >> 32) - (aj >> 32));
+		if (dr3 == 0) return INT32_MIN;
+		dd = dr3 > dq3 ? dr3 - dq3 : dq3 - dr3;
+		dds = dq3 - dr3;
+	}
+	if (dd > p.bw) return INT32_MIN;
+	if (p.bbit > 0) sc = p.kmer < dq ? p.kmer : dq;
+	else if (p.kmer <= dq && p.kmer * 3 <= dr3) sc = p.kmer;
+	else {
+		const int32_t dr = dr3 / 3, g = dr < dq ? dr : dq;
+		sc = g < p.kmer ? g : p.kmer;
+		if (dr3 - dr * 3 != 0) --sc;
+	}
+	if (dd > 0) {
+#ifdef __CUDA_ARCH__
+		const float lin = __fmul_rn((float)dd, .33334f);
+		const float lg = dd >= 2 ? __fadd_rn(__fmul_rn(p.chn_coef_log, __fsub_rn(log2_approx((float)(dd + 1)), 1.0f)), 1.0f) : (float)dd;
+		if (p.is_spliced && dds < 0) sc -= (int32_t)(lin < lg ? lin : lg);
+		else sc -= (int32_t)__fadd_rn(lin, lg);
+#else
+		volatile float lin = (float)dd * .33334f;
+		volatile float lg = (float)dd;
+		if (dd >= 2) { volatile float t = log2_approx((float)(dd + 1)) - 1.0f; t = p.chn_coef_log * t; lg = t + 1.0f; }
+		if (p.is_spliced && dds < 0) sc -= (int32_t)(lin < lg ? lin : lg);
+		else { volatile float s = lin + lg; sc -= (int32_t)s; }
+#endif
+	}
+	if (p.bbit > 0 && ai >> 32 == aj >> 32 && dd == 0) sc += 2;
+	return sc;
+}
+
+// 32 candidates j = jb, jb-1, ... (bit L = lane L = candidate jb-L) scanned in that order.
+//   rec  : candidates whose score beats everything before them (running maximum, incl. the incoming max_f)
+//   skip : non-record candidates already marked as "predecessor of something seen" (t[j] == i)
+// Applies chain.c:196-203 and returns the lane at which the scan breaks (32 = no break); n_skip is updated.
+CHN_HD int resolve_chunk(uint32_t rec, uint32_t skip, int32_t max_skip, int32_t &n_skip)
+{
+	if (skip == 0) { // only decrements
+		const int32_t d = (int32_t)
+#ifdef __CUDA_ARCH__
+			__popc(rec);
+#else
+			__builtin_popcount(rec);
+#endif
+		n_skip = n_skip > d ? n_skip - d : 0;
+		return 32;
+	}
+	uint32_t m = rec | skip;
+	while (m) {
+#ifdef __CUDA_ARCH__
+		const int b = __ffs(m) - 1;
+#else
+		const int b = __builtin_ctz(m);
+#endif
+		if (rec >> b & 1) { if (n_skip > 0) --n_skip; }
+		else if (++n_skip > max_skip) return b;
+		m &= m - 1;
+	}
+	return 32;
+}
+
+struct End { uint64_t x, y; }; // sort record: key x, payload y (same layout as mp128_t)
+
+// chain.c:8-24
+CHN_HD int64_t bk_end(int32_t max_drop, const End &z, const int32_t *f, const int32_t *p, int32_t *t)
+{
+	int64_t i = (int64_t)z.y, end_i = -1, max_i = i;
+	int32_t max_s = 0;
+	if (i < 0 || t[i] != 0) return i;
+	do {
+		t[i] = 2;
+		end_i = i = p[i];
+		const int32_t s = i < 0 ? (int32_t)z.x : (int32_t)z.x - f[i];
+		if (s > max_s) max_s = s, max_i = i;
+		else if (max_s - s > max_drop) break;
+	} while (i >= 0 && t[i] == 0);
+	for (i = (int64_t)z.y; i >= 0 && i != end_i; i = p[i]) t[i] = 0;
+	return max_i;
+}
+
+// Sequential tail of mp_chain for ONE problem.  Scratch: t[n], v[n], z[n], stack[>=1100].
+// Output: u[0..n_u) = score<<32|cnt, b[0..n_b) = compacted anchors (chains ordered by target start).  Returns n_u.
+CHN_HD int32_t backtrack_compact(const Par &p, int32_t n, const uint64_t *a, const int32_t *f, const int32_t *pp, int32_t *t, int32_t *v, End *z,
+                                 mpb::FlagRange<End> *stack, uint64_t *u, uint64_t *b, int32_t *n_b_out)
+{
+	const int32_t max_drop = p.is_spliced ? INT32_MAX : p.bw;
+	int32_t n_z = 0, n_u = 0, n_v = 0;
+	*n_b_out = 0;
+	for (int32_t i = 0; i < n; ++i) if (f[i] >= p.min_sc) z[n_z].x = (uint64_t)(int64_t)f[i], z[n_z].y = (uint64_t)i, ++n_z;
+	if (n_z == 0) return 0;
+	mpb::flag_sort_by(z, z + n_z, [](const End &e) { return e.x; }, stack);
+	for (int32_t i = 0; i < n; ++i) t[i] = 0;
+	for (int32_t k = n_z - 1; k >= 0; --k) {
+		if (t[z[k].y] != 0) continue;
+		const int32_t n_v0 = n_v;
+		const int64_t end_i = bk_end(max_drop, z[k], f, pp, t);
+		int64_t i;
+		for (i = (int64_t)z[k].y; i != end_i; i = pp[i]) v[n_v++] = (int32_t)i, t[i] = 1;
+		const int32_t sc = i < 0 ? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+		if (sc >= p.min_sc && n_v > n_v0 && n_v - n_v0 >= p.min_cnt) u[n_u++] = (uint64_t)sc << 32 | (uint64_t)(n_v - n_v0);
+		else n_v = n_v0;
+	}
+	if (n_u == 0) return 0;
+	// compact (chain.c:77-110); z[] is reused as the chain-order sort buffer, t[] as the per-chain start offsets
+	End *w = z;
+	int32_t k = 0;
+	for (int32_t i = 0; i < n_u; ++i) {
+		const int32_t ni = (int32_t)(uint32_t)u[i];
+		w[i].x = a[v[k + ni - 1]] >> 32; // first anchor of the chain after reversal
+		w[i].y = (uint64_t)k << 32 | (uint64_t)i;
+		k += ni;
+	}
+	mpb::flag_sort_by(w, w + n_u, [](const End &e) { return e.x; }, stack);
+	int32_t o = 0;
+	for (int32_t i = 0; i < n_u; ++i) {
+		const int32_t src = (int32_t)(uint32_t)w[i].y, k0 = (int32_t)(w[i].y >> 32), ni = (int32_t)(uint32_t)u[src];
+		for (int32_t j = 0; j < ni; ++j) b[o++] = a[v[k0 + (ni - j - 1)]];
+		t[i] = src; // remember the permutation to reorder u[] afterwards
+	}
+	// u2[i] = u[perm[i]]: done through v[] (free now) to avoid aliasing
+	for (int32_t i = 0; i < n_u; ++i) v[i] = t[i];
+	for (int32_t i = 0; i < n_u; ++i) { z[i].x = u[v[i]]; }
+	for (int32_t i = 0; i < n_u; ++i) u[i] = z[i].x;
+	*n_b_out = o;
+	return n_u;
+}
+
+} // namespace chn

@@ -1,0 +1,18 @@
+// chain_dev.hpp -- launcher prototypes of the chaining kernels (chain_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "chain_core.cuh"
+
+namespace mpb {
+namespace cuda {
+
+constexpr int CHAIN_STACK = 1100; // pending ranges of the flag sort per problem (<= 4 significant key bytes)
+
+void chain_launch_fill(cudaStream_t st, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, int n_prob, const chn::Par &par, int32_t *f, int32_t *p,
+                       int32_t *t);
+void chain_launch_bt(cudaStream_t st, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, int n_prob, const chn::Par &par, const int32_t *f,
+                     const int32_t *p, int32_t *t, int32_t *v, void *z, void *stack, uint64_t *u, uint64_t *b, int32_t *n_u, int32_t *n_b, int resort);
+
+} // namespace cuda
+} // namespace mpb

@@ -1,0 +1,114 @@
+// chain_kernels.cu -- minimap2-style anchor chaining on the GPU (replaces reference chain.c:160 mp_chain).
+//
+//   chain_fill_kernel  one warp per chaining problem.  Anchors are visited in order (the recurrence is sequential
+//                      in i), the predecessor scan j = i-1 .. st runs 32 candidates at a time: every lane scores
+//                      one candidate (chain.c:112 comput_sc is pure), a warp prefix-max finds the records, two
+//                      ballots + chain_core.cuh::resolve_chunk() reproduce the order-dependent max_skip logic,
+//                      t[] marks go through memory exactly as in the reference.  Latency / integer bound; the
+//                      byte volume is tiny (20 B of scratch per anchor, chain.c:175-178).
+//   chain_bt_kernel    one thread per problem: backtrack with the reference's unstable sort order, compaction,
+//                      optional re-sort of the kept anchors (the pre-chain of map.c:186-192).
+#include <cuda_runtime.h>
+#include "chain_core.cuh"
+#include "chain_dev.hpp"
+
+namespace mpb {
+namespace cuda {
+
+using namespace chn;
+
+constexpr int CHAIN_WARPS = 4;
+
+__global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_fill_kernel(const int64_t *a_off, const int32_t *cnt, const uint64_t *a_all, int n_prob, Par par,
+                                                                     int32_t *f_all, int32_t *p_all, int32_t *t_all)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int prob = blockIdx.x * CHAIN_WARPS + warp;
+	if (prob >= n_prob) return;
+	const int64_t base = a_off[prob];
+	const int32_t n = cnt ? cnt[prob] : (int32_t)(a_off[prob + 1] - base);
+	const uint64_t *a = a_all + base;
+	int32_t *f = f_all + base, *p = p_all + base, *t = t_all + base;
+	for (int32_t i = lane; i < n; i += 32) __stcg(t + i, 0);
+	__syncwarp();
+	int32_t st = 0, hi = -1, hf = 0;
+	for (int32_t i = 0; i < n; ++i) {
+		const uint64_t ai = a[i];
+		const int64_t xi = (int64_t)(ai >> 32);
+		while (st < i && ((xi - (int64_t)(a[st] >> 32)) << par.bbit) > par.max_dist_x) ++st;
+		int32_t max_f = par.kmer, max_j = -1, n_skip = 0;
+		if (hi >= 0 && hi >= st) { // chain.c:185-189: rescue through the best anchor so far
+			const int32_t sc = hf + pair_score(par, ai, a[hi]);
+			if (sc > max_f) max_f = sc, max_j = hi;
+		} else hf = 0, hi = -1;
+		if (i - st > par.max_iter) st = i - par.max_iter;
+		for (int32_t jb = i - 1; jb >= st; jb -= 32) {
+			const int32_t j = jb - lane;
+			bool ok = j >= st;
+			int32_t sc = INT32_MIN, pj = -1;
+			if (ok) {
+				sc = pair_score(par, ai, a[j]);
+				ok = sc != INT32_MIN;
+				if (ok) sc += __ldcg(f + j), pj = __ldcg(p + j);
+			}
+			if (ok && pj >= 0) __stcg(t + pj, i);
+			__syncwarp();
+			const bool marked = ok && __ldcg(t + j) == i;
+			// running maximum in scan order (lane 0 first)
+			int32_t pm = ok ? sc : INT32_MIN;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int32_t o = __shfl_up_sync(0xffffffffu, pm, d);
+				if (lane >= d) pm = pm > o ? pm : o;
+			}
+			int32_t before = __shfl_up_sync(0xffffffffu, pm, 1);
+			if (lane == 0) before = INT32_MIN;
+			before = before > max_f ? before : max_f;
+			const bool rec = ok && sc > before;
+			const uint32_t R = __ballot_sync(0xffffffffu, rec), S = __ballot_sync(0xffffffffu, ok && !rec && marked);
+			const int brk = resolve_chunk(R, S, par.max_skip, n_skip);
+			const uint32_t Rb = brk >= 32 ? R : (R & ((1u << brk) - 1u));
+			if (Rb) {
+				const int top = 31 - __clz(Rb);
+				max_f = __shfl_sync(0xffffffffu, sc, top), max_j = jb - top;
+			}
+			if (brk < 32) break;
+		}
+		if (lane == 0) __stcg(f + i, max_f), __stcg(p + i, max_j);
+		__syncwarp();
+		if (hf < max_f) hf = max_f, hi = i;
+	}
+}
+
+__global__ void __launch_bounds__(32) chain_bt_kernel(const int64_t *a_off, const int32_t *cnt, const uint64_t *a_all, int n_prob, Par par, const int32_t *f_all,
+                                                     const int32_t *p_all, int32_t *t_all, int32_t *v_all, End *z_all, FlagRange<End> *stack_all,
+                                                     uint64_t *u_all, uint64_t *b_all, int32_t *n_u_out, int32_t *n_b_out, int resort)
+{
+	const int prob = blockIdx.x * blockDim.x + threadIdx.x;
+	if (prob >= n_prob) return;
+	const int64_t base = a_off[prob];
+	const int32_t n = cnt ? cnt[prob] : (int32_t)(a_off[prob + 1] - base);
+	int32_t n_b = 0, n_u = 0;
+	if (n > 0) {
+		n_u = backtrack_compact(par, n, a_all + base, f_all + base, p_all + base, t_all + base, v_all + base, z_all + base,
+		                        stack_all + (int64_t)prob * CHAIN_STACK, u_all + base, b_all + base, &n_b);
+		if (resort && n_b > 1) // map.c:191: the anchors kept by the pre-chain go back into plain sorted order
+			flag_sort_by(b_all + base, b_all + base + n_b, [](const uint64_t &x) { return x; }, (FlagRange<uint64_t>*)(stack_all + (int64_t)prob * CHAIN_STACK));
+	}
+	n_u_out[prob] = n_u, n_b_out[prob] = n_b;
+}
+
+void chain_launch_fill(cudaStream_t st, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, int n_prob, const Par &par, int32_t *f, int32_t *p, int32_t *t)
+{
+	if (n_prob > 0) chain_fill_kernel<<<(n_prob + CHAIN_WARPS - 1) / CHAIN_WARPS, CHAIN_WARPS * 32, 0, st>>>(a_off, cnt, a, n_prob, par, f, p, t);
+}
+
+void chain_launch_bt(cudaStream_t st, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, int n_prob, const Par &par, const int32_t *f, const int32_t *p,
+                     int32_t *t, int32_t *v, void *z, void *stack, uint64_t *u, uint64_t *b, int32_t *n_u, int32_t *n_b, int resort)
+{
+	if (n_prob > 0)
+		chain_bt_kernel<<<(n_prob + 31) / 32, 32, 0, st>>>(a_off, cnt, a, n_prob, par, f, p, t, v, (End*)z, (FlagRange<End>*)stack, u, b, n_u, n_b, resort);
+}
+
+} // namespace cuda
+} // namespace mpb

@@ -1,0 +1,452 @@
+// nasw_core.cuh -- per-lane logic of the nasw DP kernels, written once as host+device code.
+//
+// The kernels (nasw_kernels.cu) run an anti-diagonal wavefront: lane l of a warp owns C consecutive
+// protein columns [l*C, l*C+C) and at step t works on nucleotide row i = t - l + 2, so every value it needs
+// from the column to its left was produced by lane l-1 one step earlier and arrives through one warp
+// shuffle.  Everything a lane does inside one step lives in the functions below; the kernel adds only the
+// shuffles and the loop.  tests/hostcheck/emu_nasw.cpp compiles this same header for the CPU and steps
+// 32 lanes in lockstep, which lets the CPU test-suite check the exact device arithmetic against the
+// oracle without a GPU (test infrastructure only; the product never runs it).
+//
+// Semantics restated from the reference (nasw-sse.c:340-551):
+//  * int16 saturating arithmetic: all values live in [-32768, 32767]; x - y is max(x - y, -32768).  The upper
+//    bound is never reached (documented precondition nasw.h:111), the floor is reproduced exactly.
+//  * the row is padded to W8 = 8*ceil(al/8) columns whose profile is -32768; they never feed real columns
+//    but do take part in the extension row maximum.
+//  * score-only mode needs only the true insertion chain It(j) = sat(max(sat(H(j-1)-go), It(j-1)) - ge).
+//  * traceback mode additionally tracks the reference's FIRST-PASS values: the striped SSE kernel restarts the
+//    insertion chain at every segment start (column % slen == 0) and its lazy-F loop then raises H and sets
+//    bit 9; the state nibble and bit 4 of the traceback word come from the first pass.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define NSW_HD __host__ __device__ __forceinline__
+#else
+#define NSW_HD inline
+#endif
+
+namespace nsw {
+
+constexpr int NEG = -32768;
+
+NSW_HD int imax(int a, int b) { return a > b ? a : b; }
+NSW_HD int subs(int x, int y) { return imax(x - y, NEG); }           // _mm_subs_epi16 (floor only)
+NSW_HD int adds(int x, int y) { return imax(x + y, NEG); }           // _mm_adds_epi16 (floor only)
+
+// row word: everything row i contributes, produced by the prep kernel (nasw-sse.c:91-210)
+//   bits 0..7  nas[i]   amino acid (0..21) of the codon ending at i
+//   bits 8..15 donor[i] (int8)     bits 16..23 acceptor[i] (int8)
+NSW_HD uint32_t row_pack(int nas, int don, int acc) { return (uint32_t)(nas & 0xff) | (uint32_t)(don & 0xff) << 8 | (uint32_t)(acc & 0xff) << 16; }
+NSW_HD int row_nas(uint32_t w) { return (int)(w & 0xff); }
+NSW_HD int row_don(uint32_t w) { return (int)(int8_t)(w >> 8 & 0xff); }
+NSW_HD int row_acc(uint32_t w) { return (int)(int8_t)(w >> 16 & 0xff); }
+
+struct Par {          // scalar parameters of one problem
+	int go, ge, io, fs;
+	int gei_stop;     // ge used on rows whose codon is a stop: fs (nasw-sse.c:263)
+};
+
+struct RowConst {     // per-row constants of the recurrences (nasw-sse.c:260-271)
+	int nas, gei, dim1, di, dip1, ai, aim1, aim2;
+};
+
+// rows i-2, i-1, i, i+1 -> constants of row i
+NSW_HD RowConst row_const(const Par &p, uint32_t w_m2, uint32_t w_m1, uint32_t w_0, uint32_t w_p1)
+{
+	RowConst r;
+	r.nas = row_nas(w_0);
+	r.gei = r.nas == 20 ? p.fs : p.ge;
+	r.dim1 = row_don(w_m1), r.di = row_don(w_0), r.dip1 = row_don(w_p1);
+	r.ai = row_acc(w_0), r.aim1 = row_acc(w_m1), r.aim2 = row_acc(w_m2);
+	return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// score-only cell (extension mode), nasw-sse.c:355-404 + closed-form lazy-F.
+//   in : h1,h2,h3 = H(i-1..i-3, j); d3 = D(i-3,j); a,b,c = running intron states of column j;
+//        l0 = H(i,j-1) (final), l1,l2,l3 = H(i-1..i-3, j-1); it = It(i,j-1); s = profile(nas_i, j)
+//   out: returns H(i,j); updates d_new, a, b, c, it (-> It(i,j))
+// ------------------------------------------------------------------------------------------------
+NSW_HD int cell_score(const Par &p, const RowConst &r, int s, int h1, int h2, int h3, int d3, int &d_new, int &a, int &b, int &c,
+                      int l0, int l1, int l2, int l3, int &it)
+{
+	int h = adds(l3, s);
+	it = subs(imax(subs(l0, p.go), it), p.ge);
+	h = imax(h, it);
+	d_new = subs(imax(subs(h3, p.go), d3), r.gei);
+	h = imax(h, d_new);
+	int u = subs(h1, p.io);
+	a = imax(subs(u, r.dim1), a);
+	h = imax(h, subs(a, r.ai));
+	u = subs(l1, p.io);
+	b = imax(subs(u, r.di), b);
+	h = imax(h, subs(b, r.aim2));
+	c = imax(subs(u, r.dip1), c);
+	h = imax(h, subs(c, r.aim1));
+	h = imax(h, subs(h1, p.fs));
+	h = imax(h, subs(h2, p.fs));
+	h = imax(h, subs(l1, p.fs));
+	h = imax(h, subs(l2, p.fs));
+	return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// traceback cell, nasw-sse.c:448-520 + lazy-F (:521-537) in closed form.
+//   extra in : f0 = first-pass H(i,j-1) and iseg = first-pass insertion chain at j-1 (both -32768 when
+//              column j starts a stripe segment), it = true insertion chain
+//   out      : hfirst (first-pass H(i,j)), returns final H(i,j), tb word (10 bits)
+// ------------------------------------------------------------------------------------------------
+NSW_HD int cell_trace(const Par &p, const RowConst &r, int s, int h1, int h2, int h3, int d3, int &d_new, int &a, int &b, int &c,
+                      int l0, int f0, int l1, int l2, int l3, int &iseg, int &it, int &hfirst, uint32_t &word)
+{
+	uint32_t y = 0, z = 0;
+	int h = adds(l3, s), t, u, v;
+	t = subs(f0, p.go);
+	if (iseg > t) z |= 1u << 4;
+	iseg = subs(imax(t, iseg), p.ge);
+	if (iseg > h) y = 1;
+	h = imax(h, iseg);
+	u = subs(h3, p.go), v = d3;
+	if (v > u) z |= 1u << 5;
+	t = subs(imax(u, v), r.gei);
+	d_new = t;
+	if (t > h) y = 2;
+	h = imax(h, t);
+	u = subs(h1, p.io), v = a;
+	t = subs(u, r.dim1);
+	if (v > t) z |= 1u << 6;
+	a = imax(t, v);
+	t = subs(a, r.ai);
+	if (t > h) y = 3;
+	h = imax(h, t);
+	u = subs(l1, p.io), v = b;
+	t = subs(u, r.di);
+	if (v > t) z |= 1u << 7;
+	b = imax(t, v);
+	t = subs(b, r.aim2);
+	if (t > h) y = 4;
+	h = imax(h, t);
+	v = c;
+	t = subs(u, r.dip1);
+	if (v > t) z |= 1u << 8;
+	c = imax(t, v);
+	t = subs(c, r.aim1);
+	if (t > h) y = 5;
+	h = imax(h, t);
+	t = subs(h1, p.fs); if (t > h) y = 6; h = imax(h, t);
+	t = subs(h2, p.fs); if (t > h) y = 7; h = imax(h, t);
+	t = subs(l1, p.fs); if (t > h) y = 8; h = imax(h, t);
+	t = subs(l2, p.fs); if (t > h) y = 9; h = imax(h, t);
+	hfirst = h;
+	it = subs(imax(subs(l0, p.go), it), p.ge);
+	if (it > h) z |= 1u << 9, h = it;
+	word = z | y;
+	return h;
+}
+
+// nasw-sse.c:330-338 evaluated exactly like the x86-64 build does: every FP32 operation rounded on its own
+// (no FMA contraction), then ie_coef*log2 + .5 truncated (nasw-sse.c:426)
+NSW_HD int ext_len_penalty(float ie_coef, int x)
+{
+	if (x < 2) return 0;
+	union { float f; uint32_t i; } z;
+	z.f = (float)x;
+	float lg = (float)((int)((z.i >> 23) & 255) - 128);
+	z.i &= ~(255u << 23);
+	z.i += 127u << 23;
+#ifdef __CUDA_ARCH__
+	float q = __fadd_rn(__fmul_rn(-0.34484843f, z.f), 2.02466578f);
+	q = __fsub_rn(__fmul_rn(q, z.f), 0.67487759f);
+	lg = __fadd_rn(lg, q);
+	return (int)__fadd_rn(__fmul_rn(ie_coef, lg), .5f);
+#else
+	volatile float q = -0.34484843f * z.f;
+	q = q + 2.02466578f;
+	q = q * z.f;
+	q = q - 0.67487759f;
+	volatile float r = lg + q;
+	volatile float m = ie_coef * r;
+	return (int)(m + .5f);
+#endif
+}
+
+// extension bookkeeping of one problem (nasw-sse.c:423-433): fed one finished row at a time
+struct ExtTracker {
+	int max_sc, max_log, max_i, max_code;
+	bool stopped;
+	NSW_HD void init() { max_sc = INT32_MIN, max_log = INT32_MIN, max_i = -1, max_code = 0, stopped = false; }
+	// best = max over columns of (H_adjusted << 12 | (4095 - column)), padding columns carry code 0
+	NSW_HD void row(int i, int best, int pen_base /* 3*al */, float ie_coef, int xdrop)
+	{
+		if (stopped) return;
+		const int tsc = best >> 12, tlog = tsc - ext_len_penalty(ie_coef, i - pen_base);
+		if (tlog > max_log) max_sc = tsc, max_log = tlog, max_i = i, max_code = best & 4095;
+		if (max_log - tlog > xdrop) stopped = true;
+	}
+};
+
+// ------------------------------------------------------------------------------------------------
+// One lane of the wavefront.  The kernels keep one of these per thread (all arrays live in registers) and
+// call step() once per wavefront step after fetching the left lane's outputs with warp shuffles.
+//   Env must provide:  uint32_t row_word(int i)            row word i (clamped to [0,nl])
+//                      const int *profile(int nas)          profile row of amino acid `nas` for THIS lane's columns
+//                      carry load/store for multi-pass problems (see kernels)
+// ------------------------------------------------------------------------------------------------
+struct LaneGeom {            // where this lane sits in the problem
+	int lane, pass, n_pass, nl, al, W8, col0;
+	bool live;               // owns real or padding columns (col0 < W8)
+};
+
+template <int C>
+struct ExtLane {
+	int H1[C], H2[C], H3[C], D1[C], D2[C], D3[C], A[C], B[C], Cc[C];
+	int code[C], bonus[C];
+	int L1, L2, L3;
+	int outH, outI, outB;    // what the lane to the right receives next step
+	uint32_t w_m1, w_0, w_p1, w_pre;
+
+	template <class Env>
+	NSW_HD void init(const LaneGeom &g, int end_bonus, const Env &env)
+	{
+		for (int k = 0; k < C; ++k) {
+			const int jg = g.col0 + k;
+			H1[k] = H2[k] = H3[k] = D1[k] = D2[k] = D3[k] = A[k] = B[k] = Cc[k] = NEG;
+			code[k] = jg < g.al ? 4095 - jg : 0;
+			bonus[k] = jg == g.al - 1 ? end_bonus : 0;
+		}
+		L1 = L2 = L3 = NEG;
+		outH = outI = NEG, outB = INT32_MIN;
+		const int i_first = 2 - g.lane;
+		w_m1 = env.row_word(i_first - 2), w_0 = env.row_word(i_first - 1), w_p1 = env.row_word(i_first), w_pre = env.row_word(i_first + 1);
+	}
+
+	// rH/rI/rB: outputs of the left lane from the previous step (ignored by lane 0 of pass 0)
+	// returns true when this lane finished a row whose best value is complete (lane 31): *row_best
+	template <class Env>
+	NSW_HD bool step(const LaneGeom &g, const Par &par, int t, int rH, int rI, int rB, Env &env, int *row_i, int *row_best)
+	{
+		const int i = t - g.lane + 2;
+		const uint32_t w_m2 = w_m1;
+		w_m1 = w_0, w_0 = w_p1, w_p1 = w_pre;
+		w_pre = env.row_word(i + 2);
+		const bool row_ok = i >= 2 && i < g.nl;
+		if (g.lane == 0) {
+			if (g.pass == 0) { // boundary column -1 (nasw-sse.c:253-271)
+				rH = NEG, rI = NEG, rB = INT32_MIN;
+				L3 = i == 2 ? 0 : NEG, L2 = L1 = i == 2 ? -par.fs : NEG;
+			} else if (row_ok) env.carry_load3(i, rH, rI, rB);
+		}
+		if (!row_ok) return false;
+		if (g.live) {
+			const RowConst rc = row_const(par, w_m2, w_m1, w_0, w_p1);
+			const int *ps = env.profile(rc.nas);
+			int l0 = rH, l1 = L1, l2 = L2, l3 = L3, it = rI, best = rB;
+			int hn[C], dn[C];
+#pragma unroll
+			for (int k = 0; k < C; ++k) {
+				hn[k] = cell_score(par, rc, ps[k], H1[k], H2[k], H3[k], D3[k], dn[k], A[k], B[k], Cc[k], l0, l1, l2, l3, it);
+				best = imax(best, (hn[k] + bonus[k]) * 4096 + code[k]);
+				l0 = hn[k], l1 = H1[k], l2 = H2[k], l3 = H3[k];
+			}
+#pragma unroll
+			for (int k = 0; k < C; ++k) H3[k] = H2[k], H2[k] = H1[k], H1[k] = hn[k], D3[k] = D2[k], D2[k] = D1[k], D1[k] = dn[k];
+			outH = hn[C - 1], outI = it, outB = best;
+		} else outB = rB;
+		if (g.lane != 0 || g.pass > 0) L3 = L2, L2 = L1, L1 = rH;
+		if (g.lane == 31) {
+			if (g.pass == g.n_pass - 1) { *row_i = i, *row_best = outB; return true; }
+			env.carry_store3(i, outH, outI, outB);
+		}
+		return false;
+	}
+};
+
+template <int C>
+struct TbLane {
+	int H1[C], H2[C], H3[C], D1[C], D2[C], D3[C], A[C], B[C], Cc[C];
+	int L1, L2, L3;
+	int outH, outF, outS, outI;
+	uint32_t w_m1, w_0, w_p1, w_pre;
+	uint32_t seg_start;      // bit k: column col0+k starts a stripe segment of the reference layout
+	int k_end;               // which of my columns is al-1 (or -1)
+	int score;               // H(nl-1, al-1) once seen
+
+	template <class Env>
+	NSW_HD void init(const LaneGeom &g, const Env &env)
+	{
+		const int slen = g.W8 / 8;
+		seg_start = 0, k_end = -1, score = NEG;
+		for (int k = 0; k < C; ++k) {
+			H1[k] = H2[k] = H3[k] = D1[k] = D2[k] = D3[k] = A[k] = B[k] = Cc[k] = NEG;
+			if (slen > 0 && (g.col0 + k) % slen == 0) seg_start |= 1u << k;
+			if (g.col0 + k == g.al - 1) k_end = k;
+		}
+		L1 = L2 = L3 = NEG;
+		outH = outF = outS = outI = NEG;
+		const int i_first = 2 - g.lane;
+		w_m1 = env.row_word(i_first - 2), w_0 = env.row_word(i_first - 1), w_p1 = env.row_word(i_first), w_pre = env.row_word(i_first + 1);
+	}
+
+	// wd[] receives the C traceback words when the function returns true
+	template <class Env>
+	NSW_HD bool step(const LaneGeom &g, const Par &par, int t, int rH, int rF, int rS, int rI, Env &env, uint32_t *wd)
+	{
+		const int i = t - g.lane + 2;
+		const uint32_t w_m2 = w_m1;
+		w_m1 = w_0, w_0 = w_p1, w_p1 = w_pre;
+		w_pre = env.row_word(i + 2);
+		const bool row_ok = i >= 2 && i < g.nl;
+		if (g.lane == 0) {
+			if (g.pass == 0) {
+				rH = rF = rS = rI = NEG;
+				L3 = i == 2 ? 0 : NEG, L2 = L1 = i == 2 ? -par.fs : NEG;
+			} else if (row_ok) env.carry_load4(i, rH, rF, rS, rI);
+		}
+		if (!row_ok) return false;
+		bool wrote = false;
+		if (g.live) {
+			const RowConst rc = row_const(par, w_m2, w_m1, w_0, w_p1);
+			const int *ps = env.profile(rc.nas);
+			int l0 = rH, f0 = rF, l1 = L1, l2 = L2, l3 = L3, iseg = rS, it = rI;
+			int hn[C], dn[C];
+#pragma unroll
+			for (int k = 0; k < C; ++k) {
+				if (seg_start >> k & 1) f0 = NEG, iseg = NEG;
+				int hf;
+				hn[k] = cell_trace(par, rc, ps[k], H1[k], H2[k], H3[k], D3[k], dn[k], A[k], B[k], Cc[k], l0, f0, l1, l2, l3, iseg, it, hf, wd[k]);
+				l0 = hn[k], f0 = hf, l1 = H1[k], l2 = H2[k], l3 = H3[k];
+			}
+			if (i == g.nl - 1 && k_end >= 0) {
+#pragma unroll
+				for (int k = 0; k < C; ++k) if (k == k_end) score = hn[k];
+			}
+#pragma unroll
+			for (int k = 0; k < C; ++k) H3[k] = H2[k], H2[k] = H1[k], H1[k] = hn[k], D3[k] = D2[k], D2[k] = D1[k], D1[k] = dn[k];
+			outH = hn[C - 1], outF = f0, outS = iseg, outI = it;
+			wrote = true;
+		}
+		if (g.lane != 0 || g.pass > 0) L3 = L2, L2 = L1, L1 = rH;
+		if (g.lane == 31 && g.pass < g.n_pass - 1) env.carry_store4(i, outH, outF, outS, outI);
+		return wrote;
+	}
+};
+
+// ------------------------------------------------------------------------------------------------
+// sequence preparation (nasw-sse.c:91-210) for one row, from a code accessor c(k) (k in [0,nl), values 0..4).
+// FORWARD orientation is used for global alignment and right extension; the LEFT variant sees the slice
+// already reversed (c(k) = original[nl-1-k], not complemented) and applies the mirrored rules.
+// ------------------------------------------------------------------------------------------------
+template <class Code>
+NSW_HD uint32_t prep_row_forward(const Code &c, int nl, int i, const int *sp /*[6]*/, const uint8_t *codon_tab, int aa_x)
+{
+	int don = sp[3], acc = sp[3], nas = aa_x;
+	if (i < nl) {
+		if (i < nl - 3) { // donor[i]
+			int t = 3;
+			const int c0 = c(i), c1 = c(i + 1), c2 = c(i + 2);
+			if (c1 == 2 && c2 == 3) { const int c3 = c(i + 3); t = (c3 == 0 || c3 == 2) ? (c0 == 2 ? -1 : 4) : 0; } // i+3 < nl holds here
+			else if (c1 == 2 && c2 == 1 && c0 == 2) t = 1;
+			else if (c1 == 0 && c2 == 3) t = 2;
+			don = (int)(int8_t)(t < 0 ? 0 : sp[t]);
+		} else don = (int)(int8_t)sp[3];
+		if (i >= 1) { // acceptor[i]
+			int t = 3, pen = 0;
+			const int cm1 = c(i - 1), c0 = c(i);
+			if (cm1 == 0 && c0 == 2) {
+				t = (i >= 2 && (c(i - 2) == 1 || c(i - 2) == 3)) ? -1 : 0;
+				for (int j = i - 4; j >= 0 && j > i - 7; --j) { const int x = c(j); if (x != 1 && x != 3) pen += sp[5]; }
+			} else if (cm1 == 0 && c0 == 1) t = 2;
+			acc = (int)(int8_t)(t < 0 ? 0 : sp[t]);
+			if (t == -1 || t == 0) acc = (int)(int8_t)(acc + pen);
+		} else acc = (int)(int8_t)sp[3];
+		if (i >= 2) {
+			const int a = c(i - 2), b = c(i - 1), d = c(i);
+			if (a < 4 && b < 4 && d < 4) nas = codon_tab[a << 4 | b << 2 | d];
+		}
+	} else don = (int)(int8_t)sp[3], acc = (int)(int8_t)sp[3];
+	return row_pack(nas, don, acc);
+}
+
+template <class Code>
+NSW_HD uint32_t prep_row_left(const Code &c, int nl, int i, const int *sp, const uint8_t *codon_tab, int aa_x)
+{
+	int don = (int)(int8_t)sp[3], acc = (int)(int8_t)sp[3], nas = aa_x;
+	if (i < nl) {
+		if (i < nl - 3) { // "donor" of the reversed string = mirrored acceptor
+			int t = 3, pen = 0;
+			const int c1 = c(i + 1), c2 = c(i + 2);
+			if (c1 == 2 && c2 == 0) {
+				const int c3 = c(i + 3);
+				t = (c3 == 1 || c3 == 3) ? -1 : 0;
+				for (int j = i + 5; j < nl && j < i + 8; ++j) { const int x = c(j); if (x != 1 && x != 3) pen += sp[5]; }
+			} else if (c1 == 1 && c2 == 0) t = 2;
+			don = (int)(int8_t)(t < 0 ? 0 : sp[t]);
+			if (t == -1 || t == 0) don = (int)(int8_t)(don + pen);
+		}
+		if (i >= 1) { // "acceptor" of the reversed string = mirrored donor
+			int t = 3;
+			const int cm1 = c(i - 1), c0 = c(i);
+			if (cm1 == 3 && c0 == 2) t = (i >= 2 && (c(i - 2) == 0 || c(i - 2) == 2)) ? ((i + 1 < nl && c(i + 1) == 2) ? -1 : 4) : 0;
+			else if (cm1 == 1 && c0 == 2 && i + 1 < nl && c(i + 1) == 1) t = 1;
+			else if (cm1 == 3 && c0 == 0) t = 2;
+			acc = (int)(int8_t)(t < 0 ? 0 : sp[t]);
+		}
+		if (i >= 2) { // codon read in the original direction: original (p-2,p-1,p) = reversed (i, i-1, i-2)
+			const int a = c(i), b = c(i - 1), d = c(i - 2);
+			if (a < 4 && b < 4 && d < 4) nas = codon_tab[a << 4 | b << 2 | d];
+		}
+	}
+	return row_pack(nas, don, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backtrack over the traceback words (nasw-sse.c:40-89).  `tb(i, j)` returns the 10-bit word of cell (i,j).
+// Operations are produced from the alignment end backwards, run-length merged except F and G
+// (nasw.h:141-151), and written into out[0..cap) growing DOWN from out[cap-1], so that on return
+// out[cap-n .. cap) is the CIGAR in forward order.  Returns n.
+// ------------------------------------------------------------------------------------------------
+template <class TbAt>
+NSW_HD int backtrack(const TbAt &tb, int nl, int al, uint32_t *out, int cap)
+{
+	int i = nl - 1, j = al - 1, last = 0, n = 0;
+	auto push = [&](uint32_t op, int len) {
+		if (n == 0 || op != (out[cap - n] & 0xf) || op == 10 || op == 11) { if (n < cap) { ++n; out[cap - n] = (uint32_t)len << 4 | op; } }
+		else out[cap - n] += (uint32_t)len << 4;
+	};
+	while (i >= 2 && j >= 0) {
+		uint32_t x = tb(i, j);
+		if (x >> 9 & 1) x = 1 | (x >> 4 << 4);
+		const int state = last == 0 ? (int)(x & 0xf) : last;
+		const int ext = (state >= 1 && state <= 5) ? (int)(x >> (state + 3) & 1) : 0;
+		switch (state) {
+		case 0: push(0, 1), i -= 3, --j; break;
+		case 1: push(1, 1), --j; break;
+		case 2: push(2, 1), i -= 3; break;
+		case 3: push(3, 1), --i; break;
+		case 4: push(12, 1), --i; if (!ext) --j; break;
+		case 5: push(13, 1), --i; if (!ext) --j; break;
+		case 6: push(10, 1), --i; break;
+		case 7: push(10, 2), i -= 2; break;
+		case 8: push(11, 1), --i, --j; break;
+		case 9: push(11, 2), i -= 2, --j; break;
+		default: i = -1000000; break; // states 10..15 never occur
+		}
+		last = (state >= 1 && state <= 5 && ext) ? state : 0;
+	}
+	if (i > -1000000) {
+		if (j > 0) push(1, j);
+		if (i >= 0) {
+			const int l = (i + 1) / 3 * 3, t = (i + 1) % 3;
+			if (l > 0) push(2, l);
+			if (t != 0) push(10, t);
+		}
+	}
+	for (int k = cap - n; k < cap; ++k) { // nasw-sse.c:30-38: tiny U/V become G
+		const uint32_t op = out[k] & 0xf;
+		if ((op == 12 || op == 13) && out[k] >> 4 < 3) out[k] = out[k] >> 4 << 4 | 11;
+	}
+	return n;
+}
+
+} // namespace nsw

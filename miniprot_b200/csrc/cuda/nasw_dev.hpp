@@ -1,0 +1,52 @@
+// nasw_dev.hpp -- device-side job descriptors of the nasw stage and the launcher prototypes (nasw_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef NS_F_CIGAR
+#define NS_F_CIGAR 0x1
+#define NS_F_EXT_LEFT 0x2
+#define NS_F_EXT_RIGHT 0x4
+#endif
+
+namespace mpb {
+namespace cuda {
+
+constexpr int NASW_WARPS = 4;   // problems per CTA (one warp each)
+constexpr int NASW_CMAX = 8;    // columns per lane in the widest instantiation (32*8 = 256 columns per pass)
+
+struct DpDev {                  // one DP problem, resident in HBM for the duration of a wave
+	int64_t g_start;            // nibble index (packed genome) of DP row 0
+	int32_t dir, comp;          // +1/-1 walk direction; 1 = complement bases (minus strand)
+	int32_t nl, al;
+	int32_t aa_off;             // first residue of the protein slice in the batch residue buffer
+	int32_t flag, io;
+	int32_t C;                  // columns per lane chosen for this problem (1, 2, 4 or 8)
+	int64_t rw_off;             // row words: nl + 1 entries
+	int64_t tb_off;             // traceback words (uint16 units); tb problems only
+	int64_t cig_off;            // CIGAR slot
+	int32_t cig_cap;
+	int32_t pad_;
+	int64_t carry_off;          // per-row carry between column passes (int units)
+};
+
+struct PrepChunk { int32_t job, row0, n_rows, pad_; };
+
+struct NaswConst {              // problem-independent parameters, passed by value (constant bank)
+	int8_t mat[484];            // 22 x 22 substitution matrix
+	uint8_t aa20[256];
+	uint8_t codon[64];
+	int32_t sp[6];
+	int32_t go, ge, fs, xdrop, end_bonus;
+	float ie_coef;
+	int32_t aa_x;               // code of 'X'
+};
+
+void nasw_launch_prep(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, uint32_t *rw);
+void nasw_launch_ext(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const uint32_t *rw, const char *aa, const NaswConst &cst, int4 *out, int *carry);
+void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const uint32_t *rw, const char *aa, const NaswConst &cst, int4 *out, int *carry,
+                    uint16_t *tb);
+void nasw_launch_bt(cudaStream_t st, const DpDev *jobs, const int *order, int n, const uint16_t *tb, uint32_t *cigar, int4 *out);
+
+} // namespace cuda
+} // namespace mpb

@@ -1,0 +1,156 @@
+// nasw_host.cu -- host side of the nasw stage: lays a wave of DP problems out in HBM, launches the kernels
+// of nasw_kernels.cu size class by size class, and brings (score, nt_len, aa_len, CIGAR) back.
+//
+// HBM layout of one wave (all grow-only arenas of the context):
+//   jobs[]    DpDev descriptors                              order[]  job ids grouped by (kind, C), longest first
+//   rw[]      one 32-bit row word per nucleotide row (+1)    carry[]  per-row spill for problems wider than a pass
+//   tb[]      16-bit traceback words, wavefront-major        cigar[]  per-problem CIGAR slots (filled from the end)
+//   out[]     int4 {score, nt_len, aa_len, n_cigar}
+// A wave whose traceback or row-word footprint exceeds the budget is cut into sub-waves.
+#include <algorithm>
+#include <numeric>
+#include "ctx.hpp"
+#include "nasw_core.cuh"
+
+namespace mpb {
+namespace cuda {
+
+static const size_t kTbBudget = (size_t)24 << 30;   // bytes of traceback words per sub-wave
+static const size_t kRwBudget = (size_t)8 << 30;    // bytes of row words per sub-wave
+
+static inline int pick_C(int al)
+{
+	const int W8 = (al + 7) / 8 * 8;
+	return W8 <= 32 ? 1 : W8 <= 64 ? 2 : W8 <= 128 ? 4 : 8;
+}
+
+static void fill_const(const ns_opt_t *o, NaswConst &c)
+{
+	memcpy(c.mat, o->sc, 484);
+	memcpy(c.aa20, ns_tab_aa20, 256);
+	memcpy(c.codon, ns_tab_codon, 64);
+	for (int i = 0; i < 6; ++i) c.sp[i] = o->sp[i];
+	c.go = o->go, c.ge = o->ge, c.fs = o->fs, c.xdrop = o->xdrop, c.end_bonus = o->end_bonus, c.ie_coef = o->ie_coef;
+	c.aa_x = ns_tab_aa20[(uint8_t)'X'];
+}
+
+// run jobs[lo, hi) as one sub-wave
+static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const NaswConst &cst, std::vector<DpDev> &jobs, size_t lo, size_t hi, DpSet &out)
+{
+	const int n = (int)(hi - lo);
+	if (n == 0) return;
+	cudaStream_t st = ctx->stream;
+	int64_t rw_tot = 0, tb_tot = 0, cig_tot = 0, carry_tot = 0;
+	std::vector<PrepChunk> chunks;
+	std::vector<int> order[2][4]; // [is_tb][log2 C]
+	for (int k = 0; k < n; ++k) {
+		DpDev &j = jobs[lo + k];
+		const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
+		j.C = pick_C(j.al);
+		const int Wp = 32 * j.C, W8 = (j.al + 7) / 8 * 8, n_pass = (W8 + Wp - 1) / Wp, T = j.nl > 2 ? j.nl - 2 + 32 : 0;
+		j.rw_off = rw_tot, rw_tot += (j.nl + 1 + 3) / 4 * 4;
+		j.tb_off = j.cig_off = 0, j.cig_cap = 0, j.carry_off = 0;
+		if (is_tb) {
+			j.tb_off = tb_tot, tb_tot += (int64_t)n_pass * T * Wp;
+			j.cig_cap = j.nl + j.al + 4;
+			j.cig_off = cig_tot, cig_tot += j.cig_cap;
+		}
+		if (n_pass > 1) j.carry_off = carry_tot, carry_tot += ((int64_t)j.nl + 1) * 4;
+		for (int r = 0; r <= j.nl; r += 4096) chunks.push_back(PrepChunk{ k, r, std::min(4096, j.nl + 1 - r), 0 });
+		order[is_tb][j.C == 1 ? 0 : j.C == 2 ? 1 : j.C == 4 ? 2 : 3].push_back(k);
+		(is_tb ? ctx->stats.dp_cells_tb : ctx->stats.dp_cells_ext) += (int64_t)j.nl * j.al;
+		(is_tb ? ctx->stats.n_dp_tb : ctx->stats.n_dp_ext) += 1;
+	}
+	std::vector<int> flat;
+	size_t first[2][4], count[2][4];
+	for (int b = 0; b < 2; ++b)
+		for (int c = 0; c < 4; ++c) {
+			std::vector<int> &v = order[b][c];
+			std::stable_sort(v.begin(), v.end(), [&](int x, int y) { return jobs[lo + x].nl > jobs[lo + y].nl; });
+			first[b][c] = flat.size(), count[b][c] = v.size();
+			flat.insert(flat.end(), v.begin(), v.end());
+		}
+	ctx->b_jobs.reserve(sizeof(DpDev) * n);
+	ctx->b_order.reserve(sizeof(int) * (flat.size() + 1));
+	ctx->b_chunks.reserve(sizeof(PrepChunk) * (chunks.size() + 1));
+	ctx->b_rw.reserve(sizeof(uint32_t) * (size_t)(rw_tot + 4));
+	ctx->b_out.reserve(sizeof(int4) * n);
+	ctx->b_carry.reserve(sizeof(int) * (size_t)(carry_tot + 4));
+	ctx->b_tb.reserve(sizeof(uint16_t) * (size_t)(tb_tot + 8));
+	ctx->b_cigar.reserve(sizeof(uint32_t) * (size_t)(cig_tot + 4));
+	ctx->h_out.reserve(sizeof(int4) * n);
+	ctx->h_cigar.reserve(sizeof(uint32_t) * (size_t)(cig_tot + 4));
+	MPB_CUDA_OK(cudaMemcpyAsync(ctx->b_jobs.p, jobs.data() + lo, sizeof(DpDev) * n, cudaMemcpyHostToDevice, st));
+	MPB_CUDA_OK(cudaMemcpyAsync(ctx->b_order.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, st));
+	MPB_CUDA_OK(cudaMemcpyAsync(ctx->b_chunks.p, chunks.data(), sizeof(PrepChunk) * chunks.size(), cudaMemcpyHostToDevice, st));
+	ctx->stats.h2d_bytes += sizeof(DpDev) * n + sizeof(int) * flat.size() + sizeof(PrepChunk) * chunks.size();
+	const DpDev *dj = ctx->b_jobs.as<DpDev>();
+	const int *dord = ctx->b_order.as<int>();
+	nasw_launch_prep(st, dj, ctx->b_chunks.as<PrepChunk>(), (int)chunks.size(), packed, cst, ctx->b_rw.as<uint32_t>());
+	ctx->stats.kernel_launches += 1;
+	static const int Cs[4] = { 1, 2, 4, 8 };
+	ctx->time_begin();
+	for (int c = 3; c >= 0; --c)
+		if (count[0][c]) {
+			nasw_launch_ext(st, Cs[c], dj, dord + first[0][c], (int)count[0][c], ctx->b_rw.as<uint32_t>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>());
+			ctx->stats.kernel_launches += 1;
+		}
+	ctx->stats.ms_dp_ext += ctx->time_end();
+	ctx->time_begin();
+	size_t n_tb = 0;
+	for (int c = 3; c >= 0; --c)
+		if (count[1][c]) {
+			nasw_launch_tb(st, Cs[c], dj, dord + first[1][c], (int)count[1][c], ctx->b_rw.as<uint32_t>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>(),
+			               ctx->b_tb.as<uint16_t>());
+			ctx->stats.kernel_launches += 1;
+			n_tb += count[1][c];
+		}
+	if (n_tb) {
+		nasw_launch_bt(st, dj, dord + first[1][0], (int)n_tb, ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
+		ctx->stats.kernel_launches += 1;
+	}
+	ctx->stats.ms_dp_tb += ctx->time_end();
+	MPB_CUDA_OK(cudaMemcpyAsync(ctx->h_out.p, ctx->b_out.p, sizeof(int4) * n, cudaMemcpyDeviceToHost, st));
+	if (cig_tot) MPB_CUDA_OK(cudaMemcpyAsync(ctx->h_cigar.p, ctx->b_cigar.p, sizeof(uint32_t) * (size_t)cig_tot, cudaMemcpyDeviceToHost, st));
+	MPB_CUDA_OK(cudaStreamSynchronize(st));
+	MPB_CUDA_OK(cudaGetLastError());
+	ctx->stats.d2h_bytes += sizeof(int4) * n + sizeof(uint32_t) * (size_t)cig_tot;
+	const int4 *ho = ctx->h_out.as<int4>();
+	const uint32_t *hc = ctx->h_cigar.as<uint32_t>();
+	for (int k = 0; k < n; ++k) {
+		const DpDev &j = jobs[lo + k];
+		out.score[lo + k] = ho[k].x, out.nt_len[lo + k] = ho[k].y, out.aa_len[lo + k] = ho[k].z;
+		if (j.cig_cap > 0 && ho[k].w > 0) {
+			const uint32_t *c = hc + j.cig_off + j.cig_cap - ho[k].w;
+			out.cig.insert(out.cig.end(), c, c + ho[k].w);
+		}
+		out.cig_off[lo + k + 1] = (int64_t)out.cig.size();
+	}
+}
+
+void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_opt_t *base, std::vector<DpDev> &jobs, DpSet &out)
+{
+	const size_t n = jobs.size();
+	out.score.assign(n, 0), out.nt_len.assign(n, 0), out.aa_len.assign(n, 0);
+	out.cig.clear(), out.cig_off.assign(n + 1, 0);
+	if (n == 0) return;
+	NaswConst cst;
+	fill_const(base, cst);
+	size_t lo = 0;
+	while (lo < n) {
+		size_t hi = lo, tb_bytes = 0, rw_bytes = 0;
+		while (hi < n) {
+			const DpDev &j = jobs[hi];
+			const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
+			const int C = pick_C(j.al), Wp = 32 * C, W8 = (j.al + 7) / 8 * 8, n_pass = (W8 + Wp - 1) / Wp;
+			const size_t tbb = is_tb ? (size_t)n_pass * (size_t)(j.nl + 30) * Wp * 2 : 0, rwb = (size_t)(j.nl + 4) * 4;
+			if (hi > lo && (tb_bytes + tbb > kTbBudget || rw_bytes + rwb > kRwBudget)) break;
+			tb_bytes += tbb, rw_bytes += rwb, ++hi;
+		}
+		run_subwave(ctx, packed, d_aa, cst, jobs, lo, hi, out);
+		lo = hi;
+	}
+}
+
+} // namespace cuda
+} // namespace mpb

@@ -1,0 +1,275 @@
+// nasw_kernels.cu -- sm_100a kernels of the splice/frameshift-aware protein-to-DNA DP ("nasw").
+//
+// Replaces reference nasw-sse.c:340 ns_global_gs16b (striped SSE2, one problem per CPU thread) by:
+//
+//   nasw_prep_kernel   one thread per nucleotide row: unpack the 4-bit genome slice (strand / reversal aware),
+//                      translate the codon ending at the row, evaluate the donor / acceptor rules, and emit one
+//                      32-bit "row word" (nasw-sse.c:91-210).  HBM-bound: 0.5 B/row read, 4 B/row written.
+//   nasw_ext_kernel    score-only extension DP (80 % of all DP cells).  One warp per problem, lane l owns C
+//                      protein columns, anti-diagonal wavefront over nucleotide rows; the left-neighbour
+//                      dependency travels by warp shuffle; the substitution profile sits in shared memory;
+//                      row words are prefetched one step ahead with coalesced loads.  Integer-issue bound.
+//   nasw_tb_kernel     global alignment with traceback: same wavefront, additionally tracks the reference's
+//                      first-pass / lazy-F distinction and streams one 16-bit traceback word per cell to HBM in
+//                      wavefront-major order (fully coalesced 64*C-byte stores per warp step).
+//   nasw_bt_kernel     one thread per problem walks the traceback words and writes the CIGAR.
+//
+// Problems wider than 32*C columns are processed in column passes of 32*C; the last lane spills its per-row
+// outputs to a carry array that lane 0 of the next pass reads back (rows stay in wavefront order).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "nasw_core.cuh"
+#include "nasw_dev.hpp"
+
+namespace mpb {
+namespace cuda {
+
+using namespace nsw;
+
+// nucleotide code of row k of a job: nibble (g_start + dir*k) of the packed genome, complemented on the - strand
+__device__ __forceinline__ int job_code(const uint8_t *packed, const DpDev &j, int k)
+{
+	const int64_t g = j.g_start + (int64_t)j.dir * k;
+	int b = packed[g >> 1] >> ((g & 1) * 4) & 0xf;
+	if (j.comp) b = b < 4 ? 3 - b : b;
+	return b;
+}
+
+// ------------------------------------------------------------------ prep
+__global__ void __launch_bounds__(256) nasw_prep_kernel(const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed,
+                                                        NaswConst cst, uint32_t *rw)
+{
+	const int ck = blockIdx.x;
+	if (ck >= n_chunks) return;
+	const PrepChunk c = chunks[ck];
+	const DpDev job = jobs[c.job];
+	auto code = [&](int k) { return job_code(packed, job, k); };
+	for (int r = c.row0 + (int)threadIdx.x; r < c.row0 + c.n_rows; r += blockDim.x) { // rows 0..nl inclusive
+		uint32_t w;
+		if (job.flag & NS_F_EXT_LEFT) w = prep_row_left(code, job.nl, r, cst.sp, cst.codon, cst.aa_x);
+		else w = prep_row_forward(code, job.nl, r, cst.sp, cst.codon, cst.aa_x);
+		rw[job.rw_off + r] = w;
+	}
+}
+
+// residue code of logical column jg (reversed for left extension)
+__device__ __forceinline__ int col_residue(const char *aa, const NaswConst &cst, const DpDev &j, int jg)
+{
+	const int p = (j.flag & NS_F_EXT_LEFT) ? j.al - 1 - jg : jg;
+	return cst.aa20[(uint8_t)aa[j.aa_off + p]];
+}
+
+__device__ __forceinline__ void build_profile(int *prof, int Wp, int pass, const char *aa, const NaswConst &cst, const DpDev &job, int lane)
+{
+	for (int j = lane; j < Wp; j += 32) {
+		const int jg = pass * Wp + j;
+		if (jg < job.al) {
+			const int r = col_residue(aa, cst, job, jg);
+			for (int a = 0; a < 22; ++a) prof[a * Wp + j] = cst.mat[a * 22 + r];
+		} else {
+			for (int a = 0; a < 22; ++a) prof[a * Wp + j] = NEG;
+		}
+	}
+	__syncwarp();
+}
+
+// what a lane needs from its surroundings (see nasw_core.cuh ExtLane/TbLane)
+struct DevEnv {
+	const uint32_t *rw;  // row words of this problem
+	int nl;
+	const int *prof;     // profile of this warp for this pass, already offset to the lane's first column
+	int Wp;
+	int *cy;             // per-row carry between column passes
+	__device__ __forceinline__ uint32_t row_word(int i) const { i = i < 0 ? 0 : (i > nl ? nl : i); return __ldg(rw + i); }
+	__device__ __forceinline__ const int *profile(int nas) const { return prof + nas * Wp; }
+	__device__ __forceinline__ void carry_load3(int i, int &a, int &b, int &c) const { a = cy[(int64_t)i * 3], b = cy[(int64_t)i * 3 + 1], c = cy[(int64_t)i * 3 + 2]; }
+	__device__ __forceinline__ void carry_store3(int i, int a, int b, int c) const { cy[(int64_t)i * 3] = a, cy[(int64_t)i * 3 + 1] = b, cy[(int64_t)i * 3 + 2] = c; }
+	__device__ __forceinline__ void carry_load4(int i, int &a, int &b, int &c, int &d) const
+	{
+		const int4 v = *reinterpret_cast<const int4*>(cy + (int64_t)i * 4);
+		a = v.x, b = v.y, c = v.z, d = v.w;
+	}
+	__device__ __forceinline__ void carry_store4(int i, int a, int b, int c, int d) const { *reinterpret_cast<int4*>(cy + (int64_t)i * 4) = make_int4(a, b, c, d); }
+};
+
+// ------------------------------------------------------------------ extension (score only)
+template <int C>
+__global__ void __launch_bounds__(NASW_WARPS * 32) nasw_ext_kernel(const DpDev *jobs, const int *order, int n_jobs, const uint32_t *rw, const char *aa,
+                                                                  NaswConst cst, int4 *out, int *carry)
+{
+	extern __shared__ int smem[];
+	constexpr int Wp = 32 * C;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int slot = blockIdx.x * NASW_WARPS + warp;
+	if (slot >= n_jobs) return;
+	const int jid = order[slot];
+	const DpDev job = jobs[jid];
+	int *prof = smem + warp * 22 * Wp;
+	LaneGeom g;
+	g.lane = lane, g.nl = job.nl, g.al = job.al, g.W8 = (job.al + 7) / 8 * 8;
+	g.n_pass = (g.W8 + Wp - 1) / Wp;
+	const int T = g.nl > 2 ? g.nl - 2 + 32 : 0;
+	Par par;
+	par.go = cst.go, par.ge = cst.ge, par.io = job.io, par.fs = cst.fs, par.gei_stop = cst.fs;
+	ExtTracker trk;
+	trk.init();
+	DevEnv env;
+	env.rw = rw + job.rw_off, env.nl = g.nl, env.prof = prof + lane * C, env.Wp = Wp, env.cy = carry + job.carry_off;
+
+	for (int pass = 0; pass < g.n_pass; ++pass) {
+		build_profile(prof, Wp, pass, aa, cst, job, lane);
+		g.pass = pass, g.col0 = pass * Wp + lane * C, g.live = g.col0 < g.W8;
+		ExtLane<C> L;
+		L.init(g, cst.end_bonus, env);
+		for (int t = 0; t < T; ++t) {
+			const int rH = __shfl_up_sync(0xffffffffu, L.outH, 1);
+			const int rI = __shfl_up_sync(0xffffffffu, L.outI, 1);
+			const int rB = __shfl_up_sync(0xffffffffu, L.outB, 1);
+			int row_i, row_best;
+			if (L.step(g, par, t, rH, rI, rB, env, &row_i, &row_best)) trk.row(row_i, row_best, g.al * 3, cst.ie_coef, cst.xdrop);
+			if (pass == g.n_pass - 1 && (t & 15) == 15) {
+				if (__shfl_sync(0xffffffffu, (int)trk.stopped, 31)) break;
+			}
+		}
+		__syncwarp();
+	}
+	if (lane == 31) {
+		int4 r;
+		r.x = trk.max_sc, r.y = trk.max_i + 1;
+		r.z = (trk.max_i >= 0 && trk.max_code != 0) ? 4095 - trk.max_code + 1 : g.al + 1;
+		r.w = 0;
+		out[jid] = r;
+	}
+}
+
+// ------------------------------------------------------------------ global alignment with traceback
+template <int C>
+__global__ void __launch_bounds__(NASW_WARPS * 32) nasw_tb_kernel(const DpDev *jobs, const int *order, int n_jobs, const uint32_t *rw, const char *aa,
+                                                                 NaswConst cst, int4 *out, int *carry, uint16_t *tb)
+{
+	extern __shared__ int smem[];
+	constexpr int Wp = 32 * C;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int slot = blockIdx.x * NASW_WARPS + warp;
+	if (slot >= n_jobs) return;
+	const int jid = order[slot];
+	const DpDev job = jobs[jid];
+	int *prof = smem + warp * 22 * Wp;
+	LaneGeom g;
+	g.lane = lane, g.nl = job.nl, g.al = job.al, g.W8 = (job.al + 7) / 8 * 8;
+	g.n_pass = (g.W8 + Wp - 1) / Wp;
+	const int T = g.nl > 2 ? g.nl - 2 + 32 : 0;
+	Par par;
+	par.go = cst.go, par.ge = cst.ge, par.io = job.io, par.fs = cst.fs, par.gei_stop = cst.fs;
+	DevEnv env;
+	env.rw = rw + job.rw_off, env.nl = g.nl, env.prof = prof + lane * C, env.Wp = Wp, env.cy = carry + job.carry_off;
+	int score = NEG;
+
+	for (int pass = 0; pass < g.n_pass; ++pass) {
+		build_profile(prof, Wp, pass, aa, cst, job, lane);
+		g.pass = pass, g.col0 = pass * Wp + lane * C, g.live = g.col0 < g.W8;
+		TbLane<C> L;
+		L.init(g, env);
+		uint16_t *tbp = tb + job.tb_off + (int64_t)pass * T * Wp + lane * C;
+		for (int t = 0; t < T; ++t) {
+			const int rH = __shfl_up_sync(0xffffffffu, L.outH, 1);
+			const int rF = __shfl_up_sync(0xffffffffu, L.outF, 1);
+			const int rS = __shfl_up_sync(0xffffffffu, L.outS, 1);
+			const int rI = __shfl_up_sync(0xffffffffu, L.outI, 1);
+			uint32_t wd[C];
+			if (L.step(g, par, t, rH, rF, rS, rI, env, wd)) {
+				// one traceback word per cell, wavefront-major: [pass][t][32*C]
+				uint16_t *dst = tbp + (int64_t)t * Wp;
+				if (C == 1) dst[0] = (uint16_t)wd[0];
+				else if (C == 2) *reinterpret_cast<uint32_t*>(dst) = wd[0] | wd[C > 1 ? 1 : 0] << 16;
+				else {
+#pragma unroll
+					for (int k = 0; k < C; k += 4) {
+						uint2 v;
+						v.x = wd[k] | wd[k + 1 < C ? k + 1 : k] << 16, v.y = wd[k + 2 < C ? k + 2 : k] | wd[k + 3 < C ? k + 3 : k] << 16;
+						*reinterpret_cast<uint2*>(dst + k) = v;
+					}
+				}
+			}
+		}
+		if (L.k_end >= 0) score = L.score;
+		__syncwarp();
+	}
+	// the lane that owns column al-1 (in its pass) holds H(nl-1, al-1)
+	const int owner = g.al > 0 ? ((g.al - 1) % Wp) / C : 0;
+	score = __shfl_sync(0xffffffffu, score, owner);
+	if (lane == 0) out[jid] = make_int4(score, g.nl, g.al, 0);
+}
+
+// ------------------------------------------------------------------ backtrack -> CIGAR
+__global__ void __launch_bounds__(128) nasw_bt_kernel(const DpDev *jobs, const int *order, int n_jobs, const uint16_t *tb, uint32_t *cigar, int4 *out)
+{
+	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot >= n_jobs) return;
+	const int jid = order[slot];
+	const DpDev job = jobs[jid];
+	const int C = job.C, Wp = 32 * C, T = job.nl > 2 ? job.nl - 2 + 32 : 0;
+	const uint16_t *base = tb + job.tb_off;
+	auto at = [&](int i, int j) -> uint32_t {
+		const int pass = j / Wp, jc = j - pass * Wp, lane = jc / C;
+		return base[((int64_t)pass * T + (i - 2 + lane)) * Wp + jc];
+	};
+	const int n = backtrack(at, job.nl, job.al, cigar + job.cig_off, job.cig_cap);
+	out[jid].w = n;
+}
+
+// ------------------------------------------------------------------ launchers
+template <int C>
+static void launch_ext(cudaStream_t st, const DpDev *jobs, const int *order, int n, const uint32_t *rw, const char *aa, const NaswConst &cst, int4 *out, int *carry)
+{
+	const int smem = NASW_WARPS * 22 * 32 * C * (int)sizeof(int);
+	static bool attr_set = false;
+	if (!attr_set) { cudaFuncSetAttribute(nasw_ext_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+	nasw_ext_kernel<C><<<(n + NASW_WARPS - 1) / NASW_WARPS, NASW_WARPS * 32, smem, st>>>(jobs, order, n, rw, aa, cst, out, carry);
+}
+
+template <int C>
+static void launch_tb(cudaStream_t st, const DpDev *jobs, const int *order, int n, const uint32_t *rw, const char *aa, const NaswConst &cst, int4 *out, int *carry,
+                      uint16_t *tb)
+{
+	const int smem = NASW_WARPS * 22 * 32 * C * (int)sizeof(int);
+	static bool attr_set = false;
+	if (!attr_set) { cudaFuncSetAttribute(nasw_tb_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+	nasw_tb_kernel<C><<<(n + NASW_WARPS - 1) / NASW_WARPS, NASW_WARPS * 32, smem, st>>>(jobs, order, n, rw, aa, cst, out, carry, tb);
+}
+
+void nasw_launch_prep(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, uint32_t *rw)
+{
+	if (n_chunks > 0) nasw_prep_kernel<<<n_chunks, 256, 0, st>>>(jobs, chunks, n_chunks, packed, cst, rw);
+}
+
+void nasw_launch_ext(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const uint32_t *rw, const char *aa, const NaswConst &cst, int4 *out, int *carry)
+{
+	if (n <= 0) return;
+	switch (C) {
+	case 1: launch_ext<1>(st, jobs, order, n, rw, aa, cst, out, carry); break;
+	case 2: launch_ext<2>(st, jobs, order, n, rw, aa, cst, out, carry); break;
+	case 4: launch_ext<4>(st, jobs, order, n, rw, aa, cst, out, carry); break;
+	default: launch_ext<8>(st, jobs, order, n, rw, aa, cst, out, carry); break;
+	}
+}
+
+void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const uint32_t *rw, const char *aa, const NaswConst &cst, int4 *out, int *carry,
+                    uint16_t *tb)
+{
+	if (n <= 0) return;
+	switch (C) {
+	case 1: launch_tb<1>(st, jobs, order, n, rw, aa, cst, out, carry, tb); break;
+	case 2: launch_tb<2>(st, jobs, order, n, rw, aa, cst, out, carry, tb); break;
+	case 4: launch_tb<4>(st, jobs, order, n, rw, aa, cst, out, carry, tb); break;
+	default: launch_tb<8>(st, jobs, order, n, rw, aa, cst, out, carry, tb); break;
+	}
+}
+
+void nasw_launch_bt(cudaStream_t st, const DpDev *jobs, const int *order, int n, const uint16_t *tb, uint32_t *cigar, int4 *out)
+{
+	if (n > 0) nasw_bt_kernel<<<(n + 127) / 128, 128, 0, st>>>(jobs, order, n, tb, cigar, out);
+}
+
+} // namespace cuda
+} // namespace mpb

@@ -10,9 +10,9 @@ HOST_SRCS = ["tables.cpp", "ntdb.cpp", "index.cpp", "hits.cpp", "align.cpp", "pa
 
 
 def build(force=False):
-    srcs = [os.path.join(CSRC, s) for s in HOST_SRCS] + [os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")]
+    srcs = [os.path.join(CSRC, s) for s in HOST_SRCS] + [os.path.join(ROOT, "tests", "hostcheck", f) for f in ("hostcheck.cpp", "emu_nasw.cpp", "emu_chain.cpp")]
     ora = sorted(glob.glob(os.path.join(ROOT, "oracle", "*.c")))
-    deps = srcs + ora + glob.glob(os.path.join(CSRC, "*.hpp")) + glob.glob(os.path.join(ROOT, "include", "*.h")) + \
+    deps = srcs + ora + glob.glob(os.path.join(CSRC, "*.hpp")) + glob.glob(os.path.join(CSRC, "cuda", "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h")) + \
         glob.glob(os.path.join(ROOT, "oracle", "*.h"))
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT

@@ -1,0 +1,151 @@
+// tests/hostcheck/emu_nasw.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Lock-step CPU emulation of the nasw wavefront kernels (miniprot_b200/csrc/cuda/nasw_kernels.cu): the per-lane
+// logic is the SAME header the kernels compile (nasw_core.cuh); only the warp shuffles, the shared-memory profile
+// and the carry arrays are replaced by plain arrays here.  Lets the CPU test-suite compare the device arithmetic
+// with the oracle for every column-per-lane variant and for multi-pass problems, without a GPU.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "cuda/nasw_core.cuh"
+
+using namespace nsw;
+
+namespace {
+
+struct EmuEnv {
+	const uint32_t *rw;
+	int nl;
+	const int *prof; // offset to the lane's first column
+	int Wp;
+	int *cy;
+	uint32_t row_word(int i) const { i = i < 0 ? 0 : (i > nl ? nl : i); return rw[i]; }
+	const int *profile(int nas) const { return prof + nas * Wp; }
+	void carry_load3(int i, int &a, int &b, int &c) const { a = cy[(int64_t)i * 3], b = cy[(int64_t)i * 3 + 1], c = cy[(int64_t)i * 3 + 2]; }
+	void carry_store3(int i, int a, int b, int c) const { cy[(int64_t)i * 3] = a, cy[(int64_t)i * 3 + 1] = b, cy[(int64_t)i * 3 + 2] = c; }
+	void carry_load4(int i, int &a, int &b, int &c, int &d) const { a = cy[(int64_t)i * 4], b = cy[(int64_t)i * 4 + 1], c = cy[(int64_t)i * 4 + 2], d = cy[(int64_t)i * 4 + 3]; }
+	void carry_store4(int i, int a, int b, int c, int d) const { cy[(int64_t)i * 4] = a, cy[(int64_t)i * 4 + 1] = b, cy[(int64_t)i * 4 + 2] = c, cy[(int64_t)i * 4 + 3] = d; }
+};
+
+struct Problem {
+	std::vector<uint32_t> rw;
+	std::vector<int> aas;
+	int nl, al, W8;
+	Par par;
+	const int8_t *mat;
+	int end_bonus, xdrop;
+	float ie_coef;
+};
+
+template <int C>
+void run_ext(const Problem &P, int *score, int *nt_len, int *aa_len)
+{
+	const int Wp = 32 * C, n_pass = (P.W8 + Wp - 1) / Wp, T = P.nl > 2 ? P.nl - 2 + 32 : 0;
+	std::vector<int> prof(22 * Wp), cy((size_t)(P.nl + 1) * 3);
+	ExtTracker trk;
+	trk.init();
+	for (int pass = 0; pass < n_pass; ++pass) {
+		for (int j = 0; j < Wp; ++j)
+			for (int a = 0; a < 22; ++a) prof[a * Wp + j] = pass * Wp + j < P.al ? P.mat[a * 22 + P.aas[pass * Wp + j]] : NEG;
+		ExtLane<C> L[32];
+		LaneGeom g[32];
+		EmuEnv env[32];
+		for (int l = 0; l < 32; ++l) {
+			g[l].lane = l, g[l].pass = pass, g[l].n_pass = n_pass, g[l].nl = P.nl, g[l].al = P.al, g[l].W8 = P.W8, g[l].col0 = pass * Wp + l * C, g[l].live = g[l].col0 < P.W8;
+			env[l].rw = P.rw.data(), env[l].nl = P.nl, env[l].prof = prof.data() + l * C, env[l].Wp = Wp, env[l].cy = cy.data();
+			L[l].init(g[l], P.end_bonus, env[l]);
+		}
+		for (int t = 0; t < T; ++t) {
+			int rH[32], rI[32], rB[32];
+			for (int l = 0; l < 32; ++l) { const int s = l ? l - 1 : 0; rH[l] = L[s].outH, rI[l] = L[s].outI, rB[l] = L[s].outB; } // __shfl_up_sync(.., 1)
+			for (int l = 0; l < 32; ++l) {
+				int ri, rb;
+				if (L[l].step(g[l], P.par, t, rH[l], rI[l], rB[l], env[l], &ri, &rb)) trk.row(ri, rb, P.al * 3, P.ie_coef, P.xdrop);
+			}
+			if (pass == n_pass - 1 && (t & 15) == 15 && trk.stopped) break;
+		}
+	}
+	*score = trk.max_sc, *nt_len = trk.max_i + 1;
+	*aa_len = (trk.max_i >= 0 && trk.max_code != 0) ? 4095 - trk.max_code + 1 : P.al + 1;
+}
+
+template <int C>
+void run_tb(const Problem &P, int *score, std::vector<uint32_t> &cigar)
+{
+	const int Wp = 32 * C, n_pass = (P.W8 + Wp - 1) / Wp, T = P.nl > 2 ? P.nl - 2 + 32 : 0;
+	std::vector<int> prof(22 * Wp), cy((size_t)(P.nl + 1) * 4);
+	std::vector<uint16_t> tb((size_t)n_pass * (T ? T : 1) * Wp, 0xffff);
+	int sc = NEG;
+	for (int pass = 0; pass < n_pass; ++pass) {
+		for (int j = 0; j < Wp; ++j)
+			for (int a = 0; a < 22; ++a) prof[a * Wp + j] = pass * Wp + j < P.al ? P.mat[a * 22 + P.aas[pass * Wp + j]] : NEG;
+		TbLane<C> L[32];
+		LaneGeom g[32];
+		EmuEnv env[32];
+		for (int l = 0; l < 32; ++l) {
+			g[l].lane = l, g[l].pass = pass, g[l].n_pass = n_pass, g[l].nl = P.nl, g[l].al = P.al, g[l].W8 = P.W8, g[l].col0 = pass * Wp + l * C, g[l].live = g[l].col0 < P.W8;
+			env[l].rw = P.rw.data(), env[l].nl = P.nl, env[l].prof = prof.data() + l * C, env[l].Wp = Wp, env[l].cy = cy.data();
+			L[l].init(g[l], env[l]);
+		}
+		for (int t = 0; t < T; ++t) {
+			int rH[32], rF[32], rS[32], rI[32];
+			for (int l = 0; l < 32; ++l) { const int s = l ? l - 1 : 0; rH[l] = L[s].outH, rF[l] = L[s].outF, rS[l] = L[s].outS, rI[l] = L[s].outI; }
+			for (int l = 0; l < 32; ++l) {
+				uint32_t wd[C];
+				if (L[l].step(g[l], P.par, t, rH[l], rF[l], rS[l], rI[l], env[l], wd))
+					for (int k = 0; k < C; ++k) tb[((size_t)pass * T + t) * Wp + l * C + k] = (uint16_t)wd[k];
+			}
+		}
+		for (int l = 0; l < 32; ++l) if (L[l].k_end >= 0) sc = L[l].score;
+	}
+	*score = sc;
+	auto at = [&](int i, int j) -> uint32_t {
+		const int pass = j / Wp, jc = j - pass * Wp, lane = jc / C;
+		return tb[((size_t)pass * T + (i - 2 + lane)) * Wp + jc];
+	};
+	const int cap = P.nl + P.al + 8;
+	std::vector<uint32_t> buf((size_t)cap);
+	const int n = backtrack(at, P.nl, P.al, buf.data(), cap);
+	cigar.assign(buf.begin() + (cap - n), buf.end());
+}
+
+} // namespace
+
+extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *codon, const int8_t *mat, const int32_t *sp, int go, int ge, int io,
+                        int fs, int xdrop, int end_bonus, float ie_coef, int flag, int C, const uint8_t *ns, int nl, const char *as, int al,
+                        int *score, int *nt_len, int *aa_len, uint32_t *cigar, int cigar_cap)
+{
+	Problem P;
+	P.nl = nl, P.al = al, P.W8 = (al + 7) / 8 * 8, P.mat = mat, P.end_bonus = end_bonus, P.xdrop = xdrop, P.ie_coef = ie_coef;
+	P.par.go = go, P.par.ge = ge, P.par.io = io, P.par.fs = fs, P.par.gei_stop = fs;
+	const bool left = flag & 2;
+	std::vector<int> code((size_t)nl);
+	for (int k = 0; k < nl; ++k) code[(size_t)k] = nt4[ns[left ? nl - 1 - k : k]];
+	auto c = [&](int k) { return code[(size_t)k]; };
+	P.rw.resize((size_t)nl + 1);
+	for (int r = 0; r <= nl; ++r) P.rw[(size_t)r] = left ? prep_row_left(c, nl, r, sp, codon, aa20['X']) : prep_row_forward(c, nl, r, sp, codon, aa20['X']);
+	P.aas.resize((size_t)al);
+	for (int j = 0; j < al; ++j) P.aas[(size_t)j] = aa20[(uint8_t)as[left ? al - 1 - j : j]];
+	*nt_len = nl, *aa_len = al;
+	int n_cig = 0;
+	if (flag & 6) {
+		switch (C) {
+		case 1: run_ext<1>(P, score, nt_len, aa_len); break;
+		case 2: run_ext<2>(P, score, nt_len, aa_len); break;
+		case 4: run_ext<4>(P, score, nt_len, aa_len); break;
+		default: run_ext<8>(P, score, nt_len, aa_len); break;
+		}
+	} else {
+		std::vector<uint32_t> cg;
+		switch (C) {
+		case 1: run_tb<1>(P, score, cg); break;
+		case 2: run_tb<2>(P, score, cg); break;
+		case 4: run_tb<4>(P, score, cg); break;
+		default: run_tb<8>(P, score, cg); break;
+		}
+		n_cig = (int)cg.size();
+		for (int k = 0; k < n_cig && k < cigar_cap; ++k) cigar[k] = cg[(size_t)k];
+	}
+	return n_cig;
+}

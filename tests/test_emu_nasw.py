@@ -1,0 +1,72 @@
+"""CPU lock-step emulation of the nasw CUDA kernels (same per-lane header the kernels compile) vs the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import build_hostcheck
+import oracle_lib as ol
+
+pytestmark = pytest.mark.skipif(not ol.have_ref(), reason="needs oracle/_ref for the tables")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    lib = C.CDLL(build_hostcheck.build())
+    lib.emu_nasw.restype = C.c_int
+    lib.emu_nasw.argtypes = [C.c_void_p] * 5 + [C.c_int] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_int] + \
+        [C.c_void_p] * 4 + [C.c_int]
+    return lib
+
+
+def emu(hc, nt, aa, flag, Ccols, mat, par):
+    r = ol.ref()
+    sp = (C.c_int32 * 6)(*par["sp"])
+    sc, ntl, aal = C.c_int(), C.c_int(), C.c_int()
+    cig = (C.c_uint32 * (len(nt) + len(aa) + 16))()
+    n = hc.emu_nasw(C.addressof(C.c_uint8.in_dll(r, "ref_ns_tab_nt4")), C.addressof(C.c_uint8.in_dll(r, "ref_ns_tab_aa20")),
+                    C.addressof(C.c_uint8.in_dll(r, "ref_ns_tab_codon")), mat.ctypes.data, C.addressof(sp), par["go"], par["ge"],
+                    par["io"], par["fs"], par["xdrop"], par["end_bonus"], par["ie_coef"], flag, Ccols,
+                    nt.ctypes.data, len(nt), aa, len(aa), C.addressof(sc), C.addressof(ntl), C.addressof(aal), C.addressof(cig), len(cig))
+    return sc.value, ntl.value, aal.value, [cig[i] for i in range(n)]
+
+
+@pytest.mark.parametrize("Ccols", [1, 2, 4, 8])
+def test_emu_matches_oracle(hc, Ccols):
+    rng = np.random.default_rng(1000 + Ccols)
+    tab, mat = ol.ref_tables(), ol.default_mat()
+    for it in range(120):
+        par = dict(ol.DEFAULT_NASW)
+        if it % 5 == 0:
+            par["sp"] = (8, 15, 21, 30, 4, 4)
+        al_max = (30, 70, 140, 300)[[1, 2, 4, 8].index(Ccols)]
+        if it % 6 == 0:
+            al_max = 32 * Ccols * 2 + 20  # force several column passes
+        nt, aa = ol.random_dp_problem(rng, al_max=al_max, flank=60)
+        if len(nt) < 3:
+            continue
+        for flag in (1, 4, 2):
+            if flag != 1 and it % 7 == 0:
+                par["io"] = 19
+            a = ol.ora_nasw(tab, nt, aa, flag, mat, par)
+            b = emu(hc, nt, aa, flag, Ccols, mat, par)
+            if flag == 1:
+                assert a[0] == b[0] and a[3] == b[3], (it, flag, len(nt), len(aa), a, b)
+            else:
+                assert a[:3] == b[:3], (it, flag, len(nt), len(aa), a[:3], b[:3])
+
+
+def test_emu_xdrop_and_tiny(hc):
+    rng = np.random.default_rng(4)
+    tab, mat = ol.ref_tables(), ol.default_mat()
+    par = dict(ol.DEFAULT_NASW, xdrop=30)
+    for it in range(30):
+        nt, aa = ol.random_dp_problem(rng, al_max=30, intron_max=0, flank=0)
+        nt = np.concatenate([nt, np.full(500, 4, np.uint8)])
+        assert ol.ora_nasw(tab, nt, aa, 4, mat, par)[:3] == emu(hc, nt, aa, 4, 1, mat, par)[:3]
+    for nl in (0, 1, 2, 3, 4, 5):  # degenerate global problems (no DP rows for nl < 3)
+        for al in (1, 2, 9):
+            nt = rng.integers(0, 4, size=nl).astype(np.uint8)
+            aa = bytes(b"ARNDCQEGH"[:al])
+            a, b = ol.ora_nasw(tab, nt, aa, 1, mat, dict(ol.DEFAULT_NASW)), emu(hc, nt, aa, 1, 1, mat, dict(ol.DEFAULT_NASW))
+            assert a[0] == b[0] and a[3] == b[3], (nl, al, a, b)
