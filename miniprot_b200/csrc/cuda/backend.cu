@@ -274,6 +274,33 @@ int mpb_nasw_batch(mpb_ctx_t *c, const ns_opt_t *opt, int32_t n, const mpb_dp_pr
 	return 0;
 }
 
+int mpb_chain_batch(mpb_ctx_t *c, const mpb_chain_par_t *par, int32_t n, const int64_t *a_off, const uint64_t *a, int64_t *u_off, uint64_t **u, int64_t *b_off,
+                    uint64_t **b)
+{
+	if (!c) return -1;
+	MPB_CUDA_OK(cudaSetDevice(c->device));
+	chn::Par p;
+	p.max_dist_x = par->max_dist_x, p.max_dist_y = par->max_dist_y, p.bw = par->bw, p.max_skip = par->max_skip, p.max_iter = par->max_iter;
+	p.min_cnt = par->min_cnt, p.min_sc = par->min_sc, p.chn_coef_log = par->chn_coef_log, p.is_spliced = par->is_spliced, p.kmer = par->kmer, p.bbit = par->bbit;
+	std::vector<int32_t> nu, nb;
+	std::vector<uint64_t> uu, bb;
+	chain_batch_run(c, p, n, a_off, a, nu, nb, uu, bb);
+	u_off[0] = b_off[0] = 0;
+	for (int32_t i = 0; i < n; ++i) u_off[i + 1] = u_off[i] + nu[(size_t)i], b_off[i + 1] = b_off[i] + nb[(size_t)i];
+	*u = (uint64_t*)malloc(sizeof(uint64_t) * (uu.size() + 1)), *b = (uint64_t*)malloc(sizeof(uint64_t) * (bb.size() + 1));
+	if (!uu.empty()) memcpy(*u, uu.data(), sizeof(uint64_t) * uu.size());
+	if (!bb.empty()) memcpy(*b, bb.data(), sizeof(uint64_t) * bb.size());
+	return 0;
+}
+
+int mpb_seed_batch(mpb_ctx_t *, const mp_idx_t *, int32_t, int32_t, const char *const *, const int32_t *, int64_t *, uint64_t **)
+{
+	fprintf(stderr, "[miniprot_b200] mpb_seed_batch: stage-level seeding entry is not exposed yet (use mpb_map_batch)\n");
+	return -1;
+}
+
+void mpb_free(void *p) { free(p); }
+
 void ns_global_gs16b(void *, const char *ns, int32_t nl, const char *as, int32_t al, const ns_opt_t *opt, const uint8_t *ss, ns_rst_t *r)
 {
 	mpb_dp_problem_t p;

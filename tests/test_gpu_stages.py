@@ -1,0 +1,93 @@
+"""GPU parity tests, stage by stage, through the C ABI of libminiprot_b200.so (mpb_nasw_batch / mpb_chain_batch):
+the CUDA kernels against the C oracle on the same seeded inputs.  Bit-exact: integer scores, lengths, CIGAR words."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import miniprot_b200 as mp
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = mp.Context(0)
+    yield c
+    c.close()
+
+
+def product_tables():
+    L = mp.lib()
+    t = ol.OraTab()
+    for f, sym in (("nt4", "ns_tab_nt4"), ("aa20", "ns_tab_aa20"), ("aa13", "ns_tab_aa13"), ("codon", "ns_tab_codon"), ("codon13", "ns_tab_codon13")):
+        setattr(t, f, C.addressof(C.c_uint8.in_dll(L, sym)))
+    return t
+
+
+def _par(opt):
+    return dict(go=opt.go, ge=opt.ge, io=opt.io, fs=opt.fs, xdrop=opt.xdrop, end_bonus=opt.end_bonus, sp=tuple(opt.sp),
+                sp_null_bonus=opt.sp_null_bonus, ie_coef=opt.ie_coef)
+
+
+@pytest.mark.parametrize("model", [1, 2])
+def test_nasw_batch_matches_oracle(ctx, model):
+    rng = np.random.default_rng(77 + model)
+    opt = mp.nsopt()
+    mp.lib().ns_opt_set_sp(C.byref(opt), model)
+    mat = opt._mat_keepalive
+    tab = product_tables()
+    probs = []
+    for it in range(700):
+        al_max = (30, 60, 120, 250, 600)[it % 5]
+        nt, aa = ol.random_dp_problem(rng, al_max=al_max, flank=80, intron_max=600 if it % 3 else 3000)
+        if len(nt) < 3 and it % 50:
+            continue
+        flag = (1, 4, 2)[it % 3]
+        io = 19 if (flag != 1 and it % 7 == 0) else opt.io
+        if flag != 1 and len(nt) < 3:
+            continue
+        probs.append((nt, aa, flag, io))
+    for nl in (0, 1, 2, 3, 4):  # degenerate global problems
+        probs.append((rng.integers(0, 4, size=nl).astype(np.uint8), b"MKV", 1, opt.io))
+    got = mp.nasw_batch(ctx, opt, probs)
+    bad = 0
+    for (nt, aa, flag, io), g in zip(probs, got):
+        par = _par(opt)
+        par["io"] = io
+        w = ol.ora_nasw(tab, nt, aa, flag, mat, par)
+        ok = (w[0] == g[0] and w[3] == g[3]) if flag == 1 else (w[:3] == g[:3])
+        if not ok:
+            bad += 1
+            if bad < 5:
+                print("MISMATCH", flag, len(nt), len(aa), w[:3], g[:3], w[3][:8], g[3][:8])
+    assert bad == 0
+    st = ctx.stats()
+    assert st.kernel_launches > 0 and st.dp_cells_ext > 0 and st.dp_cells_tb > 0
+
+
+def test_nasw_xdrop_long_tail(ctx):
+    rng = np.random.default_rng(5)
+    opt = mp.nsopt(xdrop=30)
+    tab, mat = product_tables(), opt._mat_keepalive
+    probs = []
+    for it in range(60):
+        nt, aa = ol.random_dp_problem(rng, al_max=40, intron_max=0, flank=0)
+        probs.append((np.concatenate([nt, np.full(900, 4, np.uint8)]), aa, 4, opt.io))
+    got = mp.nasw_batch(ctx, opt, probs)
+    for (nt, aa, flag, io), g in zip(probs, got):
+        assert ol.ora_nasw(tab, nt, aa, flag, mat, _par(opt))[:3] == g[:3]
+
+
+@pytest.mark.parametrize("mode", ["pre", "main", "refine"])
+def test_chain_batch_matches_oracle(ctx, mode):
+    rng = np.random.default_rng({"pre": 31, "main": 32, "refine": 33}[mode])
+    for over in ({}, dict(max_skip=2), dict(is_spliced=0, bw=500, max_dist_x=500), dict(max_iter=50)):
+        par = ol.chain_par(mode, **over)
+        lists = [ol.random_chain_problem(rng, int(rng.integers(1, 80 if i % 5 else 3000)), mode) for i in range(120)]
+        mpar = mp.ChainPar(**{f: getattr(par, f) for f, _ in mp.ChainPar._fields_})
+        got = mp.chain_batch(ctx, mpar, lists)
+        for a, (u, b) in zip(lists, got):
+            wu, wb = ol.ora_chain(par, a)
+            assert len(wu) == len(u) and (wu == u).all() and len(wb) == len(b) and (wb == b).all(), (mode, over, len(a))

@@ -1,0 +1,42 @@
+"""CPU: the product's HOST pipeline (region bookkeeping, alignment planner, statistics, PAF writer, index builder) with
+the C oracle plugged in as stage backend must reproduce the reference's PAF byte for byte (golden fixtures)."""
+import ctypes as C
+import os
+
+import pytest
+
+import build_hostcheck
+import oracle_lib as ol
+from miniprot_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+DATA = os.path.join(ol.ORA_DIR, "_ref", "data")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    lib = C.CDLL(build_hostcheck.build())
+    lib.hc_map_file.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64]
+    return lib
+
+
+def run(hc, g, p, out, flag=0, max_intron=0, auto=0, sp=-1, mini_batch=0):
+    assert hc.hc_map_file(g.encode(), p.encode(), out.encode(), flag, max_intron, auto, sp, 4, mini_batch) == 0
+    return open(out, "rb").read()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(DATA, "DPP3-hs.gen.fa.gz")), reason="bundled DPP3 pair not present (oracle/_ref/data)")
+@pytest.mark.parametrize("name,kw", [("DPP3_default", {}), ("DPP3_j2", dict(sp=2)), ("DPP3_G2k", dict(max_intron=2000))])
+def test_dpp3_golden(hc, tmp_path, name, kw):
+    got = run(hc, os.path.join(DATA, "DPP3-hs.gen.fa.gz"), os.path.join(DATA, "DPP3-mm.pep.fa.gz"), str(tmp_path / "o.paf"), **kw)
+    assert got == open(os.path.join(GOLD, name + ".paf"), "rb").read()
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "tiny5"])
+def test_synthetic_golden(hc, tmp_path, cfg):
+    g, p = synth.generate(synth.CONFIGS[cfg], str(tmp_path))
+    want = open(os.path.join(GOLD, cfg + ".paf"), "rb").read()
+    assert run(hc, g, p, str(tmp_path / "o.paf")) == want
+    # batch boundaries must not matter (SURVEY 8b determinism contract): 3 proteins per mini-batch
+    assert run(hc, g, p, str(tmp_path / "o2.paf"), mini_batch=1200) == want
