@@ -248,6 +248,12 @@ int mpb_chain_batch(mpb_ctx_t *ctx, const mpb_chain_par_t *par, int32_t n, const
 int mpb_seed_batch(mpb_ctx_t *ctx, const mp_idx_t *mi, int32_t max_occ, int32_t n_seq, const char *const *seqs,
                    const int32_t *lens, int64_t *a_off, uint64_t **a);
 
+void mpb_free(void *p);                                   /* free() for buffers this library malloc'ed */
+void mpb_regs_free(int32_t n, const int32_t *n_reg, mp_reg1_t **reg); /* free what mpb_map_batch returned */
+int32_t mpb_map_file_path(mpb_ctx_t *ctx, const mp_idx_t *mi, const char *fn, const mp_mapopt_t *opt, const char *out_path);
+void mpb_event_begin(mpb_ctx_t *ctx);                     /* CUDA-event bracket on the context's stream */
+double mpb_event_end_ms(mpb_ctx_t *ctx);
+
 /* counters since context creation (for bench.py): */
 typedef struct {
 	int64_t dp_cells_ext, dp_cells_tb; /* sum nl*al over executed DP problems */

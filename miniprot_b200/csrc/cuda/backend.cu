@@ -83,6 +83,16 @@ struct CudaStages : Stages {
 
 std::mutex g_default_mu;
 mpb_ctx_t *g_default_ctx = 0;
+std::vector<mpb_ctx_s*> g_all_ctx;
+
+// an index is identified by its address, so a context must forget it when the host object dies (the next
+// mp_idx_t may be allocated at the same address)
+void on_idx_destroy(const mp_idx_t *mi)
+{
+	std::lock_guard<std::mutex> lk(g_default_mu);
+	for (mpb_ctx_s *c : g_all_ctx)
+		if (c->mi == mi) c->mi = 0, c->d_seq = 0, c->d_ki = 0, c->d_kb = 0;
+}
 
 } // namespace
 
@@ -104,6 +114,11 @@ mpb_ctx_t *mpb_ctx_create(int device)
 	MPB_CUDA_OK(cudaEventCreate(&c->ev1));
 	memset(&c->stats, 0, sizeof(c->stats));
 	c->stages = new CudaStages(c);
+	{
+		std::lock_guard<std::mutex> lk(g_default_mu);
+		g_all_ctx.push_back(c);
+		g_idx_destroy_hook = on_idx_destroy;
+	}
 	if (ns_tab_aa20[(uint8_t)'X'] != 21) mp_start();
 	return c;
 }
@@ -111,6 +126,10 @@ mpb_ctx_t *mpb_ctx_create(int device)
 void mpb_ctx_destroy(mpb_ctx_t *c)
 {
 	if (!c) return;
+	{
+		std::lock_guard<std::mutex> lk(g_default_mu);
+		for (size_t i = 0; i < g_all_ctx.size(); ++i) if (g_all_ctx[i] == c) { g_all_ctx.erase(g_all_ctx.begin() + (ptrdiff_t)i); break; }
+	}
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = { &c->own_ki, &c->own_kb, &c->own_seq, &c->own_bo, &c->own_ctg, &c->b_jobs, &c->b_order, &c->b_chunks, &c->b_rw, &c->b_aa, &c->b_out,
@@ -300,6 +319,32 @@ int mpb_seed_batch(mpb_ctx_t *, const mp_idx_t *, int32_t, int32_t, const char *
 }
 
 void mpb_free(void *p) { free(p); }
+
+void mpb_regs_free(int32_t n, const int32_t *n_reg, mp_reg1_t **reg) // what the caller of mp_map does per protein (map.c:314-318)
+{
+	for (int32_t i = 0; i < n; ++i) {
+		for (int32_t j = 0; j < n_reg[i]; ++j) free(reg[i][j].feat), free(reg[i][j].p);
+		free(reg[i]);
+	}
+}
+
+// CUDA-event bracket on the context's stream (bench.py times its K steps with these)
+static cudaEvent_t g_bench_ev[2];
+void mpb_event_begin(mpb_ctx_t *c)
+{
+	MPB_CUDA_OK(cudaSetDevice(c->device));
+	if (!g_bench_ev[0]) { MPB_CUDA_OK(cudaEventCreate(&g_bench_ev[0])); MPB_CUDA_OK(cudaEventCreate(&g_bench_ev[1])); }
+	MPB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	MPB_CUDA_OK(cudaEventRecord(g_bench_ev[0], c->stream));
+}
+double mpb_event_end_ms(mpb_ctx_t *c)
+{
+	float ms = 0;
+	MPB_CUDA_OK(cudaEventRecord(g_bench_ev[1], c->stream));
+	MPB_CUDA_OK(cudaEventSynchronize(g_bench_ev[1]));
+	MPB_CUDA_OK(cudaEventElapsedTime(&ms, g_bench_ev[0], g_bench_ev[1]));
+	return ms;
+}
 
 void ns_global_gs16b(void *, const char *ns, int32_t nl, const char *as, int32_t al, const ns_opt_t *opt, const uint8_t *ss, ns_rst_t *r)
 {

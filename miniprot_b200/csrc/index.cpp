@@ -14,6 +14,8 @@
 
 namespace mpb {
 
+void (*g_idx_destroy_hook)(const mp_idx_t *) = 0;
+
 uint32_t hash32_mask(uint32_t x, uint32_t mask) // invertible mixer on 4k-bit keys (sketch.c:7-16)
 {
 	x = (x + ~(x << 15)) & mask;
@@ -153,6 +155,7 @@ extern "C" {
 void mp_idx_destroy(mp_idx_t *mi)
 {
 	if (!mi) return;
+	if (mpb::g_idx_destroy_hook) mpb::g_idx_destroy_hook(mi); // GPU contexts drop their resident copy of this index
 	ntdb_destroy(mi->nt);
 	free(mi->ki); free(mi->bo); free(mi->kb);
 	free(mi);

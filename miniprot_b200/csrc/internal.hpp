@@ -32,6 +32,7 @@ static inline uint8_t nt_at_v(const mp_ntdb_t *db, uint32_t vid, int64_t pos) //
 }
 
 // ---------------------------------------------------------------- index (index.cpp)
+extern void (*g_idx_destroy_hook)(const mp_idx_t *);                           // set by the CUDA backend
 int32_t idx_block2vid(const mp_idx_t *mi, uint32_t block);                  // index.c:41
 static inline uint32_t idx_n_bucket(const mp_idxopt_t *io) { return 1U << (io->kmer * 4 - io->mod_bit); }
 uint32_t hash32_mask(uint32_t key, uint32_t mask);                           // sketch.c:7

@@ -118,7 +118,7 @@ def _make_gene(rng: np.random.Generator, spec: SynthSpec, slot: int):
     mut = rng.random(plen) >= spec.identity
     sub = rng.integers(0, 20, size=plen)
     q = "".join(AA20[sub[i]] if mut[i] else prot[i] for i in range(plen))
-    return gene, q
+    return gene, q, prot
 
 
 def generate(spec: SynthSpec, outdir: str, gz: bool = False):
@@ -127,14 +127,16 @@ def generate(spec: SynthSpec, outdir: str, gz: bool = False):
     tag = spec.tag()
     gpath = os.path.join(outdir, tag + (".fa.gz" if gz else ".fa"))
     ppath = os.path.join(outdir, tag + ".faa")
-    if os.path.exists(gpath) and os.path.exists(ppath):
+    if os.path.exists(gpath) and os.path.exists(ppath) and os.path.exists(os.path.join(outdir, tag + ".planted.faa")):
         return gpath, ppath
     rng = np.random.default_rng(spec.seed)
     genome = _rand_dna(rng, spec.genome_len)
     slot = spec.genome_len // max(spec.n_genes, 1)
     prots = []
+    plants = []
     for g in range(spec.n_genes):
-        gene, q = _make_gene(rng, spec, slot)
+        gene, q, planted = _make_gene(rng, spec, slot)
+        plants.append((f"p{g}", planted))
         if len(gene) > slot - 200:
             prots.append((f"p{g}", q))  # does not fit: query kept (unmappable), nothing planted
             continue
@@ -165,7 +167,33 @@ def generate(spec: SynthSpec, outdir: str, gz: bool = False):
         for name, q in prots:
             f.write(f">{name}\n{q}\n")
     os.replace(ppath + ".tmp", ppath)
+    with open(os.path.join(outdir, tag + ".planted.faa"), "w") as f:
+        for name, q in plants:
+            f.write(f">{name}\n{q}\n")
     return gpath, ppath
+
+
+def shard_queries(spec: SynthSpec, outdir: str, shard: int) -> str:
+    """Query set of shard `shard` (weak scaling): the same planted proteins, mutated with a shard-specific seed.
+    Shard 0 is the default query file written by generate()."""
+    tag = spec.tag()
+    if shard == 0:
+        return os.path.join(outdir, tag + ".faa")
+    out = os.path.join(outdir, f"{tag}.shard{shard}.faa")
+    if os.path.exists(out):
+        return out
+    rng = np.random.default_rng(spec.seed * 1000003 + shard)
+    with open(os.path.join(outdir, tag + ".planted.faa")) as f, open(out + ".tmp", "w") as o:
+        for line in f:
+            if line.startswith(">"):
+                o.write(f">{line[1:].strip()}s{shard}\n")
+                continue
+            prot = line.strip()
+            mut = rng.random(len(prot)) >= spec.identity
+            sub = rng.integers(0, 20, size=len(prot))
+            o.write("".join(AA20[sub[i]] if mut[i] else prot[i] for i in range(len(prot))) + "\n")
+    os.replace(out + ".tmp", out)
+    return out
 
 
 # Named workloads of BASELINE.json (configs[1..4]) plus small test-sized variants.
