@@ -112,6 +112,13 @@ mpb_ctx_t *mpb_ctx_create(int device)
 	MPB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	MPB_CUDA_OK(cudaEventCreate(&c->ev0));
 	MPB_CUDA_OK(cudaEventCreate(&c->ev1));
+	MPB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+	for (int i = 0; i < mpb_ctx_s::N_SIDE; ++i) {
+		MPB_CUDA_OK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+		MPB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+		MPB_CUDA_OK(cudaEventCreate(&c->ev_k0[i]));
+		MPB_CUDA_OK(cudaEventCreate(&c->ev_k1[i]));
+	}
 	memset(&c->stats, 0, sizeof(c->stats));
 	c->stages = new CudaStages(c);
 	{
@@ -138,7 +145,8 @@ void mpb_ctx_destroy(mpb_ctx_t *c)
 	for (DevBuf &b : c->b_c) b.release();
 	c->h_out.release(), c->h_cigar.release();
 	for (PinBuf &b : c->h_c) b.release();
-	cudaEventDestroy(c->ev0), cudaEventDestroy(c->ev1);
+	cudaEventDestroy(c->ev0), cudaEventDestroy(c->ev1), cudaEventDestroy(c->ev_fork);
+	for (int i = 0; i < mpb_ctx_s::N_SIDE; ++i) cudaStreamDestroy(c->side[i]), cudaEventDestroy(c->ev_join[i]), cudaEventDestroy(c->ev_k0[i]), cudaEventDestroy(c->ev_k1[i]);
 	cudaStreamDestroy(c->stream);
 	delete c->stages;
 	delete c;

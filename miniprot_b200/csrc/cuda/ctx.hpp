@@ -9,6 +9,11 @@ struct mpb_ctx_s {
 	int device = 0;
 	cudaStream_t stream = 0;
 	cudaEvent_t ev0 = 0, ev1 = 0;
+	// side streams: size classes of one DP wave (and independent stage pieces) run concurrently; each class is bounded
+	// by its longest problem, so serialising them on one stream would add the critical paths up
+	static const int N_SIDE = 8;
+	cudaStream_t side[N_SIDE] = {0};
+	cudaEvent_t ev_fork = 0, ev_join[N_SIDE] = {0}, ev_k0[N_SIDE] = {0}, ev_k1[N_SIDE] = {0};
 
 	// resident read-only index (uploaded once, or adopted from an NCCL broadcast)
 	const mp_idx_t *mi = 0;

@@ -171,16 +171,43 @@ NSW_HD int ext_len_penalty(float ie_coef, int x)
 #endif
 }
 
+// The length penalty pen(x) = (int)(ie_coef*log2(x) + .5) (x = i - 3*al) is a non-decreasing step function of x with a
+// few dozen steps below 2^31, so the host tabulates where it steps (with the reference's exact FP32 arithmetic) and the
+// device only advances an index: thr[k] = smallest x with pen(x) > pen(thr[k-1]), val[k] = pen(thr[k]).
+constexpr int PEN_STEPS = 160;
+struct PenTable { int32_t n; int32_t thr[PEN_STEPS]; int32_t val[PEN_STEPS]; };
+
+inline void pen_table_build(float ie_coef, PenTable &t) // host only
+{
+	t.n = 0;
+	int cur = 0;
+	int64_t x = 2;
+	while (x < 2147483647LL && t.n < PEN_STEPS) {
+		// pen is monotone (the polynomial is increasing on [1,2) and steps up at octave boundaries): gallop + bisect
+		int64_t lo = x, hi = x;
+		while (hi < 2147483647LL && ext_len_penalty(ie_coef, (int)hi) <= cur) lo = hi, hi = hi * 2 < 2147483647LL ? hi * 2 : 2147483647LL;
+		if (ext_len_penalty(ie_coef, (int)hi) <= cur) break;
+		while (lo + 1 < hi) { const int64_t mid = (lo + hi) / 2; if (ext_len_penalty(ie_coef, (int)mid) > cur) hi = mid; else lo = mid; }
+		if (ext_len_penalty(ie_coef, (int)lo) > cur) hi = lo;
+		cur = ext_len_penalty(ie_coef, (int)hi);
+		t.thr[t.n] = (int32_t)hi, t.val[t.n] = cur, ++t.n;
+		x = hi + 1;
+	}
+}
+
 // extension bookkeeping of one problem (nasw-sse.c:423-433): fed one finished row at a time
 struct ExtTracker {
 	int max_sc, max_log, max_i, max_code;
+	int pen, pk;      // current penalty and index of the next step in the table
 	bool stopped;
-	NSW_HD void init() { max_sc = INT32_MIN, max_log = INT32_MIN, max_i = -1, max_code = 0, stopped = false; }
+	NSW_HD void init() { max_sc = INT32_MIN, max_log = INT32_MIN, max_i = -1, max_code = 0, pen = 0, pk = 0, stopped = false; }
 	// best = max over columns of (H_adjusted << 12 | (4095 - column)), padding columns carry code 0
-	NSW_HD void row(int i, int best, int pen_base /* 3*al */, float ie_coef, int xdrop)
+	NSW_HD void row(int i, int best, int pen_base /* 3*al */, const PenTable &pt, int xdrop)
 	{
 		if (stopped) return;
-		const int tsc = best >> 12, tlog = tsc - ext_len_penalty(ie_coef, i - pen_base);
+		const int x = i - pen_base;
+		while (pk < pt.n && x >= pt.thr[pk]) pen = pt.val[pk], ++pk;
+		const int tsc = best >> 12, tlog = tsc - pen;
 		if (tlog > max_log) max_sc = tsc, max_log = tlog, max_i = i, max_code = best & 4095;
 		if (max_log - tlog > xdrop) stopped = true;
 	}

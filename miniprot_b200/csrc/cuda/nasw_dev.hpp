@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "nasw_core.cuh"
 
 #ifndef NS_F_CIGAR
 #define NS_F_CIGAR 0x1
@@ -40,6 +41,7 @@ struct NaswConst {              // problem-independent parameters, passed by val
 	int32_t go, ge, fs, xdrop, end_bonus;
 	float ie_coef;
 	int32_t aa_x;               // code of 'X'
+	nsw::PenTable pen;          // extension length penalty as a step table (nasw-sse.c:426, FP32 done on the host)
 };
 
 void nasw_launch_prep(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, uint32_t *rw);

@@ -32,6 +32,7 @@ static void fill_const(const ns_opt_t *o, NaswConst &c)
 	for (int i = 0; i < 6; ++i) c.sp[i] = o->sp[i];
 	c.go = o->go, c.ge = o->ge, c.fs = o->fs, c.xdrop = o->xdrop, c.end_bonus = o->end_bonus, c.ie_coef = o->ie_coef;
 	c.aa_x = ns_tab_aa20[(uint8_t)'X'];
+	nsw::pen_table_build(o->ie_coef, c.pen);
 }
 
 // run jobs[lo, hi) as one sub-wave
@@ -89,31 +90,40 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	nasw_launch_prep(st, dj, ctx->b_chunks.as<PrepChunk>(), (int)chunks.size(), packed, cst, ctx->b_rw.as<uint32_t>());
 	ctx->stats.kernel_launches += 1;
 	static const int Cs[4] = { 1, 2, 4, 8 };
-	ctx->time_begin();
-	for (int c = 3; c >= 0; --c)
-		if (count[0][c]) {
-			nasw_launch_ext(st, Cs[c], dj, dord + first[0][c], (int)count[0][c], ctx->b_rw.as<uint32_t>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>());
-			ctx->stats.kernel_launches += 1;
+	// fork: every (kind, size class) runs on its own stream -- each is bounded by its longest problem
+	MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
+	bool used[mpb_ctx_s::N_SIDE] = { false };
+	for (int b = 0; b < 2; ++b)
+		for (int c = 3; c >= 0; --c) {
+			if (!count[b][c]) continue;
+			const int sid = b * 4 + c;
+			cudaStream_t ss = ctx->side[sid];
+			used[sid] = true;
+			MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
+			MPB_CUDA_OK(cudaEventRecord(ctx->ev_k0[sid], ss));
+			if (b == 0) {
+				nasw_launch_ext(ss, Cs[c], dj, dord + first[0][c], (int)count[0][c], ctx->b_rw.as<uint32_t>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>());
+				ctx->stats.kernel_launches += 1;
+			} else {
+				nasw_launch_tb(ss, Cs[c], dj, dord + first[1][c], (int)count[1][c], ctx->b_rw.as<uint32_t>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>(),
+				               ctx->b_tb.as<uint16_t>());
+				nasw_launch_bt(ss, dj, dord + first[1][c], (int)count[1][c], ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
+				ctx->stats.kernel_launches += 2;
+			}
+			MPB_CUDA_OK(cudaEventRecord(ctx->ev_k1[sid], ss));
+			MPB_CUDA_OK(cudaEventRecord(ctx->ev_join[sid], ss));
+			MPB_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_join[sid], 0));
 		}
-	ctx->stats.ms_dp_ext += ctx->time_end();
-	ctx->time_begin();
-	size_t n_tb = 0;
-	for (int c = 3; c >= 0; --c)
-		if (count[1][c]) {
-			nasw_launch_tb(st, Cs[c], dj, dord + first[1][c], (int)count[1][c], ctx->b_rw.as<uint32_t>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>(),
-			               ctx->b_tb.as<uint16_t>());
-			ctx->stats.kernel_launches += 1;
-			n_tb += count[1][c];
-		}
-	if (n_tb) {
-		nasw_launch_bt(st, dj, dord + first[1][0], (int)n_tb, ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
-		ctx->stats.kernel_launches += 1;
-	}
-	ctx->stats.ms_dp_tb += ctx->time_end();
 	MPB_CUDA_OK(cudaMemcpyAsync(ctx->h_out.p, ctx->b_out.p, sizeof(int4) * n, cudaMemcpyDeviceToHost, st));
 	if (cig_tot) MPB_CUDA_OK(cudaMemcpyAsync(ctx->h_cigar.p, ctx->b_cigar.p, sizeof(uint32_t) * (size_t)cig_tot, cudaMemcpyDeviceToHost, st));
 	MPB_CUDA_OK(cudaStreamSynchronize(st));
 	MPB_CUDA_OK(cudaGetLastError());
+	for (int sid = 0; sid < mpb_ctx_s::N_SIDE; ++sid)
+		if (used[sid]) { // sum of the classes' own durations (they overlap in time; the wave's wall time is what the step pays)
+			float ms = 0;
+			cudaEventElapsedTime(&ms, ctx->ev_k0[sid], ctx->ev_k1[sid]);
+			(sid < 4 ? ctx->stats.ms_dp_ext : ctx->stats.ms_dp_tb) += ms;
+		}
 	ctx->stats.d2h_bytes += sizeof(int4) * n + sizeof(uint32_t) * (size_t)cig_tot;
 	const int4 *ho = ctx->h_out.as<int4>();
 	const uint32_t *hc = ctx->h_cigar.as<uint32_t>();

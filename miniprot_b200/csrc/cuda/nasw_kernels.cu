@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_ext_kernel(const DpDev *
 			const int rI = __shfl_up_sync(0xffffffffu, L.outI, 1);
 			const int rB = __shfl_up_sync(0xffffffffu, L.outB, 1);
 			int row_i, row_best;
-			if (L.step(g, par, t, rH, rI, rB, env, &row_i, &row_best)) trk.row(row_i, row_best, g.al * 3, cst.ie_coef, cst.xdrop);
+			if (L.step(g, par, t, rH, rI, rB, env, &row_i, &row_best)) trk.row(row_i, row_best, g.al * 3, cst.pen, cst.xdrop);
 			if (pass == g.n_pass - 1 && (t & 15) == 15) {
 				if (__shfl_sync(0xffffffffu, (int)trk.stopped, 31)) break;
 			}

@@ -45,6 +45,8 @@ void run_ext(const Problem &P, int *score, int *nt_len, int *aa_len)
 	std::vector<int> prof(22 * Wp), cy((size_t)(P.nl + 1) * 3);
 	ExtTracker trk;
 	trk.init();
+	PenTable pt;
+	pen_table_build(P.ie_coef, pt);
 	for (int pass = 0; pass < n_pass; ++pass) {
 		for (int j = 0; j < Wp; ++j)
 			for (int a = 0; a < 22; ++a) prof[a * Wp + j] = pass * Wp + j < P.al ? P.mat[a * 22 + P.aas[pass * Wp + j]] : NEG;
@@ -61,7 +63,7 @@ void run_ext(const Problem &P, int *score, int *nt_len, int *aa_len)
 			for (int l = 0; l < 32; ++l) { const int s = l ? l - 1 : 0; rH[l] = L[s].outH, rI[l] = L[s].outI, rB[l] = L[s].outB; } // __shfl_up_sync(.., 1)
 			for (int l = 0; l < 32; ++l) {
 				int ri, rb;
-				if (L[l].step(g[l], P.par, t, rH[l], rI[l], rB[l], env[l], &ri, &rb)) trk.row(ri, rb, P.al * 3, P.ie_coef, P.xdrop);
+				if (L[l].step(g[l], P.par, t, rH[l], rI[l], rB[l], env[l], &ri, &rb)) trk.row(ri, rb, P.al * 3, pt, P.xdrop);
 			}
 			if (pass == n_pass - 1 && (t & 15) == 15 && trk.stopped) break;
 		}
@@ -148,4 +150,17 @@ extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *
 		for (int k = 0; k < n_cig && k < cigar_cap; ++k) cigar[k] = cg[(size_t)k];
 	}
 	return n_cig;
+}
+
+// step-table form of the extension length penalty vs the direct FP32 formula, for x in [0, xmax]
+extern "C" int emu_pen_check(float ie_coef, int xmax)
+{
+	PenTable pt;
+	pen_table_build(ie_coef, pt);
+	int bad = 0, pen = 0, pk = 0;
+	for (int x = 0; x <= xmax; ++x) {
+		while (pk < pt.n && x >= pt.thr[pk]) pen = pt.val[pk], ++pk;
+		bad += pen != ext_len_penalty(ie_coef, x);
+	}
+	return bad;
 }

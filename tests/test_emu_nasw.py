@@ -70,3 +70,10 @@ def test_emu_xdrop_and_tiny(hc):
             aa = bytes(b"ARNDCQEGH"[:al])
             a, b = ol.ora_nasw(tab, nt, aa, 1, mat, dict(ol.DEFAULT_NASW)), emu(hc, nt, aa, 1, 1, mat, dict(ol.DEFAULT_NASW))
             assert a[0] == b[0] and a[3] == b[3], (nl, al, a, b)
+
+
+def test_pen_table_equals_fp_formula(hc):
+    hc.emu_pen_check.restype = C.c_int
+    hc.emu_pen_check.argtypes = [C.c_float, C.c_int]
+    for coef in (0.5, 0.25, 1.0, 3.0):  # PEN_STEPS covers ie_coef up to ~5
+        assert hc.emu_pen_check(coef, 3_000_000) == 0
