@@ -126,70 +126,86 @@ CHN_HD int resolve_chunk(uint32_t rec, uint32_t skip, int32_t max_skip, int32_t 
 	return 32;
 }
 
-struct End { uint64_t x, y; }; // sort record: key x, payload y (same layout as mp128_t)
+// Sort records are packed into 8 bytes: key (score, or target coordinate) in the high 32 bits, anchor / chain index in
+// the low 32.  The reference sorts 16-byte {x, y} records by x alone (radix_sort_mp128x); the resulting permutation
+// depends only on the keys, so the packed form leaves ties in exactly the same places at half the traffic.
+CHN_HD uint64_t rec_key(uint64_t r) { return r >> 32; }
 
-// chain.c:8-24
-CHN_HD int64_t bk_end(int32_t max_drop, const End &z, const int32_t *f, const int32_t *p, int32_t *t)
+// chain.c:8-24.  T is the mark array type (int32 in global memory, or int8 when it lives in shared memory).
+template <class T>
+CHN_HD int64_t bk_end(int32_t max_drop, uint64_t z, const int32_t *f, const int32_t *p, T *t)
 {
-	int64_t i = (int64_t)z.y, end_i = -1, max_i = i;
+	const int32_t zx = (int32_t)(z >> 32);
+	int64_t i = (int64_t)(uint32_t)z, end_i = -1, max_i = i;
 	int32_t max_s = 0;
 	if (i < 0 || t[i] != 0) return i;
 	do {
 		t[i] = 2;
 		end_i = i = p[i];
-		const int32_t s = i < 0 ? (int32_t)z.x : (int32_t)z.x - f[i];
+		const int32_t s = i < 0 ? zx : zx - f[i];
 		if (s > max_s) max_s = s, max_i = i;
 		else if (max_s - s > max_drop) break;
 	} while (i >= 0 && t[i] == 0);
-	for (i = (int64_t)z.y; i >= 0 && i != end_i; i = p[i]) t[i] = 0;
+	for (i = (int64_t)(uint32_t)z; i >= 0 && i != end_i; i = p[i]) t[i] = 0;
 	return max_i;
 }
 
-// Sequential tail of mp_chain for ONE problem.  Scratch: t[n], v[n], z[n], stack[>=1100].
+// Sequential tail of mp_chain for ONE problem, after z[0..n_z) has been filled with (f<<32 | index) records in index
+// order and t[0..n) cleared.  Scratch: t[n] marks, v[n], z[>=n], stack[>=CHAIN_STACK]; f[] is OVERWRITTEN (it is dead after
+// the peeling and serves as the chain-offset table of the compaction).
 // Output: u[0..n_u) = score<<32|cnt, b[0..n_b) = compacted anchors (chains ordered by target start).  Returns n_u.
-CHN_HD int32_t backtrack_compact(const Par &p, int32_t n, const uint64_t *a, const int32_t *f, const int32_t *pp, int32_t *t, int32_t *v, End *z,
-                                 mpb::FlagRange<End> *stack, uint64_t *u, uint64_t *b, int32_t *n_b_out)
+template <class T>
+CHN_HD int32_t peel_and_compact(const Par &p, int32_t n_z, const uint64_t *a, int32_t *f, const int32_t *pp, T *t, int32_t *v, uint64_t *z,
+                                mpb::FlagRange<uint64_t> *stack, uint64_t *u, uint64_t *b, int32_t *n_b_out)
 {
 	const int32_t max_drop = p.is_spliced ? INT32_MAX : p.bw;
-	int32_t n_z = 0, n_u = 0, n_v = 0;
+	int32_t n_u = 0, n_v = 0;
 	*n_b_out = 0;
-	for (int32_t i = 0; i < n; ++i) if (f[i] >= p.min_sc) z[n_z].x = (uint64_t)(int64_t)f[i], z[n_z].y = (uint64_t)i, ++n_z;
 	if (n_z == 0) return 0;
-	mpb::flag_sort_by(z, z + n_z, [](const End &e) { return e.x; }, stack);
-	for (int32_t i = 0; i < n; ++i) t[i] = 0;
+	mpb::flag_sort_by(z, z + n_z, [](const uint64_t &e) { return rec_key(e); }, stack);
 	for (int32_t k = n_z - 1; k >= 0; --k) {
-		if (t[z[k].y] != 0) continue;
+		const int32_t zi = (int32_t)(uint32_t)z[k], zx = (int32_t)(z[k] >> 32);
+		if (t[zi] != 0) continue;
 		const int32_t n_v0 = n_v;
 		const int64_t end_i = bk_end(max_drop, z[k], f, pp, t);
 		int64_t i;
-		for (i = (int64_t)z[k].y; i != end_i; i = pp[i]) v[n_v++] = (int32_t)i, t[i] = 1;
-		const int32_t sc = i < 0 ? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+		for (i = zi; i != end_i; i = pp[i]) v[n_v++] = (int32_t)i, t[i] = 1;
+		const int32_t sc = i < 0 ? zx : zx - f[i];
 		if (sc >= p.min_sc && n_v > n_v0 && n_v - n_v0 >= p.min_cnt) u[n_u++] = (uint64_t)sc << 32 | (uint64_t)(n_v - n_v0);
 		else n_v = n_v0;
 	}
 	if (n_u == 0) return 0;
-	// compact (chain.c:77-110); z[] is reused as the chain-order sort buffer, t[] as the per-chain start offsets
-	End *w = z;
+	// compact (chain.c:77-110): chains reversed to ascending order, then ordered by first target coordinate
 	int32_t k = 0;
 	for (int32_t i = 0; i < n_u; ++i) {
 		const int32_t ni = (int32_t)(uint32_t)u[i];
-		w[i].x = a[v[k + ni - 1]] >> 32; // first anchor of the chain after reversal
-		w[i].y = (uint64_t)k << 32 | (uint64_t)i;
+		z[i] = (a[v[k + ni - 1]] >> 32) << 32 | (uint32_t)i; // first anchor of the chain after reversal
+		f[i] = k;
 		k += ni;
 	}
-	mpb::flag_sort_by(w, w + n_u, [](const End &e) { return e.x; }, stack);
+	mpb::flag_sort_by(z, z + n_u, [](const uint64_t &e) { return rec_key(e); }, stack);
 	int32_t o = 0;
 	for (int32_t i = 0; i < n_u; ++i) {
-		const int32_t src = (int32_t)(uint32_t)w[i].y, k0 = (int32_t)(w[i].y >> 32), ni = (int32_t)(uint32_t)u[src];
+		const int32_t src = (int32_t)(uint32_t)z[i], k0 = f[src], ni = (int32_t)(uint32_t)u[src];
 		for (int32_t j = 0; j < ni; ++j) b[o++] = a[v[k0 + (ni - j - 1)]];
-		t[i] = src; // remember the permutation to reorder u[] afterwards
 	}
-	// u2[i] = u[perm[i]]: done through v[] (free now) to avoid aliasing
-	for (int32_t i = 0; i < n_u; ++i) v[i] = t[i];
-	for (int32_t i = 0; i < n_u; ++i) { z[i].x = u[v[i]]; }
-	for (int32_t i = 0; i < n_u; ++i) u[i] = z[i].x;
+	for (int32_t i = 0; i < n_u; ++i) z[i] = u[(uint32_t)z[i]]; // u2[i] = u[perm[i]]
+	for (int32_t i = 0; i < n_u; ++i) u[i] = z[i];
 	*n_b_out = o;
 	return n_u;
+}
+
+// single-threaded form used by the CPU emulation and by problems too large for shared memory
+template <class T>
+CHN_HD int32_t backtrack_compact(const Par &p, int32_t n, const uint64_t *a, int32_t *f, const int32_t *pp, T *t, int32_t *v, uint64_t *z,
+                                 mpb::FlagRange<uint64_t> *stack, uint64_t *u, uint64_t *b, int32_t *n_b_out)
+{
+	int32_t n_z = 0;
+	for (int32_t i = 0; i < n; ++i) {
+		t[i] = 0;
+		if (f[i] >= p.min_sc) z[n_z++] = (uint64_t)(uint32_t)f[i] << 32 | (uint32_t)i;
+	}
+	return peel_and_compact(p, n_z, a, f, pp, t, v, z, stack, u, b, n_b_out);
 }
 
 } // namespace chn

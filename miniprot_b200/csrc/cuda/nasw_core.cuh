@@ -428,6 +428,88 @@ NSW_HD uint32_t prep_row_left(const Code &c, int nl, int i, const int *sp, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// backtrack over the traceback words (nasw-sse.c:40-89), run at a time.
+//
+// The reference walks one cell per iteration.  Consecutive cells very often repeat the same move (match runs along the
+// diagonal, introns thousands of rows long, gap runs), and a run is exactly "the cells along one direction whose word
+// keeps satisfying one condition", so a warp can test 32 cells of the run at once.  `Scan` supplies that test:
+//     int lead(kind, i, j, &n_valid)   number of LEADING cells k = 0..31 along the direction of `kind` that are inside
+//                                      the matrix and satisfy its condition; n_valid = cells of the 32 that are inside
+//       kind 0  cells (i-3k, j-k)  condition: the cell decodes to state 0 (match)            [M run]
+//       kind 1  cells (i,   j-k)   condition: bit 4 (insertion extended)                      [I run]
+//       kind 2  cells (i-3k, j)    condition: bit 5 (deletion extended)                       [D run]
+//       kind 3/4/5  cells (i-k, j) condition: bit 6/7/8 (intron phase 0/1/2 extended)         [N/U/V run]
+//     uint32_t word(i, j)          one traceback word
+// "inside" means i >= 2 and j >= 0, the loop condition of the reference.  The GPU kernel implements lead() with one
+// load per lane and a ballot; the CPU emulation loops over k.  Everything else -- the state machine, CIGAR run-length
+// merging (F and G never merge, nasw.h:141-151), the leftover rules and the tiny-U/V fix -- is this one function.
+// Operations are written into out[0..cap) growing DOWN from out[cap-1]; on return out[cap-n .. cap) is the CIGAR in
+// forward order.  Only the caller with `writer` set stores (lane 0 on the GPU).
+// ------------------------------------------------------------------------------------------------
+template <class Scan>
+NSW_HD int backtrack_runs(Scan &sc, int nl, int al, uint32_t *out, int cap, bool writer)
+{
+	int i = nl - 1, j = al - 1, last = 0, n = 0;
+	uint32_t cur_op = 0xffffffffu;
+	int cur_len = 0;
+	auto flush = [&]() {
+		if (cur_len > 0 && n < cap) {
+			++n;
+			uint32_t op = cur_op;
+			if ((op == 12 || op == 13) && cur_len < 3) op = 11; // nasw-sse.c:30-38: tiny U/V become G
+			if (writer) out[cap - n] = (uint32_t)cur_len << 4 | op;
+		}
+		cur_len = 0;
+	};
+	auto push = [&](uint32_t op, int len) {
+		if (cur_len > 0 && op == cur_op && op != 10 && op != 11) cur_len += len;
+		else { flush(); cur_op = op, cur_len = len; }
+	};
+	while (i >= 2 && j >= 0) {
+		int state = last;
+		if (state == 0) {
+			uint32_t x = sc.word(i, j);
+			state = (x >> 9 & 1) ? 1 : (int)(x & 0xf);
+		}
+		if (state == 0) { // match run along the diagonal
+			int nv;
+			const int c = sc.lead(0, i, j, nv);
+			push(0, c), i -= 3 * c, j -= c; // c >= 1: cell 0 is a match
+		} else if (state <= 5) { // runs that continue while the extension bit of the current cell is set
+			const int di = state == 1 ? 0 : state == 2 ? 3 : 1, dj = state == 1 ? 1 : 0;
+			const uint32_t op = state <= 3 ? (uint32_t)state : (uint32_t)(state + 8); // I, D, N, U(12), V(13)
+			int nv;
+			const int c = sc.lead(state, i, j, nv);
+			int cells;
+			if (c == 32) cells = 32, last = state;          // still extending after 32 cells
+			else if (c < nv) cells = c + 1, last = 0;       // cell c is inside and ends the run (its bit is clear)
+			else cells = c, last = state;                   // ran out of the matrix while extending
+			push(op, cells), i -= di * cells, j -= dj * cells;
+			if ((state == 4 || state == 5) && c < 32 && c < nv) --j; // the closing cell of a phase-1/2 intron consumes the residue
+		} else {
+			switch (state) {
+			case 6: push(10, 1), --i; break;
+			case 7: push(10, 2), i -= 2; break;
+			case 8: push(11, 1), --i, --j; break;
+			case 9: push(11, 2), i -= 2, --j; break;
+			default: i = -1000000; break; // states 10..15 never occur
+			}
+			last = 0;
+		}
+	}
+	if (i > -1000000) {
+		if (j > 0) push(1, j);
+		if (i >= 0) {
+			const int l = (i + 1) / 3 * 3, t = (i + 1) % 3;
+			if (l > 0) push(2, l);
+			if (t != 0) push(10, t);
+		}
+	}
+	flush();
+	return n;
+}
+
+// ------------------------------------------------------------------------------------------------
 // backtrack over the traceback words (nasw-sse.c:40-89).  `tb(i, j)` returns the 10-bit word of cell (i,j).
 // Operations are produced from the alignment end backwards, run-length merged except F and G
 // (nasw.h:141-151), and written into out[0..cap) growing DOWN from out[cap-1], so that on return

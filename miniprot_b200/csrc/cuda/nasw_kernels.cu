@@ -202,20 +202,45 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_tb_kernel(const DpDev *j
 }
 
 // ------------------------------------------------------------------ backtrack -> CIGAR
-__global__ void __launch_bounds__(128) nasw_bt_kernel(const DpDev *jobs, const int *order, int n_jobs, const uint16_t *tb, uint32_t *cigar, int4 *out)
+// One warp per problem.  The walk is sequential, but it proceeds a RUN at a time (nasw_core.cuh::backtrack_runs): the 32
+// lanes fetch the next 32 cells along the current move direction in one round trip and a ballot tells how far the run
+// goes, instead of one dependent L2 access per cell (introns are thousands of cells long).
+struct DevScan {
+	const uint16_t *base;
+	int C, Wp, T, lane;
+	__device__ __forceinline__ uint32_t at(int i, int j) const
+	{
+		const int pass = j / Wp, jc = j - pass * Wp, ln = jc / C;
+		return base[((int64_t)pass * T + (i - 2 + ln)) * Wp + jc];
+	}
+	__device__ __forceinline__ uint32_t word(int i, int j) const { return at(i, j); }
+	__device__ __forceinline__ int lead(int kind, int i, int j, int &n_valid) const
+	{
+		const int di = kind == 0 ? 3 : kind == 1 ? 0 : kind == 2 ? 3 : 1, dj = kind <= 1 ? 1 : 0;
+		const int ii = i - di * lane, jj = j - dj * lane;
+		const bool valid = ii >= 2 && jj >= 0;
+		bool ok = false;
+		if (valid) {
+			const uint32_t x = at(ii, jj);
+			ok = kind == 0 ? (!(x >> 9 & 1) && (x & 0xf) == 0) : (x >> (kind + 3) & 1);
+		}
+		const uint32_t vm = __ballot_sync(0xffffffffu, valid), om = __ballot_sync(0xffffffffu, ok);
+		n_valid = __popc(vm);
+		return om == 0xffffffffu ? 32 : __ffs(~om) - 1;
+	}
+};
+
+__global__ void __launch_bounds__(NASW_WARPS * 32) nasw_bt_kernel(const DpDev *jobs, const int *order, int n_jobs, const uint16_t *tb, uint32_t *cigar, int4 *out)
 {
-	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int slot = blockIdx.x * NASW_WARPS + warp;
 	if (slot >= n_jobs) return;
 	const int jid = order[slot];
 	const DpDev job = jobs[jid];
-	const int C = job.C, Wp = 32 * C, T = job.nl > 2 ? job.nl - 2 + 32 : 0;
-	const uint16_t *base = tb + job.tb_off;
-	auto at = [&](int i, int j) -> uint32_t {
-		const int pass = j / Wp, jc = j - pass * Wp, lane = jc / C;
-		return base[((int64_t)pass * T + (i - 2 + lane)) * Wp + jc];
-	};
-	const int n = backtrack(at, job.nl, job.al, cigar + job.cig_off, job.cig_cap);
-	out[jid].w = n;
+	DevScan sc;
+	sc.base = tb + job.tb_off, sc.C = job.C, sc.Wp = 32 * job.C, sc.T = job.nl > 2 ? job.nl - 2 + 32 : 0, sc.lane = lane;
+	const int n = backtrack_runs(sc, job.nl, job.al, cigar + job.cig_off, job.cig_cap, lane == 0);
+	if (lane == 0) out[jid].w = n;
 }
 
 // ------------------------------------------------------------------ launchers
@@ -268,7 +293,7 @@ void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order,
 
 void nasw_launch_bt(cudaStream_t st, const DpDev *jobs, const int *order, int n, const uint16_t *tb, uint32_t *cigar, int4 *out)
 {
-	if (n > 0) nasw_bt_kernel<<<(n + 127) / 128, 128, 0, st>>>(jobs, order, n, tb, cigar, out);
+	if (n > 0) nasw_bt_kernel<<<(n + NASW_WARPS - 1) / NASW_WARPS, NASW_WARPS * 32, 0, st>>>(jobs, order, n, tb, cigar, out);
 }
 
 } // namespace cuda

@@ -60,13 +60,15 @@ static void chain_problems(mpb_ctx_s *ctx, int n_prob, const std::vector<int64_t
 	n_u.assign((size_t)n_prob, 0), n_b.assign((size_t)n_prob, 0), u.clear(), bb.clear();
 	if (n_prob == 0) return;
 	int32_t *f, *p, *t, *v, *d_nu, *d_nb, *d_nu2, *d_nb2;
-	chn::End *z;
+	uint64_t *z;
+	int32_t *d_list;
 	uint64_t *du, *db, *du2, *db2, *gu, *gb;
 	int64_t *d_go_u, *d_go_b;
 	void *stack;
 	auto layout = [&](Carver &c) {
 		f = c.take<int32_t>(N + 1), p = c.take<int32_t>(N + 1), t = c.take<int32_t>(N + 1), v = c.take<int32_t>(N + 1);
-		z = c.take<chn::End>(N + 1);
+		z = c.take<uint64_t>(N + 1);
+		d_list = c.take<int32_t>((size_t)n_prob);
 		du = c.take<uint64_t>(N + 1), db = c.take<uint64_t>(N + 1), du2 = c.take<uint64_t>(N + 1), db2 = c.take<uint64_t>(N + 1);
 		gu = c.take<uint64_t>(N + 1), gb = c.take<uint64_t>(N + 1);
 		d_nu = c.take<int32_t>((size_t)n_prob), d_nb = c.take<int32_t>((size_t)n_prob), d_nu2 = c.take<int32_t>((size_t)n_prob), d_nb2 = c.take<int32_t>((size_t)n_prob);
@@ -76,18 +78,44 @@ static void chain_problems(mpb_ctx_s *ctx, int n_prob, const std::vector<int64_t
 	ctx->b_c[8].reserve(carve_size(layout));
 	Carver cv(ctx->b_c[8].p);
 	layout(cv);
+	// size classes of the backtrack kernel (anchors per problem -> shared memory per warp); sizes are taken from the
+	// offsets, an upper bound for the main chain that follows a pre-chain
+	static const int caps[3] = { 2048, 8192, 25000 };
+	std::vector<int32_t> lists[4];
+	for (int i = 0; i < n_prob; ++i) {
+		const int64_t n = h_off[(size_t)i + 1] - h_off[(size_t)i];
+		lists[n <= caps[0] ? 0 : n <= caps[1] ? 1 : n <= caps[2] ? 2 : 3].push_back(i);
+	}
+	std::vector<int32_t> flat;
+	size_t lfirst[4];
+	for (int c = 0; c < 4; ++c) lfirst[c] = flat.size(), flat.insert(flat.end(), lists[c].begin(), lists[c].end());
+	MPB_CUDA_OK(cudaMemcpyAsync(d_list, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice, st));
+	auto backtrack = [&](const int32_t *cnt, const uint64_t *in, const chn::Par &par, uint64_t *uo, uint64_t *bo, int32_t *nuo, int32_t *nbo, int resort) {
+		// the classes are independent: run them on side streams (each is bounded by its slowest problem)
+		MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
+		for (int c = 0; c < 4; ++c) {
+			if (lists[c].empty()) continue;
+			cudaStream_t ss = ctx->side[c];
+			MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
+			if (c < 3) chain_launch_bt_smem(ss, d_list + lfirst[c], (int)lists[c].size(), caps[c], d_off, cnt, in, par, f, p, v, stack, uo, bo, nuo, nbo, resort);
+			else chain_launch_bt(ss, d_list + lfirst[c], (int)lists[c].size(), d_off, cnt, in, par, f, p, t, v, z, stack, uo, bo, nuo, nbo, resort);
+			MPB_CUDA_OK(cudaEventRecord(ctx->ev_join[c], ss));
+			MPB_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_join[c], 0));
+			ctx->stats.kernel_launches += 1;
+		}
+	};
 	ctx->time_begin();
 	const uint64_t *in = d_a;
 	const int32_t *cnt = 0;
 	if (pre) {
 		chain_launch_fill(st, d_off, 0, d_a, n_prob, *pre, f, p, t);
-		chain_launch_bt(st, d_off, 0, d_a, n_prob, *pre, f, p, t, v, z, stack, du, db, d_nu, d_nb, 1);
+		backtrack(0, d_a, *pre, du, db, d_nu, d_nb, 1);
 		in = db, cnt = d_nb;
-		ctx->stats.kernel_launches += 2;
+		ctx->stats.kernel_launches += 1;
 	}
 	chain_launch_fill(st, d_off, cnt, in, n_prob, mainp, f, p, t);
-	chain_launch_bt(st, d_off, cnt, in, n_prob, mainp, f, p, t, v, z, stack, du2, db2, d_nu2, d_nb2, 0);
-	ctx->stats.kernel_launches += 2;
+	backtrack(cnt, in, mainp, du2, db2, d_nu2, d_nb2, 0);
+	ctx->stats.kernel_launches += 1;
 	MPB_CUDA_OK(cudaMemcpyAsync(n_u.data(), d_nu2, sizeof(int32_t) * (size_t)n_prob, cudaMemcpyDeviceToHost, st));
 	MPB_CUDA_OK(cudaMemcpyAsync(n_b.data(), d_nb2, sizeof(int32_t) * (size_t)n_prob, cudaMemcpyDeviceToHost, st));
 	MPB_CUDA_OK(cudaStreamSynchronize(st));

@@ -58,11 +58,11 @@ extern "C" int emu_chain(const Par *par_, int32_t n, const uint64_t *a, int reso
 		f[(size_t)i] = max_f, p[(size_t)i] = max_j;
 		if (hf < max_f) hf = max_f, hi = i;
 	}
-	std::vector<End> z((size_t)n + 1);
-	std::vector<mpb::FlagRange<End>> stack(8 * 256 + 8);
+	std::vector<uint64_t> z((size_t)n + 1);
+	std::vector<mpb::FlagRange<uint64_t>> stack(8 * 256 + 8);
 	int32_t n_b = 0, n_u = 0;
 	if (n > 0) n_u = backtrack_compact(par, n, a, f.data(), p.data(), t.data(), v.data(), z.data(), stack.data(), u_out, b_out, &n_b);
-	if (resort && n_b > 1) mpb::flag_sort_by(b_out, b_out + n_b, [](const uint64_t &x) { return x; }, (mpb::FlagRange<uint64_t>*)stack.data());
+	if (resort && n_b > 1) mpb::flag_sort_by(b_out, b_out + n_b, [](const uint64_t &x) { return x; }, stack.data());
 	*n_b_out = n_b;
 	return n_u;
 }

@@ -5,6 +5,7 @@
 // and the carry arrays are replaced by plain arrays here.  Lets the CPU test-suite compare the device arithmetic
 // with the oracle for every column-per-lane variant and for multi-pass problems, without a GPU.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -107,9 +108,31 @@ void run_tb(const Problem &P, int *score, std::vector<uint32_t> &cigar)
 		return tb[((size_t)pass * T + (i - 2 + lane)) * Wp + jc];
 	};
 	const int cap = P.nl + P.al + 8;
-	std::vector<uint32_t> buf((size_t)cap);
-	const int n = backtrack(at, P.nl, P.al, buf.data(), cap);
-	cigar.assign(buf.begin() + (cap - n), buf.end());
+	std::vector<uint32_t> buf((size_t)cap), buf2((size_t)cap);
+	const int n = backtrack(at, P.nl, P.al, buf.data(), cap); // cell-at-a-time walk (the reference's own formulation)
+	struct CpuScan { // what the GPU does with one load per lane and a ballot
+		decltype(at) &tb;
+		uint32_t word(int i, int j) const { return tb(i, j); }
+		int lead(int kind, int i, int j, int &n_valid) const
+		{
+			const int di = kind == 0 ? 3 : kind == 1 ? 0 : kind == 2 ? 3 : 1, dj = kind <= 1 ? 1 : 0;
+			int c = 0;
+			bool open = true;
+			n_valid = 0;
+			for (int k = 0; k < 32; ++k) {
+				const int ii = i - di * k, jj = j - dj * k;
+				if (ii < 2 || jj < 0) break;
+				++n_valid;
+				const uint32_t x = tb(ii, jj);
+				const bool ok = kind == 0 ? ((x >> 9 & 1) ? false : (x & 0xf) == 0) : (x >> (kind + 3) & 1);
+				if (open && ok) ++c; else open = false;
+			}
+			return c;
+		}
+	} scan{at};
+	const int n2 = backtrack_runs(scan, P.nl, P.al, buf2.data(), cap, true);
+	if (n2 != n || memcmp(buf.data() + (cap - n), buf2.data() + (cap - n2), sizeof(uint32_t) * (size_t)n) != 0) { fprintf(stderr, "[emu] run-based backtrack differs from the cell walk\n"); abort(); }
+	cigar.assign(buf2.begin() + (cap - n2), buf2.end());
 }
 
 } // namespace
