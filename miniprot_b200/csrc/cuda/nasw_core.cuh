@@ -47,19 +47,31 @@ struct Par {          // scalar parameters of one problem
 	int gei_stop;     // ge used on rows whose codon is a stop: fs (nasw-sse.c:263)
 };
 
-struct RowConst {     // per-row constants of the recurrences (nasw-sse.c:260-271)
-	int nas, gei, dim1, di, dip1, ai, aim1, aim2;
-};
+// Row record: everything row i contributes to the recurrences, with the constants already combined (written by the prep
+// kernel, 32 B per row, read by the DP kernels with two 128-bit loads one step ahead):
+//   cA = io + donor[i-1], cB = io + donor[i], cC = io + donor[i+1]   (A/B/C intron-open terms, nasw-sse.c:373-392)
+//   aA = acceptor[i], aB = acceptor[i-2], aC = acceptor[i-1]         gei = fs on stop-codon rows else ge (nasw-sse.c:263)
+// sat(sat(x - io) - d) == sat(x - (io + d)) because both penalties are >= 0 (floor clamping composes); the device path
+// has no --spsc input, which is the only source of negative donor/acceptor values.
+struct RowRec { int cA, cB, cC, gei, aA, aB, aC, nas; };
 
-// rows i-2, i-1, i, i+1 -> constants of row i
-NSW_HD RowConst row_const(const Par &p, uint32_t w_m2, uint32_t w_m1, uint32_t w_0, uint32_t w_p1)
+NSW_HD RowRec make_row_rec(const Par &p, uint32_t w_m2, uint32_t w_m1, uint32_t w_0, uint32_t w_p1)
 {
-	RowConst r;
+	RowRec r;
 	r.nas = row_nas(w_0);
 	r.gei = r.nas == 20 ? p.fs : p.ge;
-	r.dim1 = row_don(w_m1), r.di = row_don(w_0), r.dip1 = row_don(w_p1);
-	r.ai = row_acc(w_0), r.aim1 = row_acc(w_m1), r.aim2 = row_acc(w_m2);
+	r.cA = p.io + row_don(w_m1), r.cB = p.io + row_don(w_0), r.cC = p.io + row_don(w_p1);
+	r.aA = row_acc(w_0), r.aC = row_acc(w_m1), r.aB = row_acc(w_m2);
 	return r;
+}
+
+NSW_HD int imax3(int a, int b, int c)
+{
+#ifdef __CUDA_ARCH__
+	return __vimax3_s32(a, b, c);
+#else
+	return imax(imax(a, b), c);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -67,27 +79,24 @@ NSW_HD RowConst row_const(const Par &p, uint32_t w_m2, uint32_t w_m1, uint32_t w
 //   in : h1,h2,h3 = H(i-1..i-3, j); d3 = D(i-3,j); a,b,c = running intron states of column j;
 //        l0 = H(i,j-1) (final), l1,l2,l3 = H(i-1..i-3, j-1); it = It(i,j-1); s = profile(nas_i, j)
 //   out: returns H(i,j); updates d_new, a, b, c, it (-> It(i,j))
+// Every stored value stays >= -32768, so the per-operation floor of the SSE kernel is needed only where a value is
+// carried (it, d_new) or first formed (the match term); max(h, x) absorbs it everywhere else.  17 integer ops.
 // ------------------------------------------------------------------------------------------------
-NSW_HD int cell_score(const Par &p, const RowConst &r, int s, int h1, int h2, int h3, int d3, int &d_new, int &a, int &b, int &c,
+NSW_HD int cell_score(const Par &p, const RowRec &r, int s, int h1, int h2, int h3, int d3, int &d_new, int &a, int &b, int &c,
                       int l0, int l1, int l2, int l3, int &it)
 {
 	int h = adds(l3, s);
-	it = subs(imax(subs(l0, p.go), it), p.ge);
-	h = imax(h, it);
-	d_new = subs(imax(subs(h3, p.go), d3), r.gei);
-	h = imax(h, d_new);
-	int u = subs(h1, p.io);
-	a = imax(subs(u, r.dim1), a);
-	h = imax(h, subs(a, r.ai));
-	u = subs(l1, p.io);
-	b = imax(subs(u, r.di), b);
-	h = imax(h, subs(b, r.aim2));
-	c = imax(subs(u, r.dip1), c);
-	h = imax(h, subs(c, r.aim1));
-	h = imax(h, subs(h1, p.fs));
-	h = imax(h, subs(h2, p.fs));
-	h = imax(h, subs(l1, p.fs));
-	h = imax(h, subs(l2, p.fs));
+	it = subs(imax(l0 - p.go, it), p.ge);
+	d_new = subs(imax(h3 - p.go, d3), r.gei);
+	a = imax(h1 - r.cA, a);
+	b = imax(l1 - r.cB, b);
+	c = imax(l1 - r.cC, c);
+	const int fg = imax(imax3(h1, h2, l1), l2) - p.fs;
+	h = imax3(h, it, d_new);
+	h = imax(h, a - r.aA);
+	h = imax(h, b - r.aB);
+	h = imax(h, c - r.aC);
+	h = imax(h, fg);
 	return h;
 }
 
@@ -96,8 +105,9 @@ NSW_HD int cell_score(const Par &p, const RowConst &r, int s, int h1, int h2, in
 //   extra in : f0 = first-pass H(i,j-1) and iseg = first-pass insertion chain at j-1 (both -32768 when
 //              column j starts a stripe segment), it = true insertion chain
 //   out      : hfirst (first-pass H(i,j)), returns final H(i,j), tb word (10 bits)
+// Comparisons see exactly the saturated values the SSE kernel compares.
 // ------------------------------------------------------------------------------------------------
-NSW_HD int cell_trace(const Par &p, const RowConst &r, int s, int h1, int h2, int h3, int d3, int &d_new, int &a, int &b, int &c,
+NSW_HD int cell_trace(const Par &p, const RowRec &r, int s, int h1, int h2, int h3, int d3, int &d_new, int &a, int &b, int &c,
                       int l0, int f0, int l1, int l2, int l3, int &iseg, int &it, int &hfirst, uint32_t &word)
 {
 	uint32_t y = 0, z = 0;
@@ -113,25 +123,22 @@ NSW_HD int cell_trace(const Par &p, const RowConst &r, int s, int h1, int h2, in
 	d_new = t;
 	if (t > h) y = 2;
 	h = imax(h, t);
-	u = subs(h1, p.io), v = a;
-	t = subs(u, r.dim1);
+	t = subs(h1, r.cA), v = a;
 	if (v > t) z |= 1u << 6;
 	a = imax(t, v);
-	t = subs(a, r.ai);
+	t = subs(a, r.aA);
 	if (t > h) y = 3;
 	h = imax(h, t);
-	u = subs(l1, p.io), v = b;
-	t = subs(u, r.di);
+	t = subs(l1, r.cB), v = b;
 	if (v > t) z |= 1u << 7;
 	b = imax(t, v);
-	t = subs(b, r.aim2);
+	t = subs(b, r.aB);
 	if (t > h) y = 4;
 	h = imax(h, t);
-	v = c;
-	t = subs(u, r.dip1);
+	t = subs(l1, r.cC), v = c;
 	if (v > t) z |= 1u << 8;
 	c = imax(t, v);
-	t = subs(c, r.aim1);
+	t = subs(c, r.aC);
 	if (t > h) y = 5;
 	h = imax(h, t);
 	t = subs(h1, p.fs); if (t > h) y = 6; h = imax(h, t);
@@ -204,38 +211,44 @@ struct ExtTracker {
 	// best = max over columns of (H_adjusted << 12 | (4095 - column)), padding columns carry code 0
 	NSW_HD void row(int i, int best, int pen_base /* 3*al */, const PenTable &pt, int xdrop)
 	{
-		if (stopped) return;
 		const int x = i - pen_base;
-		while (pk < pt.n && x >= pt.thr[pk]) pen = pt.val[pk], ++pk;
+		while (pk < pt.n && x >= pt.thr[pk]) pen = pt.val[pk], ++pk; // a few dozen iterations over the whole problem
 		const int tsc = best >> 12, tlog = tsc - pen;
-		if (tlog > max_log) max_sc = tsc, max_log = tlog, max_i = i, max_code = best & 4095;
-		if (max_log - tlog > xdrop) stopped = true;
+		const bool better = !stopped && tlog > max_log;
+		max_sc = better ? tsc : max_sc, max_i = better ? i : max_i, max_code = better ? (best & 4095) : max_code;
+		max_log = better ? tlog : max_log;
+		stopped = stopped || max_log - tlog > xdrop;
 	}
 };
 
 // ------------------------------------------------------------------------------------------------
 // One lane of the wavefront.  The kernels keep one of these per thread (all arrays live in registers) and
 // call step() once per wavefront step after fetching the left lane's outputs with warp shuffles.
-//   Env must provide:  uint32_t row_word(int i)            row word i (clamped to [0,nl])
+//   Env must provide:  RowRec row_rec(int i)               record of row i (index clamped to [0,nl]); prefetched a step ahead
 //                      const int *profile(int nas)          profile row of amino acid `nas` for THIS lane's columns
 //                      carry load/store for multi-pass problems (see kernels)
+// MULTI = the problem is wider than one pass (32*C columns): lane 0 of pass > 0 reads the previous pass's last
+// column from the carry array and lane 31 of every pass but the last writes it.  Single-pass instantiations carry
+// none of that code.  Lane-0 boundary handling and the extension tracker are branch-free on purpose: a warp pays
+// for every divergent side path on every step, and one step is the unit of the critical path (nl steps).
 // ------------------------------------------------------------------------------------------------
 struct LaneGeom {            // where this lane sits in the problem
 	int lane, pass, n_pass, nl, al, W8, col0;
 	bool live;               // owns real or padding columns (col0 < W8)
 };
 
-template <int C>
+template <int C, bool MULTI>
 struct ExtLane {
 	int H1[C], H2[C], H3[C], D1[C], D2[C], D3[C], A[C], B[C], Cc[C];
 	int code[C], bonus[C];
 	int L1, L2, L3;
 	int outH, outI, outB;    // what the lane to the right receives next step
-	uint32_t w_m1, w_0, w_p1, w_pre;
+	RowRec nxt;              // record of the row this lane processes at the NEXT step
 
 	template <class Env>
 	NSW_HD void init(const LaneGeom &g, int end_bonus, const Env &env)
 	{
+#pragma unroll
 		for (int k = 0; k < C; ++k) {
 			const int jg = g.col0 + k;
 			H1[k] = H2[k] = H3[k] = D1[k] = D2[k] = D3[k] = A[k] = B[k] = Cc[k] = NEG;
@@ -244,29 +257,27 @@ struct ExtLane {
 		}
 		L1 = L2 = L3 = NEG;
 		outH = outI = NEG, outB = INT32_MIN;
-		const int i_first = 2 - g.lane;
-		w_m1 = env.row_word(i_first - 2), w_0 = env.row_word(i_first - 1), w_p1 = env.row_word(i_first), w_pre = env.row_word(i_first + 1);
+		nxt = env.row_rec(2 - g.lane);
 	}
 
-	// rH/rI/rB: outputs of the left lane from the previous step (ignored by lane 0 of pass 0)
-	// returns true when this lane finished a row whose best value is complete (lane 31): *row_best
+	// rH/rI/rB: outputs of the left lane from the previous step (ignored by lane 0 of pass 0).
+	// Returns the row this lane just finished (or -1); outB then holds the best value of that row over all columns up
+	// to and including this lane's -- complete in lane 31 of the last pass, which feeds the ExtTracker.
 	template <class Env>
-	NSW_HD bool step(const LaneGeom &g, const Par &par, int t, int rH, int rI, int rB, Env &env, int *row_i, int *row_best)
+	NSW_HD int step(const LaneGeom &g, const Par &par, int t, int rH, int rI, int rB, Env &env)
 	{
 		const int i = t - g.lane + 2;
-		const uint32_t w_m2 = w_m1;
-		w_m1 = w_0, w_0 = w_p1, w_p1 = w_pre;
-		w_pre = env.row_word(i + 2);
+		const RowRec rc = nxt;
+		nxt = env.row_rec(i + 1);
 		const bool row_ok = i >= 2 && i < g.nl;
 		if (g.lane == 0) {
-			if (g.pass == 0) { // boundary column -1 (nasw-sse.c:253-271)
+			if (!MULTI || g.pass == 0) { // boundary column -1 (nasw-sse.c:253-271): real values only while i == 2
 				rH = NEG, rI = NEG, rB = INT32_MIN;
 				L3 = i == 2 ? 0 : NEG, L2 = L1 = i == 2 ? -par.fs : NEG;
 			} else if (row_ok) env.carry_load3(i, rH, rI, rB);
 		}
-		if (!row_ok) return false;
+		if (!row_ok) return -1;
 		if (g.live) {
-			const RowConst rc = row_const(par, w_m2, w_m1, w_0, w_p1);
 			const int *ps = env.profile(rc.nas);
 			int l0 = rH, l1 = L1, l2 = L2, l3 = L3, it = rI, best = rB;
 			int hn[C], dn[C];
@@ -280,21 +291,18 @@ struct ExtLane {
 			for (int k = 0; k < C; ++k) H3[k] = H2[k], H2[k] = H1[k], H1[k] = hn[k], D3[k] = D2[k], D2[k] = D1[k], D1[k] = dn[k];
 			outH = hn[C - 1], outI = it, outB = best;
 		} else outB = rB;
-		if (g.lane != 0 || g.pass > 0) L3 = L2, L2 = L1, L1 = rH;
-		if (g.lane == 31) {
-			if (g.pass == g.n_pass - 1) { *row_i = i, *row_best = outB; return true; }
-			env.carry_store3(i, outH, outI, outB);
-		}
-		return false;
+		if (g.lane != 0 || (MULTI && g.pass > 0)) L3 = L2, L2 = L1, L1 = rH;
+		if (MULTI && g.lane == 31 && g.pass < g.n_pass - 1) env.carry_store3(i, outH, outI, outB);
+		return i;
 	}
 };
 
-template <int C>
+template <int C, bool MULTI>
 struct TbLane {
 	int H1[C], H2[C], H3[C], D1[C], D2[C], D3[C], A[C], B[C], Cc[C];
 	int L1, L2, L3;
 	int outH, outF, outS, outI;
-	uint32_t w_m1, w_0, w_p1, w_pre;
+	RowRec nxt;
 	uint32_t seg_start;      // bit k: column col0+k starts a stripe segment of the reference layout
 	int k_end;               // which of my columns is al-1 (or -1)
 	int score;               // H(nl-1, al-1) once seen
@@ -304,6 +312,7 @@ struct TbLane {
 	{
 		const int slen = g.W8 / 8;
 		seg_start = 0, k_end = -1, score = NEG;
+#pragma unroll
 		for (int k = 0; k < C; ++k) {
 			H1[k] = H2[k] = H3[k] = D1[k] = D2[k] = D3[k] = A[k] = B[k] = Cc[k] = NEG;
 			if (slen > 0 && (g.col0 + k) % slen == 0) seg_start |= 1u << k;
@@ -311,8 +320,7 @@ struct TbLane {
 		}
 		L1 = L2 = L3 = NEG;
 		outH = outF = outS = outI = NEG;
-		const int i_first = 2 - g.lane;
-		w_m1 = env.row_word(i_first - 2), w_0 = env.row_word(i_first - 1), w_p1 = env.row_word(i_first), w_pre = env.row_word(i_first + 1);
+		nxt = env.row_rec(2 - g.lane);
 	}
 
 	// wd[] receives the C traceback words when the function returns true
@@ -320,12 +328,11 @@ struct TbLane {
 	NSW_HD bool step(const LaneGeom &g, const Par &par, int t, int rH, int rF, int rS, int rI, Env &env, uint32_t *wd)
 	{
 		const int i = t - g.lane + 2;
-		const uint32_t w_m2 = w_m1;
-		w_m1 = w_0, w_0 = w_p1, w_p1 = w_pre;
-		w_pre = env.row_word(i + 2);
+		const RowRec rc = nxt;
+		nxt = env.row_rec(i + 1);
 		const bool row_ok = i >= 2 && i < g.nl;
 		if (g.lane == 0) {
-			if (g.pass == 0) {
+			if (!MULTI || g.pass == 0) {
 				rH = rF = rS = rI = NEG;
 				L3 = i == 2 ? 0 : NEG, L2 = L1 = i == 2 ? -par.fs : NEG;
 			} else if (row_ok) env.carry_load4(i, rH, rF, rS, rI);
@@ -333,7 +340,6 @@ struct TbLane {
 		if (!row_ok) return false;
 		bool wrote = false;
 		if (g.live) {
-			const RowConst rc = row_const(par, w_m2, w_m1, w_0, w_p1);
 			const int *ps = env.profile(rc.nas);
 			int l0 = rH, f0 = rF, l1 = L1, l2 = L2, l3 = L3, iseg = rS, it = rI;
 			int hn[C], dn[C];
@@ -353,8 +359,8 @@ struct TbLane {
 			outH = hn[C - 1], outF = f0, outS = iseg, outI = it;
 			wrote = true;
 		}
-		if (g.lane != 0 || g.pass > 0) L3 = L2, L2 = L1, L1 = rH;
-		if (g.lane == 31 && g.pass < g.n_pass - 1) env.carry_store4(i, outH, outF, outS, outI);
+		if (g.lane != 0 || (MULTI && g.pass > 0)) L3 = L2, L2 = L1, L1 = rH;
+		if (MULTI && g.lane == 31 && g.pass < g.n_pass - 1) env.carry_store4(i, outH, outF, outS, outI);
 		return wrote;
 	}
 };

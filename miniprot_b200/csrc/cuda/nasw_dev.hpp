@@ -14,7 +14,8 @@ namespace mpb {
 namespace cuda {
 
 constexpr int NASW_WARPS = 4;   // problems per CTA (one warp each)
-constexpr int NASW_CMAX = 8;    // columns per lane in the widest instantiation (32*8 = 256 columns per pass)
+constexpr int NASW_CMAX = 8;
+constexpr int PREP_ROWS = 4096; // rows per prep CTA    // columns per lane in the widest instantiation (32*8 = 256 columns per pass)
 
 struct DpDev {                  // one DP problem, resident in HBM for the duration of a wave
 	int64_t g_start;            // nibble index (packed genome) of DP row 0
@@ -23,7 +24,7 @@ struct DpDev {                  // one DP problem, resident in HBM for the durat
 	int32_t aa_off;             // first residue of the protein slice in the batch residue buffer
 	int32_t flag, io;
 	int32_t C;                  // columns per lane chosen for this problem (1, 2, 4 or 8)
-	int64_t rw_off;             // row words: nl + 1 entries
+	int64_t rw_off;             // row records (32 B each): nl + 1 entries, offset in rows
 	int64_t tb_off;             // traceback words (uint16 units); tb problems only
 	int64_t cig_off;            // CIGAR slot
 	int32_t cig_cap;
@@ -44,9 +45,9 @@ struct NaswConst {              // problem-independent parameters, passed by val
 	nsw::PenTable pen;          // extension length penalty as a step table (nasw-sse.c:426, FP32 done on the host)
 };
 
-void nasw_launch_prep(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, uint32_t *rw);
-void nasw_launch_ext(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const uint32_t *rw, const char *aa, const NaswConst &cst, int4 *out, int *carry);
-void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const uint32_t *rw, const char *aa, const NaswConst &cst, int4 *out, int *carry,
+void nasw_launch_prep(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, int4 *rec);
+void nasw_launch_ext(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, int *carry);
+void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, int *carry,
                     uint16_t *tb);
 void nasw_launch_bt(cudaStream_t st, const DpDev *jobs, const int *order, int n, const uint16_t *tb, uint32_t *cigar, int4 *out);
 

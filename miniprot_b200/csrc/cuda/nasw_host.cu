@@ -43,7 +43,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	cudaStream_t st = ctx->stream;
 	int64_t rw_tot = 0, tb_tot = 0, cig_tot = 0, carry_tot = 0;
 	std::vector<PrepChunk> chunks;
-	std::vector<int> order[2][4]; // [is_tb][log2 C]
+	std::vector<int> order[2][5]; // [is_tb][log2 C; 4 = multi-pass]
 	for (int k = 0; k < n; ++k) {
 		DpDev &j = jobs[lo + k];
 		const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
@@ -57,15 +57,15 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 			j.cig_off = cig_tot, cig_tot += j.cig_cap;
 		}
 		if (n_pass > 1) j.carry_off = carry_tot, carry_tot += ((int64_t)j.nl + 1) * 4;
-		for (int r = 0; r <= j.nl; r += 4096) chunks.push_back(PrepChunk{ k, r, std::min(4096, j.nl + 1 - r), 0 });
-		order[is_tb][j.C == 1 ? 0 : j.C == 2 ? 1 : j.C == 4 ? 2 : 3].push_back(k);
+		for (int r = 0; r <= j.nl; r += PREP_ROWS) chunks.push_back(PrepChunk{ k, r, std::min(PREP_ROWS, j.nl + 1 - r), 0 });
+		order[is_tb][n_pass > 1 ? 4 : j.C == 1 ? 0 : j.C == 2 ? 1 : j.C == 4 ? 2 : 3].push_back(k);
 		(is_tb ? ctx->stats.dp_cells_tb : ctx->stats.dp_cells_ext) += (int64_t)j.nl * j.al;
 		(is_tb ? ctx->stats.n_dp_tb : ctx->stats.n_dp_ext) += 1;
 	}
 	std::vector<int> flat;
-	size_t first[2][4], count[2][4];
+	size_t first[2][5], count[2][5];
 	for (int b = 0; b < 2; ++b)
-		for (int c = 0; c < 4; ++c) {
+		for (int c = 0; c < 5; ++c) {
 			std::vector<int> &v = order[b][c];
 			std::stable_sort(v.begin(), v.end(), [&](int x, int y) { return jobs[lo + x].nl > jobs[lo + y].nl; });
 			first[b][c] = flat.size(), count[b][c] = v.size();
@@ -74,7 +74,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	ctx->b_jobs.reserve(sizeof(DpDev) * n);
 	ctx->b_order.reserve(sizeof(int) * (flat.size() + 1));
 	ctx->b_chunks.reserve(sizeof(PrepChunk) * (chunks.size() + 1));
-	ctx->b_rw.reserve(sizeof(uint32_t) * (size_t)(rw_tot + 4));
+	ctx->b_rw.reserve(32 * (size_t)(rw_tot + 4));
 	ctx->b_out.reserve(sizeof(int4) * n);
 	ctx->b_carry.reserve(sizeof(int) * (size_t)(carry_tot + 4));
 	ctx->b_tb.reserve(sizeof(uint16_t) * (size_t)(tb_tot + 8));
@@ -87,25 +87,25 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	ctx->stats.h2d_bytes += sizeof(DpDev) * n + sizeof(int) * flat.size() + sizeof(PrepChunk) * chunks.size();
 	const DpDev *dj = ctx->b_jobs.as<DpDev>();
 	const int *dord = ctx->b_order.as<int>();
-	nasw_launch_prep(st, dj, ctx->b_chunks.as<PrepChunk>(), (int)chunks.size(), packed, cst, ctx->b_rw.as<uint32_t>());
+	nasw_launch_prep(st, dj, ctx->b_chunks.as<PrepChunk>(), (int)chunks.size(), packed, cst, ctx->b_rw.as<int4>());
 	ctx->stats.kernel_launches += 1;
-	static const int Cs[4] = { 1, 2, 4, 8 };
+	static const int Cs[5] = { 1, 2, 4, 8, 16 };
 	// fork: every (kind, size class) runs on its own stream -- each is bounded by its longest problem
 	MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
-	bool used[mpb_ctx_s::N_SIDE] = { false };
+	bool used[mpb_ctx_s::N_SIDE] = { false }, is_ext_sid[mpb_ctx_s::N_SIDE] = { false };
 	for (int b = 0; b < 2; ++b)
-		for (int c = 3; c >= 0; --c) {
+		for (int c = 4; c >= 0; --c) {
 			if (!count[b][c]) continue;
-			const int sid = b * 4 + c;
+			const int sid = (b * 5 + c) % mpb_ctx_s::N_SIDE;
 			cudaStream_t ss = ctx->side[sid];
-			used[sid] = true;
+			used[sid] = true, is_ext_sid[sid] = b == 0;
 			MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
 			MPB_CUDA_OK(cudaEventRecord(ctx->ev_k0[sid], ss));
 			if (b == 0) {
-				nasw_launch_ext(ss, Cs[c], dj, dord + first[0][c], (int)count[0][c], ctx->b_rw.as<uint32_t>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>());
+				nasw_launch_ext(ss, Cs[c], dj, dord + first[0][c], (int)count[0][c], ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>());
 				ctx->stats.kernel_launches += 1;
 			} else {
-				nasw_launch_tb(ss, Cs[c], dj, dord + first[1][c], (int)count[1][c], ctx->b_rw.as<uint32_t>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>(),
+				nasw_launch_tb(ss, Cs[c], dj, dord + first[1][c], (int)count[1][c], ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>(),
 				               ctx->b_tb.as<uint16_t>());
 				nasw_launch_bt(ss, dj, dord + first[1][c], (int)count[1][c], ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
 				ctx->stats.kernel_launches += 2;
@@ -122,7 +122,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		if (used[sid]) { // sum of the classes' own durations (they overlap in time; the wave's wall time is what the step pays)
 			float ms = 0;
 			cudaEventElapsedTime(&ms, ctx->ev_k0[sid], ctx->ev_k1[sid]);
-			(sid < 4 ? ctx->stats.ms_dp_ext : ctx->stats.ms_dp_tb) += ms;
+			(is_ext_sid[sid] ? ctx->stats.ms_dp_ext : ctx->stats.ms_dp_tb) += ms;
 		}
 	ctx->stats.d2h_bytes += sizeof(int4) * n + sizeof(uint32_t) * (size_t)cig_tot;
 	const int4 *ho = ctx->h_out.as<int4>();
@@ -153,7 +153,7 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_
 			const DpDev &j = jobs[hi];
 			const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
 			const int C = pick_C(j.al), Wp = 32 * C, W8 = (j.al + 7) / 8 * 8, n_pass = (W8 + Wp - 1) / Wp;
-			const size_t tbb = is_tb ? (size_t)n_pass * (size_t)(j.nl + 30) * Wp * 2 : 0, rwb = (size_t)(j.nl + 4) * 4;
+			const size_t tbb = is_tb ? (size_t)n_pass * (size_t)(j.nl + 30) * Wp * 2 : 0, rwb = (size_t)(j.nl + 4) * 32;
 			if (hi > lo && (tb_bytes + tbb > kTbBudget || rw_bytes + rwb > kRwBudget)) break;
 			tb_bytes += tbb, rw_bytes += rwb, ++hi;
 		}

@@ -36,19 +36,30 @@ __device__ __forceinline__ int job_code(const uint8_t *packed, const DpDev &j, i
 }
 
 // ------------------------------------------------------------------ prep
+// One CTA per chunk of <= PREP_ROWS rows of one problem: phase 1 evaluates the per-row splice / codon rules into shared
+// memory (with a halo of 2 rows before and 1 after), phase 2 combines rows i-2..i+1 into the 32-byte record of row i.
 __global__ void __launch_bounds__(256) nasw_prep_kernel(const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed,
-                                                        NaswConst cst, uint32_t *rw)
+                                                        NaswConst cst, int4 *rec)
 {
+	__shared__ uint32_t w[PREP_ROWS + 4];
 	const int ck = blockIdx.x;
 	if (ck >= n_chunks) return;
 	const PrepChunk c = chunks[ck];
 	const DpDev job = jobs[c.job];
 	auto code = [&](int k) { return job_code(packed, job, k); };
-	for (int r = c.row0 + (int)threadIdx.x; r < c.row0 + c.n_rows; r += blockDim.x) { // rows 0..nl inclusive
-		uint32_t w;
-		if (job.flag & NS_F_EXT_LEFT) w = prep_row_left(code, job.nl, r, cst.sp, cst.codon, cst.aa_x);
-		else w = prep_row_forward(code, job.nl, r, cst.sp, cst.codon, cst.aa_x);
-		rw[job.rw_off + r] = w;
+	for (int x = threadIdx.x; x < c.n_rows + 3; x += blockDim.x) { // smem slot x <-> row c.row0 - 2 + x
+		int r = c.row0 - 2 + x;
+		r = r < 0 ? 0 : (r > job.nl ? job.nl : r);
+		w[x] = (job.flag & NS_F_EXT_LEFT) ? prep_row_left(code, job.nl, r, cst.sp, cst.codon, cst.aa_x) : prep_row_forward(code, job.nl, r, cst.sp, cst.codon, cst.aa_x);
+	}
+	__syncthreads();
+	Par par;
+	par.go = cst.go, par.ge = cst.ge, par.io = job.io, par.fs = cst.fs, par.gei_stop = cst.fs;
+	for (int x = threadIdx.x; x < c.n_rows; x += blockDim.x) {
+		const RowRec r = make_row_rec(par, w[x], w[x + 1], w[x + 2], w[x + 3]);
+		int4 *dst = rec + (job.rw_off + c.row0 + x) * 2;
+		dst[0] = make_int4(r.cA, r.cB, r.cC, r.gei);
+		dst[1] = make_int4(r.aA, r.aB, r.aC, r.nas);
 	}
 }
 
@@ -75,12 +86,19 @@ __device__ __forceinline__ void build_profile(int *prof, int Wp, int pass, const
 
 // what a lane needs from its surroundings (see nasw_core.cuh ExtLane/TbLane)
 struct DevEnv {
-	const uint32_t *rw;  // row words of this problem
+	const int4 *rec;     // row records of this problem (2 x int4 per row)
 	int nl;
 	const int *prof;     // profile of this warp for this pass, already offset to the lane's first column
 	int Wp;
 	int *cy;             // per-row carry between column passes
-	__device__ __forceinline__ uint32_t row_word(int i) const { i = i < 0 ? 0 : (i > nl ? nl : i); return __ldg(rw + i); }
+	__device__ __forceinline__ RowRec row_rec(int i) const
+	{
+		i = i < 0 ? 0 : (i > nl ? nl : i);
+		const int4 a = __ldg(rec + 2 * i), b = __ldg(rec + 2 * i + 1);
+		RowRec r;
+		r.cA = a.x, r.cB = a.y, r.cC = a.z, r.gei = a.w, r.aA = b.x, r.aB = b.y, r.aC = b.z, r.nas = b.w;
+		return r;
+	}
 	__device__ __forceinline__ const int *profile(int nas) const { return prof + nas * Wp; }
 	__device__ __forceinline__ void carry_load3(int i, int &a, int &b, int &c) const { a = cy[(int64_t)i * 3], b = cy[(int64_t)i * 3 + 1], c = cy[(int64_t)i * 3 + 2]; }
 	__device__ __forceinline__ void carry_store3(int i, int a, int b, int c) const { cy[(int64_t)i * 3] = a, cy[(int64_t)i * 3 + 1] = b, cy[(int64_t)i * 3 + 2] = c; }
@@ -93,8 +111,8 @@ struct DevEnv {
 };
 
 // ------------------------------------------------------------------ extension (score only)
-template <int C>
-__global__ void __launch_bounds__(NASW_WARPS * 32) nasw_ext_kernel(const DpDev *jobs, const int *order, int n_jobs, const uint32_t *rw, const char *aa,
+template <int C, bool MULTI>
+__global__ void __launch_bounds__(NASW_WARPS * 32) nasw_ext_kernel(const DpDev *jobs, const int *order, int n_jobs, const int4 *rec, const char *aa,
                                                                   NaswConst cst, int4 *out, int *carry)
 {
 	extern __shared__ int smem[];
@@ -114,19 +132,19 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_ext_kernel(const DpDev *
 	ExtTracker trk;
 	trk.init();
 	DevEnv env;
-	env.rw = rw + job.rw_off, env.nl = g.nl, env.prof = prof + lane * C, env.Wp = Wp, env.cy = carry + job.carry_off;
+	env.rec = rec + job.rw_off * 2, env.nl = g.nl, env.prof = prof + lane * C, env.Wp = Wp, env.cy = carry + job.carry_off;
 
 	for (int pass = 0; pass < g.n_pass; ++pass) {
 		build_profile(prof, Wp, pass, aa, cst, job, lane);
 		g.pass = pass, g.col0 = pass * Wp + lane * C, g.live = g.col0 < g.W8;
-		ExtLane<C> L;
+		ExtLane<C, MULTI> L;
 		L.init(g, cst.end_bonus, env);
 		for (int t = 0; t < T; ++t) {
 			const int rH = __shfl_up_sync(0xffffffffu, L.outH, 1);
 			const int rI = __shfl_up_sync(0xffffffffu, L.outI, 1);
 			const int rB = __shfl_up_sync(0xffffffffu, L.outB, 1);
-			int row_i, row_best;
-			if (L.step(g, par, t, rH, rI, rB, env, &row_i, &row_best)) trk.row(row_i, row_best, g.al * 3, cst.pen, cst.xdrop);
+			const int row_i = L.step(g, par, t, rH, rI, rB, env);
+			if (row_i >= 0 && pass == g.n_pass - 1) trk.row(row_i, L.outB, g.al * 3, cst.pen, cst.xdrop); // only lane 31's tracker is read
 			if (pass == g.n_pass - 1 && (t & 15) == 15) {
 				if (__shfl_sync(0xffffffffu, (int)trk.stopped, 31)) break;
 			}
@@ -143,8 +161,8 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_ext_kernel(const DpDev *
 }
 
 // ------------------------------------------------------------------ global alignment with traceback
-template <int C>
-__global__ void __launch_bounds__(NASW_WARPS * 32) nasw_tb_kernel(const DpDev *jobs, const int *order, int n_jobs, const uint32_t *rw, const char *aa,
+template <int C, bool MULTI>
+__global__ void __launch_bounds__(NASW_WARPS * 32) nasw_tb_kernel(const DpDev *jobs, const int *order, int n_jobs, const int4 *rec, const char *aa,
                                                                  NaswConst cst, int4 *out, int *carry, uint16_t *tb)
 {
 	extern __shared__ int smem[];
@@ -162,13 +180,13 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_tb_kernel(const DpDev *j
 	Par par;
 	par.go = cst.go, par.ge = cst.ge, par.io = job.io, par.fs = cst.fs, par.gei_stop = cst.fs;
 	DevEnv env;
-	env.rw = rw + job.rw_off, env.nl = g.nl, env.prof = prof + lane * C, env.Wp = Wp, env.cy = carry + job.carry_off;
+	env.rec = rec + job.rw_off * 2, env.nl = g.nl, env.prof = prof + lane * C, env.Wp = Wp, env.cy = carry + job.carry_off;
 	int score = NEG;
 
 	for (int pass = 0; pass < g.n_pass; ++pass) {
 		build_profile(prof, Wp, pass, aa, cst, job, lane);
 		g.pass = pass, g.col0 = pass * Wp + lane * C, g.live = g.col0 < g.W8;
-		TbLane<C> L;
+		TbLane<C, MULTI> L;
 		L.init(g, env);
 		uint16_t *tbp = tb + job.tb_off + (int64_t)pass * T * Wp + lane * C;
 		for (int t = 0; t < T; ++t) {
@@ -244,50 +262,53 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_bt_kernel(const DpDev *j
 }
 
 // ------------------------------------------------------------------ launchers
-template <int C>
-static void launch_ext(cudaStream_t st, const DpDev *jobs, const int *order, int n, const uint32_t *rw, const char *aa, const NaswConst &cst, int4 *out, int *carry)
+template <int C, bool MULTI>
+static void launch_ext(cudaStream_t st, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, int *carry)
 {
 	const int smem = NASW_WARPS * 22 * 32 * C * (int)sizeof(int);
 	static bool attr_set = false;
-	if (!attr_set) { cudaFuncSetAttribute(nasw_ext_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-	nasw_ext_kernel<C><<<(n + NASW_WARPS - 1) / NASW_WARPS, NASW_WARPS * 32, smem, st>>>(jobs, order, n, rw, aa, cst, out, carry);
+	if (!attr_set) { cudaFuncSetAttribute(nasw_ext_kernel<C, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+	nasw_ext_kernel<C, MULTI><<<(n + NASW_WARPS - 1) / NASW_WARPS, NASW_WARPS * 32, smem, st>>>(jobs, order, n, rec, aa, cst, out, carry);
 }
 
-template <int C>
-static void launch_tb(cudaStream_t st, const DpDev *jobs, const int *order, int n, const uint32_t *rw, const char *aa, const NaswConst &cst, int4 *out, int *carry,
+template <int C, bool MULTI>
+static void launch_tb(cudaStream_t st, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, int *carry,
                       uint16_t *tb)
 {
 	const int smem = NASW_WARPS * 22 * 32 * C * (int)sizeof(int);
 	static bool attr_set = false;
-	if (!attr_set) { cudaFuncSetAttribute(nasw_tb_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-	nasw_tb_kernel<C><<<(n + NASW_WARPS - 1) / NASW_WARPS, NASW_WARPS * 32, smem, st>>>(jobs, order, n, rw, aa, cst, out, carry, tb);
+	if (!attr_set) { cudaFuncSetAttribute(nasw_tb_kernel<C, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+	nasw_tb_kernel<C, MULTI><<<(n + NASW_WARPS - 1) / NASW_WARPS, NASW_WARPS * 32, smem, st>>>(jobs, order, n, rec, aa, cst, out, carry, tb);
 }
 
-void nasw_launch_prep(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, uint32_t *rw)
+void nasw_launch_prep(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, int4 *rec)
 {
-	if (n_chunks > 0) nasw_prep_kernel<<<n_chunks, 256, 0, st>>>(jobs, chunks, n_chunks, packed, cst, rw);
+	if (n_chunks > 0) nasw_prep_kernel<<<n_chunks, 256, 0, st>>>(jobs, chunks, n_chunks, packed, cst, rec);
 }
 
-void nasw_launch_ext(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const uint32_t *rw, const char *aa, const NaswConst &cst, int4 *out, int *carry)
+// C = 1, 2, 4, 8: single-pass problems (at most 32*C padded columns); C = 16 stands for "8 columns per lane, several passes"
+void nasw_launch_ext(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, int *carry)
 {
 	if (n <= 0) return;
 	switch (C) {
-	case 1: launch_ext<1>(st, jobs, order, n, rw, aa, cst, out, carry); break;
-	case 2: launch_ext<2>(st, jobs, order, n, rw, aa, cst, out, carry); break;
-	case 4: launch_ext<4>(st, jobs, order, n, rw, aa, cst, out, carry); break;
-	default: launch_ext<8>(st, jobs, order, n, rw, aa, cst, out, carry); break;
+	case 1: launch_ext<1, false>(st, jobs, order, n, rec, aa, cst, out, carry); break;
+	case 2: launch_ext<2, false>(st, jobs, order, n, rec, aa, cst, out, carry); break;
+	case 4: launch_ext<4, false>(st, jobs, order, n, rec, aa, cst, out, carry); break;
+	case 8: launch_ext<8, false>(st, jobs, order, n, rec, aa, cst, out, carry); break;
+	default: launch_ext<8, true>(st, jobs, order, n, rec, aa, cst, out, carry); break;
 	}
 }
 
-void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const uint32_t *rw, const char *aa, const NaswConst &cst, int4 *out, int *carry,
+void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, int *carry,
                     uint16_t *tb)
 {
 	if (n <= 0) return;
 	switch (C) {
-	case 1: launch_tb<1>(st, jobs, order, n, rw, aa, cst, out, carry, tb); break;
-	case 2: launch_tb<2>(st, jobs, order, n, rw, aa, cst, out, carry, tb); break;
-	case 4: launch_tb<4>(st, jobs, order, n, rw, aa, cst, out, carry, tb); break;
-	default: launch_tb<8>(st, jobs, order, n, rw, aa, cst, out, carry, tb); break;
+	case 1: launch_tb<1, false>(st, jobs, order, n, rec, aa, cst, out, carry, tb); break;
+	case 2: launch_tb<2, false>(st, jobs, order, n, rec, aa, cst, out, carry, tb); break;
+	case 4: launch_tb<4, false>(st, jobs, order, n, rec, aa, cst, out, carry, tb); break;
+	case 8: launch_tb<8, false>(st, jobs, order, n, rec, aa, cst, out, carry, tb); break;
+	default: launch_tb<8, true>(st, jobs, order, n, rec, aa, cst, out, carry, tb); break;
 	}
 }
 

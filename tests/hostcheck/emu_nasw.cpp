@@ -16,12 +16,12 @@ using namespace nsw;
 namespace {
 
 struct EmuEnv {
-	const uint32_t *rw;
+	const RowRec *rec;
 	int nl;
 	const int *prof; // offset to the lane's first column
 	int Wp;
 	int *cy;
-	uint32_t row_word(int i) const { i = i < 0 ? 0 : (i > nl ? nl : i); return rw[i]; }
+	RowRec row_rec(int i) const { i = i < 0 ? 0 : (i > nl ? nl : i); return rec[i]; }
 	const int *profile(int nas) const { return prof + nas * Wp; }
 	void carry_load3(int i, int &a, int &b, int &c) const { a = cy[(int64_t)i * 3], b = cy[(int64_t)i * 3 + 1], c = cy[(int64_t)i * 3 + 2]; }
 	void carry_store3(int i, int a, int b, int c) const { cy[(int64_t)i * 3] = a, cy[(int64_t)i * 3 + 1] = b, cy[(int64_t)i * 3 + 2] = c; }
@@ -30,7 +30,7 @@ struct EmuEnv {
 };
 
 struct Problem {
-	std::vector<uint32_t> rw;
+	std::vector<RowRec> rec;
 	std::vector<int> aas;
 	int nl, al, W8;
 	Par par;
@@ -39,7 +39,7 @@ struct Problem {
 	float ie_coef;
 };
 
-template <int C>
+template <int C, bool MULTI>
 void run_ext(const Problem &P, int *score, int *nt_len, int *aa_len)
 {
 	const int Wp = 32 * C, n_pass = (P.W8 + Wp - 1) / Wp, T = P.nl > 2 ? P.nl - 2 + 32 : 0;
@@ -51,29 +51,32 @@ void run_ext(const Problem &P, int *score, int *nt_len, int *aa_len)
 	for (int pass = 0; pass < n_pass; ++pass) {
 		for (int j = 0; j < Wp; ++j)
 			for (int a = 0; a < 22; ++a) prof[a * Wp + j] = pass * Wp + j < P.al ? P.mat[a * 22 + P.aas[pass * Wp + j]] : NEG;
-		ExtLane<C> L[32];
+		ExtLane<C, MULTI> L[32];
+		ExtTracker trks[32];
+		for (int l = 0; l < 32; ++l) trks[l] = trk;
 		LaneGeom g[32];
 		EmuEnv env[32];
 		for (int l = 0; l < 32; ++l) {
 			g[l].lane = l, g[l].pass = pass, g[l].n_pass = n_pass, g[l].nl = P.nl, g[l].al = P.al, g[l].W8 = P.W8, g[l].col0 = pass * Wp + l * C, g[l].live = g[l].col0 < P.W8;
-			env[l].rw = P.rw.data(), env[l].nl = P.nl, env[l].prof = prof.data() + l * C, env[l].Wp = Wp, env[l].cy = cy.data();
+			env[l].rec = P.rec.data(), env[l].nl = P.nl, env[l].prof = prof.data() + l * C, env[l].Wp = Wp, env[l].cy = cy.data();
 			L[l].init(g[l], P.end_bonus, env[l]);
 		}
 		for (int t = 0; t < T; ++t) {
 			int rH[32], rI[32], rB[32];
 			for (int l = 0; l < 32; ++l) { const int s = l ? l - 1 : 0; rH[l] = L[s].outH, rI[l] = L[s].outI, rB[l] = L[s].outB; } // __shfl_up_sync(.., 1)
 			for (int l = 0; l < 32; ++l) {
-				int ri, rb;
-				if (L[l].step(g[l], P.par, t, rH[l], rI[l], rB[l], env[l], &ri, &rb)) trk.row(ri, rb, P.al * 3, pt, P.xdrop);
+				const int ri = L[l].step(g[l], P.par, t, rH[l], rI[l], rB[l], env[l]);
+				if (ri >= 0 && pass == n_pass - 1) trks[l].row(ri, L[l].outB, P.al * 3, pt, P.xdrop); // every lane tracks; lane 31 counts
 			}
-			if (pass == n_pass - 1 && (t & 15) == 15 && trk.stopped) break;
+			if (pass == n_pass - 1 && (t & 15) == 15 && trks[31].stopped) break;
 		}
+		trk = trks[31];
 	}
 	*score = trk.max_sc, *nt_len = trk.max_i + 1;
 	*aa_len = (trk.max_i >= 0 && trk.max_code != 0) ? 4095 - trk.max_code + 1 : P.al + 1;
 }
 
-template <int C>
+template <int C, bool MULTI>
 void run_tb(const Problem &P, int *score, std::vector<uint32_t> &cigar)
 {
 	const int Wp = 32 * C, n_pass = (P.W8 + Wp - 1) / Wp, T = P.nl > 2 ? P.nl - 2 + 32 : 0;
@@ -83,12 +86,12 @@ void run_tb(const Problem &P, int *score, std::vector<uint32_t> &cigar)
 	for (int pass = 0; pass < n_pass; ++pass) {
 		for (int j = 0; j < Wp; ++j)
 			for (int a = 0; a < 22; ++a) prof[a * Wp + j] = pass * Wp + j < P.al ? P.mat[a * 22 + P.aas[pass * Wp + j]] : NEG;
-		TbLane<C> L[32];
+		TbLane<C, MULTI> L[32];
 		LaneGeom g[32];
 		EmuEnv env[32];
 		for (int l = 0; l < 32; ++l) {
 			g[l].lane = l, g[l].pass = pass, g[l].n_pass = n_pass, g[l].nl = P.nl, g[l].al = P.al, g[l].W8 = P.W8, g[l].col0 = pass * Wp + l * C, g[l].live = g[l].col0 < P.W8;
-			env[l].rw = P.rw.data(), env[l].nl = P.nl, env[l].prof = prof.data() + l * C, env[l].Wp = Wp, env[l].cy = cy.data();
+			env[l].rec = P.rec.data(), env[l].nl = P.nl, env[l].prof = prof.data() + l * C, env[l].Wp = Wp, env[l].cy = cy.data();
 			L[l].init(g[l], env[l]);
 		}
 		for (int t = 0; t < T; ++t) {
@@ -148,26 +151,32 @@ extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *
 	std::vector<int> code((size_t)nl);
 	for (int k = 0; k < nl; ++k) code[(size_t)k] = nt4[ns[left ? nl - 1 - k : k]];
 	auto c = [&](int k) { return code[(size_t)k]; };
-	P.rw.resize((size_t)nl + 1);
-	for (int r = 0; r <= nl; ++r) P.rw[(size_t)r] = left ? prep_row_left(c, nl, r, sp, codon, aa20['X']) : prep_row_forward(c, nl, r, sp, codon, aa20['X']);
+	std::vector<uint32_t> w((size_t)nl + 4);
+	for (int x = 0; x < nl + 4; ++x) { // slot x <-> row x - 2, clamped like the prep kernel
+		int r = x - 2;
+		r = r < 0 ? 0 : (r > nl ? nl : r);
+		w[(size_t)x] = left ? prep_row_left(c, nl, r, sp, codon, aa20['X']) : prep_row_forward(c, nl, r, sp, codon, aa20['X']);
+	}
+	P.rec.resize((size_t)nl + 1);
+	for (int r = 0; r <= nl; ++r) P.rec[(size_t)r] = make_row_rec(P.par, w[(size_t)r], w[(size_t)r + 1], w[(size_t)r + 2], w[(size_t)r + 3]);
 	P.aas.resize((size_t)al);
 	for (int j = 0; j < al; ++j) P.aas[(size_t)j] = aa20[(uint8_t)as[left ? al - 1 - j : j]];
 	*nt_len = nl, *aa_len = al;
 	int n_cig = 0;
 	if (flag & 6) {
 		switch (C) {
-		case 1: run_ext<1>(P, score, nt_len, aa_len); break;
-		case 2: run_ext<2>(P, score, nt_len, aa_len); break;
-		case 4: run_ext<4>(P, score, nt_len, aa_len); break;
-		default: run_ext<8>(P, score, nt_len, aa_len); break;
+		case 1: P.W8 <= 32 ? run_ext<1, false>(P, score, nt_len, aa_len) : run_ext<1, true>(P, score, nt_len, aa_len); break;
+		case 2: P.W8 <= 64 ? run_ext<2, false>(P, score, nt_len, aa_len) : run_ext<2, true>(P, score, nt_len, aa_len); break;
+		case 4: P.W8 <= 128 ? run_ext<4, false>(P, score, nt_len, aa_len) : run_ext<4, true>(P, score, nt_len, aa_len); break;
+		default: P.W8 <= 256 ? run_ext<8, false>(P, score, nt_len, aa_len) : run_ext<8, true>(P, score, nt_len, aa_len); break;
 		}
 	} else {
 		std::vector<uint32_t> cg;
 		switch (C) {
-		case 1: run_tb<1>(P, score, cg); break;
-		case 2: run_tb<2>(P, score, cg); break;
-		case 4: run_tb<4>(P, score, cg); break;
-		default: run_tb<8>(P, score, cg); break;
+		case 1: P.W8 <= 32 ? run_tb<1, false>(P, score, cg) : run_tb<1, true>(P, score, cg); break;
+		case 2: P.W8 <= 64 ? run_tb<2, false>(P, score, cg) : run_tb<2, true>(P, score, cg); break;
+		case 4: P.W8 <= 128 ? run_tb<4, false>(P, score, cg) : run_tb<4, true>(P, score, cg); break;
+		default: P.W8 <= 256 ? run_tb<8, false>(P, score, cg) : run_tb<8, true>(P, score, cg); break;
 		}
 		n_cig = (int)cg.size();
 		for (int k = 0; k < n_cig && k < cigar_cap; ++k) cigar[k] = cg[(size_t)k];
