@@ -286,6 +286,7 @@ def main():
         "dp_gcell_per_s": cells / (ms / args.steps / 1e3) / 1e9 * world,
         "stage_ms_per_step": {"seed": st.ms_seed / args.steps, "chain": st.ms_chain / args.steps, "refine": st.ms_refine / args.steps,
                               "dp_ext": st.ms_dp_ext / args.steps, "dp_tb": st.ms_dp_tb / args.steps},
+        "wall_ms_per_step": dict(zip(["S1_seed_chain", "H1_regions", "S2_refine", "H2_plan", "S3_dp_waves", "H3_finish"], [w / args.steps for w in st.ms_wall])),
         "e2e": {"value": e2e, "unit": "proteins/s", "h2d_bytes_per_step": st2.h2d_bytes // args.steps, "d2h_bytes_per_step": st2.d2h_bytes // args.steps,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(st.kernel_launches), "roofline": roofline, "int_rate": int_rate, "cpu_baseline": cpu, "clocks": sampler.summary()}))

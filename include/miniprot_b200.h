@@ -261,7 +261,8 @@ typedef struct {
 	int64_t n_anchors, n_chain_problems, n_refine_regions;
 	int64_t kernel_launches;
 	int64_t h2d_bytes, d2h_bytes;
-	double ms_seed, ms_chain, ms_refine, ms_dp_ext, ms_dp_tb; /* CUDA-event time per stage */
+	double ms_seed, ms_chain, ms_refine, ms_dp_ext, ms_dp_tb; /* CUDA-event time per stage (kernels of one stage may overlap) */
+	double ms_wall[6]; /* host wall clock per dispatcher phase: S1, H1, S2, H2, S3 (three DP waves incl. their host steps), H3 */
 } mpb_stats_t;
 void mpb_get_stats(const mpb_ctx_t *ctx, mpb_stats_t *st);
 void mpb_reset_stats(mpb_ctx_t *ctx);

@@ -56,6 +56,7 @@ struct CudaStages : Stages {
 		return ctx->b_aa.as<char>();
 	}
 
+	void note_wall(int phase, double ms) override { if (phase >= 0 && phase < 6) ctx->stats.ms_wall[phase] += ms; }
 	void seed_chain(const mp_idx_t *mi, const mp_mapopt_t *opt, const Batch &b, ChainSet &out) override
 	{
 		need_index(mi);

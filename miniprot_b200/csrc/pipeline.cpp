@@ -14,6 +14,7 @@
 // Results per protein are identical to mp_map() (no state crosses proteins: SURVEY 8b "determinism contract").
 #include <stdio.h>
 #include <algorithm>
+#include <chrono>
 #include "internal.hpp"
 #include "align.hpp"
 #include "fastx.hpp"
@@ -35,10 +36,17 @@ void map_batch(Stages *st, const mp_idx_t *mi, const mp_mapopt_t *opt, const Bat
 {
 	const int32_t n = b.n, kmer = mi->opt.kmer;
 	std::vector<QueryState> qs((size_t)n);
+	auto t_prev = std::chrono::steady_clock::now();
+	auto lap = [&](int phase) {
+		const auto now = std::chrono::steady_clock::now();
+		st->note_wall(phase, std::chrono::duration<double, std::milli>(now - t_prev).count());
+		t_prev = now;
+	};
 
 	// ---- S1
 	ChainSet cs;
 	st->seed_chain(mi, opt, b, cs);
+	lap(0);
 
 	// ---- H1 + S2 work list
 	std::vector<RefineJob> rjobs;
@@ -66,10 +74,12 @@ void map_batch(Stages *st, const mp_idx_t *mi, const mp_mapopt_t *opt, const Bat
 	}
 	rjob_first[(size_t)n] = (int32_t)rjobs.size();
 	cs = ChainSet(); // first-round anchors are not needed any more
+	lap(1);
 
 	// ---- S2
 	RefineSet rs;
 	st->refine(mi, opt, b, rjobs, rs);
+	lap(2);
 
 	// ---- H2: adopt refined chains (map.c:83-109), re-rank (map.c:217-221)
 	const int32_t k2 = opt->kmer2;
@@ -120,11 +130,13 @@ void map_batch(Stages *st, const mp_idx_t *mi, const mp_mapopt_t *opt, const Bat
 					plans.push_back(std::move(p));
 			}
 		}
+		lap(3);
 		st->nasw(mi, &nso, b, w1, o1);
 		for (RegionPlan &p : plans) p.after_wave1(opt, o1, w1r);
 		st->nasw(mi, &nso, b, w1r, o1r);
 		for (RegionPlan &p : plans) p.after_retry(mi, opt, b.seq[p.qid], o1r, w2);
 		st->nasw(mi, &nso, b, w2, o2);
+		lap(4);
 		for (RegionPlan &p : plans) p.finish(mi, opt, b.seq[p.qid], o1, o2);
 		// ---- H3 (map.c:228-236)
 		for (int32_t q = 0; q < n; ++q) {
@@ -143,6 +155,7 @@ void map_batch(Stages *st, const mp_idx_t *mi, const mp_mapopt_t *opt, const Bat
 		for (int32_t i = 0; i < Q.n_reg; ++i) Q.reg[i].a = 0; // the anchor store dies with this call
 		n_reg_out[q] = Q.n_reg, reg_out[q] = Q.reg;
 	}
+	lap(5);
 }
 
 // map.c:293-326: per protein, hits in rank order subject to --outn / --outs / --outc; unmapped line with -u
