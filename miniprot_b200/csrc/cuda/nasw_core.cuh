@@ -205,14 +205,17 @@ inline void pen_table_build(float ie_coef, PenTable &t) // host only
 // extension bookkeeping of one problem (nasw-sse.c:423-433): fed one finished row at a time
 struct ExtTracker {
 	int max_sc, max_log, max_i, max_code;
-	int pen, pk;      // current penalty and index of the next step in the table
+	int pen, pk, next_thr; // current penalty, index of the next table step, and the x at which it applies
 	bool stopped;
-	NSW_HD void init() { max_sc = INT32_MIN, max_log = INT32_MIN, max_i = -1, max_code = 0, pen = 0, pk = 0, stopped = false; }
+	NSW_HD void init() { max_sc = INT32_MIN, max_log = INT32_MIN, max_i = -1, max_code = 0, pen = 0, pk = 0, next_thr = 2, stopped = false; }
 	// best = max over columns of (H_adjusted << 12 | (4095 - column)), padding columns carry code 0
 	NSW_HD void row(int i, int best, int pen_base /* 3*al */, const PenTable &pt, int xdrop)
 	{
 		const int x = i - pen_base;
-		while (pk < pt.n && x >= pt.thr[pk]) pen = pt.val[pk], ++pk; // a few dozen iterations over the whole problem
+		if (x >= next_thr) { // a few dozen times per problem
+			while (pk < pt.n && x >= pt.thr[pk]) pen = pt.val[pk], ++pk;
+			next_thr = pk < pt.n ? pt.thr[pk] : INT32_MAX;
+		}
 		const int tsc = best >> 12, tlog = tsc - pen;
 		const bool better = !stopped && tlog > max_log;
 		max_sc = better ? tsc : max_sc, max_i = better ? i : max_i, max_code = better ? (best & 4095) : max_code;
@@ -237,61 +240,67 @@ struct LaneGeom {            // where this lane sits in the problem
 	bool live;               // owns real or padding columns (col0 < W8)
 };
 
+// The rolling rows (H of rows i-1..i-3, D of row i-3, the left column's history) and the prefetched row records are
+// kept in small arrays indexed by the step PHASE P = t mod 6 known at compile time (the kernels unroll the step loop by
+// six), so "rotating" them is register renaming instead of ~25 moves per step.
 template <int C, bool MULTI>
 struct ExtLane {
-	int H1[C], H2[C], H3[C], D1[C], D2[C], D3[C], A[C], B[C], Cc[C];
+	int Hr[3][C], Dr[3][C], A[C], B[C], Cc[C];
 	int code[C], bonus[C];
-	int L1, L2, L3;
+	int Lr[3];
 	int outH, outI, outB;    // what the lane to the right receives next step
-	RowRec nxt;              // record of the row this lane processes at the NEXT step
+	RowRec rec[2];           // records of the rows of this step (phase parity) and the next
 
 	template <class Env>
-	NSW_HD void init(const LaneGeom &g, int end_bonus, const Env &env)
+	NSW_HD void init(const LaneGeom &g, int end_bonus, int fs, const Env &env)
 	{
 #pragma unroll
 		for (int k = 0; k < C; ++k) {
 			const int jg = g.col0 + k;
-			H1[k] = H2[k] = H3[k] = D1[k] = D2[k] = D3[k] = A[k] = B[k] = Cc[k] = NEG;
+			Hr[0][k] = Hr[1][k] = Hr[2][k] = Dr[0][k] = Dr[1][k] = Dr[2][k] = A[k] = B[k] = Cc[k] = NEG;
 			code[k] = jg < g.al ? 4095 - jg : 0;
 			bonus[k] = jg == g.al - 1 ? end_bonus : 0;
 		}
-		L1 = L2 = L3 = NEG;
+		Lr[0] = Lr[1] = Lr[2] = NEG;
+		if (g.lane == 0 && g.pass == 0) Lr[0] = 0, Lr[1] = Lr[2] = -fs; // H(-1,-1) = 0, H(0,-1) = H(1,-1) = -fs, seen by row 2 only
 		outH = outI = NEG, outB = INT32_MIN;
-		nxt = env.row_rec(2 - g.lane);
+		rec[0] = env.row_rec(2 - g.lane), rec[1] = env.row_rec(3 - g.lane);
 	}
+	// the boundary column is -32768 for every row after the first (nasw-sse.c:266-270): call once after step t = 0
+	NSW_HD void after_first_step(const LaneGeom &g) { if (g.lane == 0 && g.pass == 0) Lr[0] = Lr[1] = Lr[2] = NEG; }
 
-	// rH/rI/rB: outputs of the left lane from the previous step (ignored by lane 0 of pass 0).
+	// P = t mod 6.  rH/rI/rB: outputs of the left lane from the previous step (ignored by lane 0 of pass 0).
 	// Returns the row this lane just finished (or -1); outB then holds the best value of that row over all columns up
 	// to and including this lane's -- complete in lane 31 of the last pass, which feeds the ExtTracker.
-	template <class Env>
+	template <int P, class Env>
 	NSW_HD int step(const LaneGeom &g, const Par &par, int t, int rH, int rI, int rB, Env &env)
 	{
+		constexpr int h3 = P % 3, h2 = (P + 1) % 3, h1 = (P + 2) % 3, rp = P % 2; // slot h3 holds row i-3 and receives row i
 		const int i = t - g.lane + 2;
-		const RowRec rc = nxt;
-		nxt = env.row_rec(i + 1);
+		const RowRec rc = rec[rp];
+		rec[rp] = env.row_rec(i + 2);
+		if (g.lane == 0) env.prefetch_row(i + 24); // lane 0 is the first to touch a row: pull its line towards L1 early
 		const bool row_ok = i >= 2 && i < g.nl;
-		if (g.lane == 0) {
-			if (!MULTI || g.pass == 0) { // boundary column -1 (nasw-sse.c:253-271): real values only while i == 2
-				rH = NEG, rI = NEG, rB = INT32_MIN;
-				L3 = i == 2 ? 0 : NEG, L2 = L1 = i == 2 ? -par.fs : NEG;
-			} else if (row_ok) env.carry_load3(i, rH, rI, rB);
+		if (g.lane == 0) { // boundary column -1 (nasw-sse.c:253-271); its row history is preset by init()/after_first_step()
+			if (!MULTI || g.pass == 0) rH = NEG, rI = NEG, rB = INT32_MIN;
+			else if (row_ok) env.carry_load3(i, rH, rI, rB);
 		}
 		if (!row_ok) return -1;
 		if (g.live) {
 			const int *ps = env.profile(rc.nas);
-			int l0 = rH, l1 = L1, l2 = L2, l3 = L3, it = rI, best = rB;
+			int l0 = rH, l1 = Lr[h1], l2 = Lr[h2], l3 = Lr[h3], it = rI, best = rB;
 			int hn[C], dn[C];
 #pragma unroll
 			for (int k = 0; k < C; ++k) {
-				hn[k] = cell_score(par, rc, ps[k], H1[k], H2[k], H3[k], D3[k], dn[k], A[k], B[k], Cc[k], l0, l1, l2, l3, it);
+				hn[k] = cell_score(par, rc, ps[k], Hr[h1][k], Hr[h2][k], Hr[h3][k], Dr[h3][k], dn[k], A[k], B[k], Cc[k], l0, l1, l2, l3, it);
 				best = imax(best, (hn[k] + bonus[k]) * 4096 + code[k]);
-				l0 = hn[k], l1 = H1[k], l2 = H2[k], l3 = H3[k];
+				l0 = hn[k], l1 = Hr[h1][k], l2 = Hr[h2][k], l3 = Hr[h3][k];
 			}
 #pragma unroll
-			for (int k = 0; k < C; ++k) H3[k] = H2[k], H2[k] = H1[k], H1[k] = hn[k], D3[k] = D2[k], D2[k] = D1[k], D1[k] = dn[k];
+			for (int k = 0; k < C; ++k) Hr[h3][k] = hn[k], Dr[h3][k] = dn[k];
 			outH = hn[C - 1], outI = it, outB = best;
 		} else outB = rB;
-		if (g.lane != 0 || (MULTI && g.pass > 0)) L3 = L2, L2 = L1, L1 = rH;
+		if (g.lane != 0 || (MULTI && g.pass > 0)) Lr[h3] = rH;
 		if (MULTI && g.lane == 31 && g.pass < g.n_pass - 1) env.carry_store3(i, outH, outI, outB);
 		return i;
 	}
@@ -299,67 +308,69 @@ struct ExtLane {
 
 template <int C, bool MULTI>
 struct TbLane {
-	int H1[C], H2[C], H3[C], D1[C], D2[C], D3[C], A[C], B[C], Cc[C];
-	int L1, L2, L3;
+	int Hr[3][C], Dr[3][C], A[C], B[C], Cc[C];
+	int Lr[3];
 	int outH, outF, outS, outI;
-	RowRec nxt;
+	RowRec rec[2];
 	uint32_t seg_start;      // bit k: column col0+k starts a stripe segment of the reference layout
 	int k_end;               // which of my columns is al-1 (or -1)
 	int score;               // H(nl-1, al-1) once seen
 
 	template <class Env>
-	NSW_HD void init(const LaneGeom &g, const Env &env)
+	NSW_HD void init(const LaneGeom &g, int fs, const Env &env)
 	{
 		const int slen = g.W8 / 8;
 		seg_start = 0, k_end = -1, score = NEG;
 #pragma unroll
 		for (int k = 0; k < C; ++k) {
-			H1[k] = H2[k] = H3[k] = D1[k] = D2[k] = D3[k] = A[k] = B[k] = Cc[k] = NEG;
+			Hr[0][k] = Hr[1][k] = Hr[2][k] = Dr[0][k] = Dr[1][k] = Dr[2][k] = A[k] = B[k] = Cc[k] = NEG;
 			if (slen > 0 && (g.col0 + k) % slen == 0) seg_start |= 1u << k;
 			if (g.col0 + k == g.al - 1) k_end = k;
 		}
-		L1 = L2 = L3 = NEG;
+		Lr[0] = Lr[1] = Lr[2] = NEG;
+		if (g.lane == 0 && g.pass == 0) Lr[0] = 0, Lr[1] = Lr[2] = -fs;
 		outH = outF = outS = outI = NEG;
-		nxt = env.row_rec(2 - g.lane);
+		rec[0] = env.row_rec(2 - g.lane), rec[1] = env.row_rec(3 - g.lane);
 	}
+	NSW_HD void after_first_step(const LaneGeom &g) { if (g.lane == 0 && g.pass == 0) Lr[0] = Lr[1] = Lr[2] = NEG; }
 
 	// wd[] receives the C traceback words when the function returns true
-	template <class Env>
+	template <int P, class Env>
 	NSW_HD bool step(const LaneGeom &g, const Par &par, int t, int rH, int rF, int rS, int rI, Env &env, uint32_t *wd)
 	{
+		constexpr int h3 = P % 3, h2 = (P + 1) % 3, h1 = (P + 2) % 3, rp = P % 2;
 		const int i = t - g.lane + 2;
-		const RowRec rc = nxt;
-		nxt = env.row_rec(i + 1);
+		const RowRec rc = rec[rp];
+		rec[rp] = env.row_rec(i + 2);
+		if (g.lane == 0) env.prefetch_row(i + 24);
 		const bool row_ok = i >= 2 && i < g.nl;
 		if (g.lane == 0) {
-			if (!MULTI || g.pass == 0) {
-				rH = rF = rS = rI = NEG;
-				L3 = i == 2 ? 0 : NEG, L2 = L1 = i == 2 ? -par.fs : NEG;
-			} else if (row_ok) env.carry_load4(i, rH, rF, rS, rI);
+			if (!MULTI || g.pass == 0) rH = rF = rS = rI = NEG;
+			else if (row_ok) env.carry_load4(i, rH, rF, rS, rI);
 		}
 		if (!row_ok) return false;
 		bool wrote = false;
 		if (g.live) {
 			const int *ps = env.profile(rc.nas);
-			int l0 = rH, f0 = rF, l1 = L1, l2 = L2, l3 = L3, iseg = rS, it = rI;
+			int l0 = rH, f0 = rF, l1 = Lr[h1], l2 = Lr[h2], l3 = Lr[h3], iseg = rS, it = rI;
 			int hn[C], dn[C];
 #pragma unroll
 			for (int k = 0; k < C; ++k) {
 				if (seg_start >> k & 1) f0 = NEG, iseg = NEG;
 				int hf;
-				hn[k] = cell_trace(par, rc, ps[k], H1[k], H2[k], H3[k], D3[k], dn[k], A[k], B[k], Cc[k], l0, f0, l1, l2, l3, iseg, it, hf, wd[k]);
-				l0 = hn[k], f0 = hf, l1 = H1[k], l2 = H2[k], l3 = H3[k];
+				hn[k] = cell_trace(par, rc, ps[k], Hr[h1][k], Hr[h2][k], Hr[h3][k], Dr[h3][k], dn[k], A[k], B[k], Cc[k], l0, f0, l1, l2, l3, iseg, it, hf, wd[k]);
+				l0 = hn[k], f0 = hf, l1 = Hr[h1][k], l2 = Hr[h2][k], l3 = Hr[h3][k];
 			}
 			if (i == g.nl - 1 && k_end >= 0) {
 #pragma unroll
 				for (int k = 0; k < C; ++k) if (k == k_end) score = hn[k];
 			}
 #pragma unroll
-			for (int k = 0; k < C; ++k) H3[k] = H2[k], H2[k] = H1[k], H1[k] = hn[k], D3[k] = D2[k], D2[k] = D1[k], D1[k] = dn[k];
+			for (int k = 0; k < C; ++k) Hr[h3][k] = hn[k], Dr[h3][k] = dn[k];
 			outH = hn[C - 1], outF = f0, outS = iseg, outI = it;
 			wrote = true;
 		}
-		if (g.lane != 0 || (MULTI && g.pass > 0)) L3 = L2, L2 = L1, L1 = rH;
+		if (g.lane != 0 || (MULTI && g.pass > 0)) Lr[h3] = rH;
 		if (MULTI && g.lane == 31 && g.pass < g.n_pass - 1) env.carry_store4(i, outH, outF, outS, outI);
 		return wrote;
 	}

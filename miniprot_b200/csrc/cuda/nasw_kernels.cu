@@ -99,6 +99,10 @@ struct DevEnv {
 		r.cA = a.x, r.cB = a.y, r.cC = a.z, r.gei = a.w, r.aA = b.x, r.aB = b.y, r.aC = b.z, r.nas = b.w;
 		return r;
 	}
+	__device__ __forceinline__ void prefetch_row(int i) const
+	{
+		if (i <= nl) asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + 2 * (i < 0 ? 0 : i)));
+	}
 	__device__ __forceinline__ const int *profile(int nas) const { return prof + nas * Wp; }
 	__device__ __forceinline__ void carry_load3(int i, int &a, int &b, int &c) const { a = cy[(int64_t)i * 3], b = cy[(int64_t)i * 3 + 1], c = cy[(int64_t)i * 3 + 2]; }
 	__device__ __forceinline__ void carry_store3(int i, int a, int b, int c) const { cy[(int64_t)i * 3] = a, cy[(int64_t)i * 3 + 1] = b, cy[(int64_t)i * 3 + 2] = c; }
@@ -138,17 +142,20 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_ext_kernel(const DpDev *
 		build_profile(prof, Wp, pass, aa, cst, job, lane);
 		g.pass = pass, g.col0 = pass * Wp + lane * C, g.live = g.col0 < g.W8;
 		ExtLane<C, MULTI> L;
-		L.init(g, cst.end_bonus, env);
-		for (int t = 0; t < T; ++t) {
-			const int rH = __shfl_up_sync(0xffffffffu, L.outH, 1);
-			const int rI = __shfl_up_sync(0xffffffffu, L.outI, 1);
-			const int rB = __shfl_up_sync(0xffffffffu, L.outB, 1);
-			const int row_i = L.step(g, par, t, rH, rI, rB, env);
-			if (row_i >= 0 && pass == g.n_pass - 1) trk.row(row_i, L.outB, g.al * 3, cst.pen, cst.xdrop); // only lane 31's tracker is read
-			if (pass == g.n_pass - 1 && (t & 15) == 15) {
+		L.init(g, cst.end_bonus, par.fs, env);
+#define NSW_EXT_STEP(P) { \
+			const int rH = __shfl_up_sync(0xffffffffu, L.outH, 1), rI = __shfl_up_sync(0xffffffffu, L.outI, 1), rB = __shfl_up_sync(0xffffffffu, L.outB, 1); \
+			const int row_i = L.template step<P>(g, par, t + P, rH, rI, rB, env); \
+			if (row_i >= 0 && pass == g.n_pass - 1) trk.row(row_i, L.outB, g.al * 3, cst.pen, cst.xdrop); /* only lane 31's tracker is read */ }
+		for (int t = 0; t < T; t += 6) { // unrolled by the phase period so that row rotation is register renaming
+			NSW_EXT_STEP(0)
+			if (t == 0) L.after_first_step(g);
+			NSW_EXT_STEP(1) NSW_EXT_STEP(2) NSW_EXT_STEP(3) NSW_EXT_STEP(4) NSW_EXT_STEP(5)
+			if (pass == g.n_pass - 1 && (t % 12) == 6) {
 				if (__shfl_sync(0xffffffffu, (int)trk.stopped, 31)) break;
 			}
 		}
+#undef NSW_EXT_STEP
 		__syncwarp();
 	}
 	if (lane == 31) {
@@ -161,6 +168,22 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_ext_kernel(const DpDev *
 }
 
 // ------------------------------------------------------------------ global alignment with traceback
+// one traceback word per cell, wavefront-major [pass][step][32*C]: a warp step is one coalesced 64*C-byte store
+template <int C>
+__device__ __forceinline__ void store_words(uint16_t *dst, const uint32_t *wd)
+{
+	if (C == 1) dst[0] = (uint16_t)wd[0];
+	else if (C == 2) *reinterpret_cast<uint32_t*>(dst) = wd[0] | wd[C > 1 ? 1 : 0] << 16;
+	else {
+#pragma unroll
+		for (int k = 0; k < C; k += 4) {
+			uint2 v;
+			v.x = wd[k] | wd[k + 1 < C ? k + 1 : k] << 16, v.y = wd[k + 2 < C ? k + 2 : k] | wd[k + 3 < C ? k + 3 : k] << 16;
+			*reinterpret_cast<uint2*>(dst + k) = v;
+		}
+	}
+}
+
 template <int C, bool MULTI>
 __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_tb_kernel(const DpDev *jobs, const int *order, int n_jobs, const int4 *rec, const char *aa,
                                                                  NaswConst cst, int4 *out, int *carry, uint16_t *tb)
@@ -187,29 +210,19 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_tb_kernel(const DpDev *j
 		build_profile(prof, Wp, pass, aa, cst, job, lane);
 		g.pass = pass, g.col0 = pass * Wp + lane * C, g.live = g.col0 < g.W8;
 		TbLane<C, MULTI> L;
-		L.init(g, env);
+		L.init(g, par.fs, env);
 		uint16_t *tbp = tb + job.tb_off + (int64_t)pass * T * Wp + lane * C;
-		for (int t = 0; t < T; ++t) {
-			const int rH = __shfl_up_sync(0xffffffffu, L.outH, 1);
-			const int rF = __shfl_up_sync(0xffffffffu, L.outF, 1);
-			const int rS = __shfl_up_sync(0xffffffffu, L.outS, 1);
-			const int rI = __shfl_up_sync(0xffffffffu, L.outI, 1);
-			uint32_t wd[C];
-			if (L.step(g, par, t, rH, rF, rS, rI, env, wd)) {
-				// one traceback word per cell, wavefront-major: [pass][t][32*C]
-				uint16_t *dst = tbp + (int64_t)t * Wp;
-				if (C == 1) dst[0] = (uint16_t)wd[0];
-				else if (C == 2) *reinterpret_cast<uint32_t*>(dst) = wd[0] | wd[C > 1 ? 1 : 0] << 16;
-				else {
-#pragma unroll
-					for (int k = 0; k < C; k += 4) {
-						uint2 v;
-						v.x = wd[k] | wd[k + 1 < C ? k + 1 : k] << 16, v.y = wd[k + 2 < C ? k + 2 : k] | wd[k + 3 < C ? k + 3 : k] << 16;
-						*reinterpret_cast<uint2*>(dst + k) = v;
-					}
-				}
-			}
+#define NSW_TB_STEP(P) { \
+			const int rH = __shfl_up_sync(0xffffffffu, L.outH, 1), rF = __shfl_up_sync(0xffffffffu, L.outF, 1); \
+			const int rS = __shfl_up_sync(0xffffffffu, L.outS, 1), rI = __shfl_up_sync(0xffffffffu, L.outI, 1); \
+			uint32_t wd[C]; \
+			if (L.template step<P>(g, par, t + P, rH, rF, rS, rI, env, wd)) store_words<C>(tbp + (int64_t)(t + P) * Wp, wd); }
+		for (int t = 0; t < T; t += 6) {
+			NSW_TB_STEP(0)
+			if (t == 0) L.after_first_step(g);
+			NSW_TB_STEP(1) NSW_TB_STEP(2) NSW_TB_STEP(3) NSW_TB_STEP(4) NSW_TB_STEP(5)
 		}
+#undef NSW_TB_STEP
 		if (L.k_end >= 0) score = L.score;
 		__syncwarp();
 	}

@@ -22,6 +22,7 @@ struct EmuEnv {
 	int Wp;
 	int *cy;
 	RowRec row_rec(int i) const { i = i < 0 ? 0 : (i > nl ? nl : i); return rec[i]; }
+	void prefetch_row(int) const {}
 	const int *profile(int nas) const { return prof + nas * Wp; }
 	void carry_load3(int i, int &a, int &b, int &c) const { a = cy[(int64_t)i * 3], b = cy[(int64_t)i * 3 + 1], c = cy[(int64_t)i * 3 + 2]; }
 	void carry_store3(int i, int a, int b, int c) const { cy[(int64_t)i * 3] = a, cy[(int64_t)i * 3 + 1] = b, cy[(int64_t)i * 3 + 2] = c; }
@@ -59,15 +60,24 @@ void run_ext(const Problem &P, int *score, int *nt_len, int *aa_len)
 		for (int l = 0; l < 32; ++l) {
 			g[l].lane = l, g[l].pass = pass, g[l].n_pass = n_pass, g[l].nl = P.nl, g[l].al = P.al, g[l].W8 = P.W8, g[l].col0 = pass * Wp + l * C, g[l].live = g[l].col0 < P.W8;
 			env[l].rec = P.rec.data(), env[l].nl = P.nl, env[l].prof = prof.data() + l * C, env[l].Wp = Wp, env[l].cy = cy.data();
-			L[l].init(g[l], P.end_bonus, env[l]);
+			L[l].init(g[l], P.end_bonus, P.par.fs, env[l]);
 		}
 		for (int t = 0; t < T; ++t) {
 			int rH[32], rI[32], rB[32];
 			for (int l = 0; l < 32; ++l) { const int s = l ? l - 1 : 0; rH[l] = L[s].outH, rI[l] = L[s].outI, rB[l] = L[s].outB; } // __shfl_up_sync(.., 1)
 			for (int l = 0; l < 32; ++l) {
-				const int ri = L[l].step(g[l], P.par, t, rH[l], rI[l], rB[l], env[l]);
+				int ri;
+				switch (t % 6) { // the kernels unroll the loop by the phase period
+				case 0: ri = L[l].template step<0>(g[l], P.par, t, rH[l], rI[l], rB[l], env[l]); break;
+				case 1: ri = L[l].template step<1>(g[l], P.par, t, rH[l], rI[l], rB[l], env[l]); break;
+				case 2: ri = L[l].template step<2>(g[l], P.par, t, rH[l], rI[l], rB[l], env[l]); break;
+				case 3: ri = L[l].template step<3>(g[l], P.par, t, rH[l], rI[l], rB[l], env[l]); break;
+				case 4: ri = L[l].template step<4>(g[l], P.par, t, rH[l], rI[l], rB[l], env[l]); break;
+				default: ri = L[l].template step<5>(g[l], P.par, t, rH[l], rI[l], rB[l], env[l]); break;
+				}
 				if (ri >= 0 && pass == n_pass - 1) trks[l].row(ri, L[l].outB, P.al * 3, pt, P.xdrop); // every lane tracks; lane 31 counts
 			}
+			if (t == 0) for (int l = 0; l < 32; ++l) L[l].after_first_step(g[l]);
 			if (pass == n_pass - 1 && (t & 15) == 15 && trks[31].stopped) break;
 		}
 		trk = trks[31];
@@ -92,16 +102,26 @@ void run_tb(const Problem &P, int *score, std::vector<uint32_t> &cigar)
 		for (int l = 0; l < 32; ++l) {
 			g[l].lane = l, g[l].pass = pass, g[l].n_pass = n_pass, g[l].nl = P.nl, g[l].al = P.al, g[l].W8 = P.W8, g[l].col0 = pass * Wp + l * C, g[l].live = g[l].col0 < P.W8;
 			env[l].rec = P.rec.data(), env[l].nl = P.nl, env[l].prof = prof.data() + l * C, env[l].Wp = Wp, env[l].cy = cy.data();
-			L[l].init(g[l], env[l]);
+			L[l].init(g[l], P.par.fs, env[l]);
 		}
 		for (int t = 0; t < T; ++t) {
 			int rH[32], rF[32], rS[32], rI[32];
 			for (int l = 0; l < 32; ++l) { const int s = l ? l - 1 : 0; rH[l] = L[s].outH, rF[l] = L[s].outF, rS[l] = L[s].outS, rI[l] = L[s].outI; }
 			for (int l = 0; l < 32; ++l) {
 				uint32_t wd[C];
-				if (L[l].step(g[l], P.par, t, rH[l], rF[l], rS[l], rI[l], env[l], wd))
+				bool w;
+				switch (t % 6) {
+				case 0: w = L[l].template step<0>(g[l], P.par, t, rH[l], rF[l], rS[l], rI[l], env[l], wd); break;
+				case 1: w = L[l].template step<1>(g[l], P.par, t, rH[l], rF[l], rS[l], rI[l], env[l], wd); break;
+				case 2: w = L[l].template step<2>(g[l], P.par, t, rH[l], rF[l], rS[l], rI[l], env[l], wd); break;
+				case 3: w = L[l].template step<3>(g[l], P.par, t, rH[l], rF[l], rS[l], rI[l], env[l], wd); break;
+				case 4: w = L[l].template step<4>(g[l], P.par, t, rH[l], rF[l], rS[l], rI[l], env[l], wd); break;
+				default: w = L[l].template step<5>(g[l], P.par, t, rH[l], rF[l], rS[l], rI[l], env[l], wd); break;
+				}
+				if (w)
 					for (int k = 0; k < C; ++k) tb[((size_t)pass * T + t) * Wp + l * C + k] = (uint16_t)wd[k];
 			}
+			if (t == 0) for (int l = 0; l < 32; ++l) L[l].after_first_step(g[l]);
 		}
 		for (int l = 0; l < 32; ++l) if (L[l].k_end >= 0) sc = L[l].score;
 	}
