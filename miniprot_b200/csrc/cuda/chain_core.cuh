@@ -154,7 +154,8 @@ CHN_HD int64_t bk_end(int32_t max_drop, uint64_t z, const int32_t *f, const int3
 // order and t[0..n) cleared.  Scratch: t[n] marks, v[n], z[>=n], stack[>=CHAIN_STACK]; f[] is OVERWRITTEN (it is dead after
 // the peeling and serves as the chain-offset table of the compaction).
 // Output: u[0..n_u) = score<<32|cnt, b[0..n_b) = compacted anchors (chains ordered by target start).  Returns n_u.
-template <class T>
+// PRESORTED: z[] has already been sorted by the caller (the warp-cooperative sort of the shared-memory kernel).
+template <class T, bool PRESORTED = false>
 CHN_HD int32_t peel_and_compact(const Par &p, int32_t n_z, const uint64_t *a, int32_t *f, const int32_t *pp, T *t, int32_t *v, uint64_t *z,
                                 mpb::FlagRange<uint64_t> *stack, uint64_t *u, uint64_t *b, int32_t *n_b_out)
 {
@@ -162,7 +163,7 @@ CHN_HD int32_t peel_and_compact(const Par &p, int32_t n_z, const uint64_t *a, in
 	int32_t n_u = 0, n_v = 0;
 	*n_b_out = 0;
 	if (n_z == 0) return 0;
-	mpb::flag_sort_by(z, z + n_z, [](const uint64_t &e) { return rec_key(e); }, stack);
+	if (!PRESORTED) mpb::flag_sort_by(z, z + n_z, [](const uint64_t &e) { return rec_key(e); }, stack);
 	for (int32_t k = n_z - 1; k >= 0; --k) {
 		const int32_t zi = (int32_t)(uint32_t)z[k], zx = (int32_t)(z[k] >> 32);
 		if (t[zi] != 0) continue;

@@ -80,6 +80,70 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_fill_kernel(const int6
 	}
 }
 
+// Warp-cooperative form of flagsort.hpp::flag_sort_by for records in shared memory: identical permutation (every pass
+// and every insertion sort acts on the same disjoint range with the same sequential semantics), but the histogram, the
+// key-range scan and the many small insertion sorts are spread over the 32 lanes; only the cycle-leader permutation of
+// a pass -- the part whose order defines the reference's tie order -- stays on lane 0.
+struct WarpSortScratch { uint32_t cnt[256]; uint32_t head[256]; uint32_t tail[256]; int top; };
+
+template <class KeyFn>
+__device__ void flag_sort_warp(uint64_t *rec, int n, KeyFn key, FlagRange<uint64_t> *stack, WarpSortScratch *ws, int lane)
+{
+	if (n <= 64) {
+		if (lane == 0) insertion_sort_by(rec, rec + n, key);
+		__syncwarp();
+		return;
+	}
+	if (lane == 0) ws->top = 1, stack[0] = FlagRange<uint64_t>{rec, rec + n, 56};
+	__syncwarp();
+	while (ws->top > 0) {
+		const FlagRange<uint64_t> r = stack[ws->top - 1];
+		__syncwarp();
+		if (lane == 0) ws->top -= 1;
+		const int m = (int)(r.end - r.beg);
+		uint64_t lo = ~0ULL, hi = 0;
+		for (int i = lane; i < m; i += 32) { const uint64_t k = key(r.beg[i]); lo = k < lo ? k : lo, hi = k > hi ? k : hi; }
+		for (int d = 16; d; d >>= 1) {
+			const uint64_t ol = __shfl_xor_sync(0xffffffffu, lo, d), oh = __shfl_xor_sync(0xffffffffu, hi, d);
+			lo = ol < lo ? ol : lo, hi = oh > hi ? oh : hi;
+		}
+		int shift = r.shift;
+		while (shift > 0 && (lo >> shift) == (hi >> shift)) shift -= 8; // passes that cannot move anything
+		if (shift == 0 && lo == hi) { __syncwarp(); continue; }
+		for (int k = lane; k < 256; k += 32) ws->cnt[k] = 0;
+		__syncwarp();
+		for (int i = lane; i < m; i += 32) atomicAdd(&ws->cnt[(key(r.beg[i]) >> shift) & 255], 1u);
+		__syncwarp();
+		if (lane == 0) {
+			uint32_t acc = 0;
+			for (int k = 0; k < 256; ++k) ws->head[k] = acc, acc += ws->cnt[k], ws->tail[k] = acc;
+			uint64_t *b = r.beg;
+			for (int k = 0; k < 256;) { // the cycle-leader permutation (ksort.h:133-146), sequential by definition
+				if (ws->head[k] == ws->tail[k]) { ++k; continue; }
+				int d = (int)((key(b[ws->head[k]]) >> shift) & 255);
+				if (d == k) { ++ws->head[k]; continue; }
+				uint64_t hand = b[ws->head[k]];
+				do {
+					const uint64_t next = b[ws->head[d]];
+					b[ws->head[d]++] = hand;
+					hand = next;
+					d = (int)((key(hand) >> shift) & 255);
+				} while (d != k);
+				b[ws->head[k]++] = hand;
+			}
+		}
+		__syncwarp();
+		if (shift > 0) {
+			for (int k = lane; k < 256; k += 32) { // buckets are disjoint: refine them in parallel
+				const uint32_t e = ws->tail[k], bgn = k ? ws->tail[k - 1] : 0;
+				if (e - bgn > 64) { const int slot = atomicAdd(&ws->top, 1); stack[slot] = FlagRange<uint64_t>{r.beg + bgn, r.beg + e, shift - 8}; }
+				else if (e - bgn > 1) insertion_sort_by(r.beg + bgn, r.beg + e, key);
+			}
+		}
+		__syncwarp();
+	}
+}
+
 // Backtrack + compaction, one WARP per problem, sort records and marks in shared memory.
 // Lanes cooperate on the parallel parts (clearing marks, gathering the (score, index) records in order, re-sorting the
 // kept anchors' staging copies); lane 0 runs the order-dependent part (flag sort, best-first peeling, chain ordering)
@@ -89,6 +153,7 @@ __global__ void __launch_bounds__(32) chain_bt_smem_kernel(const int32_t *list, 
                                                           uint64_t *u_all, uint64_t *b_all, int32_t *n_u_out, int32_t *n_b_out, int resort)
 {
 	extern __shared__ uint64_t zs[];
+	__shared__ WarpSortScratch ws;
 	if ((int)blockIdx.x >= n_list) return;
 	const int prob = list[blockIdx.x], lane = threadIdx.x;
 	const int64_t base = a_off[prob];
@@ -106,15 +171,16 @@ __global__ void __launch_bounds__(32) chain_bt_smem_kernel(const int32_t *list, 
 	}
 	__syncwarp();
 	int32_t n_u = 0, n_b = 0;
+	FlagRange<uint64_t> *stack = stack_all + (int64_t)prob * CHAIN_STACK;
+	flag_sort_warp(zs, n_z, [](const uint64_t &e) { return rec_key(e); }, stack, &ws, lane); // chain ends by score, reference tie order
 	if (lane == 0 && n > 0)
-		n_u = peel_and_compact(par, n_z, a_all + base, f, p_all + base, ts, v_all + base, zs, stack_all + (int64_t)prob * CHAIN_STACK, u_all + base, b_all + base, &n_b);
+		n_u = peel_and_compact<int8_t, true>(par, n_z, a_all + base, f, p_all + base, ts, v_all + base, zs, stack, u_all + base, b_all + base, &n_b);
 	n_b = __shfl_sync(0xffffffffu, n_b, 0);
 	if (resort && n_b > 1) { // map.c:191: the anchors kept by the pre-chain go back into plain sorted order
 		uint64_t *b = b_all + base;
 		for (int32_t i = lane; i < n_b; i += 32) zs[i] = b[i];
 		__syncwarp();
-		if (lane == 0) flag_sort_by(zs, zs + n_b, [](const uint64_t &x) { return x; }, stack_all + (int64_t)prob * CHAIN_STACK);
-		__syncwarp();
+		flag_sort_warp(zs, n_b, [](const uint64_t &x) { return x; }, stack, &ws, lane);
 		for (int32_t i = lane; i < n_b; i += 32) b[i] = zs[i];
 	}
 	if (lane == 0) n_u_out[prob] = n_u, n_b_out[prob] = n_b;
