@@ -11,7 +11,7 @@ struct mpb_ctx_s {
 	cudaEvent_t ev0 = 0, ev1 = 0;
 	// side streams: size classes of one DP wave (and independent stage pieces) run concurrently; each class is bounded
 	// by its longest problem, so serialising them on one stream would add the critical paths up
-	static const int N_SIDE = 10;
+	static const int N_SIDE = 18;
 	cudaStream_t side[N_SIDE] = {0};
 	cudaEvent_t ev_fork = 0, ev_join[N_SIDE] = {0}, ev_k0[N_SIDE] = {0}, ev_k1[N_SIDE] = {0};
 

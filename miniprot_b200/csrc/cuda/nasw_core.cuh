@@ -377,6 +377,83 @@ struct TbLane {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Block-wide wavefront ("v3"): one THREAD per protein column, three nucleotide rows per step.
+//
+// The number of wavefront steps of a problem is fixed by its nucleotide length (100 k rows for a default extension
+// window), and a step costs a few hundred cycles of mostly fixed overhead (neighbour exchange, row-record fetch, loop,
+// tracker) however few columns a lane owns.  So the critical path is shortest when every thread owns ONE column and
+// amortises the overhead over several rows: thread x of a CTA of NW warps handles column x and, at macro-step T, the
+// rows 3(T-x)+2 .. 3(T-x)+4.  Three is the period of the H/D row rotation, so row r of a macro-step always lives in
+// slot r (no moves).  Thread x receives what thread x-1 produced for the same three rows one macro-step earlier: by
+// warp shuffle inside a warp, through a double-buffered shared-memory slot across warps (one __syncthreads per
+// macro-step).  Problems of up to 32*NW (<= 256) padded columns run this way; wider ones keep the column-pass kernels.
+// ------------------------------------------------------------------------------------------------
+struct Geo3 { int x, nl, al, W8; bool live, first; };
+
+template <bool TB>
+struct Lane3 {
+	int H[3], D[3], A, B, Cc, L[3];
+	RowRec rec[6];
+	int oH[3], oI[3], oX[3], oS[3]; // per row of the macro-step: final H, insertion chain, (ext) running best / (tb) first-pass H, (tb) segment chain
+	int code, bonus, score;
+	bool seg_start, end_col;
+
+	NSW_HD static int row_of(const Geo3 &g, int T, int r) { return 3 * (T - g.x) + 2 + r; }
+
+	template <class Env>
+	NSW_HD void init(const Geo3 &g, int end_bonus, int fs, const Env &env)
+	{
+		const int slen = g.W8 / 8;
+		for (int k = 0; k < 3; ++k) H[k] = D[k] = L[k] = NEG, oH[k] = oI[k] = oS[k] = NEG, oX[k] = TB ? NEG : INT32_MIN;
+		A = B = Cc = NEG;
+		if (g.first) L[0] = 0, L[1] = L[2] = -fs; // H(-1,-1), H(0,-1), H(1,-1): seen by row 2 only (nasw-sse.c:253-258)
+		code = g.x < g.al ? 4095 - g.x : 0, bonus = g.x == g.al - 1 ? end_bonus : 0;
+		seg_start = slen > 0 && g.x % slen == 0, end_col = g.x == g.al - 1, score = NEG;
+		const int i0 = row_of(g, 0, 0);
+		for (int k = 0; k < 6; ++k) rec[k] = env.row_rec(i0 + k);
+	}
+
+	// One macro-step.  PH = T mod 2 selects the half of the record buffer.  rH/rI/rX/rS[r]: outputs of thread x-1 for row r.
+	// wd[r] receives the traceback word of row r (TB) and done[r] tells whether row r was a real row of this thread.
+	template <int PH, class Env>
+	NSW_HD void macro(const Geo3 &g, const Par &par, int T, const int *rH, const int *rI, const int *rX, const int *rS, Env &env, uint32_t *wd, bool *done)
+	{
+#pragma unroll
+		for (int r = 0; r < 3; ++r) {
+			const int h3 = r, h2 = (r + 1) % 3, h1 = (r + 2) % 3;
+			const int i = row_of(g, T, r);
+			const RowRec rc = rec[3 * PH + r];
+			rec[3 * PH + r] = env.row_rec(i + 6);
+			const bool row_ok = i >= 2 && i < g.nl;
+			done[r] = false;
+			if (!row_ok) continue;
+			int l0 = rH[r], it = rI[r], lx = rX[r], ls = TB ? rS[r] : 0;
+			if (g.first) l0 = NEG, it = NEG, lx = TB ? NEG : INT32_MIN, ls = NEG;
+			if (g.live) {
+				const int s = env.profile(rc.nas)[0];
+				int d_new;
+				if (TB) {
+					int f0 = lx, iseg = ls, hf;
+					if (seg_start) f0 = NEG, iseg = NEG;
+					const int h = cell_trace(par, rc, s, H[h1], H[h2], H[h3], D[h3], d_new, A, B, Cc, l0, f0, L[h1], L[h2], L[h3], iseg, it, hf, wd[r]);
+					H[h3] = h, D[h3] = d_new;
+					oH[r] = h, oI[r] = it, oX[r] = hf, oS[r] = iseg;
+					if (end_col && i == g.nl - 1) score = h;
+				} else {
+					const int h = cell_score(par, rc, s, H[h1], H[h2], H[h3], D[h3], d_new, A, B, Cc, l0, L[h1], L[h2], L[h3], it);
+					H[h3] = h, D[h3] = d_new;
+					oH[r] = h, oI[r] = it, oX[r] = imax(lx, (h + bonus) * 4096 + code);
+				}
+				done[r] = true;
+			} else if (!TB) oX[r] = lx, done[r] = true; // dead columns only hand the row maximum on
+			if (!g.first) L[h3] = rH[r];
+			else if (i == 2) L[0] = L[1] = L[2] = NEG; // the boundary column is -32768 for every later row (nasw-sse.c:266-270)
+		}
+		if (g.nl > 0 && g.first) env.prefetch_row(row_of(g, T, 0) + 72);
+	}
+};
+
+// ------------------------------------------------------------------------------------------------
 // sequence preparation (nasw-sse.c:91-210) for one row, from a code accessor c(k) (k in [0,nl), values 0..4).
 // FORWARD orientation is used for global alignment and right extension; the LEFT variant sees the slice
 // already reversed (c(k) = original[nl-1-k], not complemented) and applies the mirrored rules.

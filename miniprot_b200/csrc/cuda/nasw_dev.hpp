@@ -23,12 +23,12 @@ struct DpDev {                  // one DP problem, resident in HBM for the durat
 	int32_t nl, al;
 	int32_t aa_off;             // first residue of the protein slice in the batch residue buffer
 	int32_t flag, io;
-	int32_t C;                  // columns per lane chosen for this problem (1, 2, 4 or 8)
+	int32_t C;                  // column-pass kernels: columns per lane (1, 2, 4, 8); 0 = block-wide wavefront kernel
 	int64_t rw_off;             // row records (32 B each): nl + 1 entries, offset in rows
 	int64_t tb_off;             // traceback words (uint16 units); tb problems only
 	int64_t cig_off;            // CIGAR slot
 	int32_t cig_cap;
-	int32_t pad_;
+	int32_t pad_;               // block-wide wavefront: traceback row width (32 * warps per problem)
 	int64_t carry_off;          // per-row carry between column passes (int units)
 };
 
@@ -48,6 +48,8 @@ struct NaswConst {              // problem-independent parameters, passed by val
 void nasw_launch_prep(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, int4 *rec);
 void nasw_launch_ext(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, int *carry);
 void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, int *carry,
+                    uint16_t *tb);
+void nasw_launch_v3(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out,
                     uint16_t *tb);
 void nasw_launch_bt(cudaStream_t st, const DpDev *jobs, const int *order, int n, const uint16_t *tb, uint32_t *cigar, int4 *out);
 

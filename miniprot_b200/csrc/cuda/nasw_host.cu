@@ -24,6 +24,20 @@ static inline int pick_C(int al)
 	return W8 <= 32 ? 1 : W8 <= 64 ? 2 : W8 <= 128 ? 4 : 8;
 }
 
+// Kernel family: the block-wide wavefront (one thread per column, nasw_v3_kernel) serves every problem of up to 256 padded
+// columns; wider ones use the column-pass kernels (8 columns per lane, several passes).  MPB_NASW_KERNEL=cols forces the
+// column-pass family for everything (A/B measurements only).
+static inline bool use_v3(int al)
+{
+	static const int forced_cols = [] { const char *e = getenv("MPB_NASW_KERNEL"); return e && strcmp(e, "cols") == 0; }();
+	return !forced_cols && (al + 7) / 8 * 8 <= 256;
+}
+static inline int v3_warps(int al)
+{
+	const int nw = ((al + 7) / 8 * 8 + 31) / 32;
+	return nw <= 1 ? 1 : nw <= 2 ? 2 : nw <= 4 ? 4 : 8;
+}
+
 static void fill_const(const ns_opt_t *o, NaswConst &c)
 {
 	memcpy(c.mat, o->sc, 484);
@@ -43,14 +57,19 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	cudaStream_t st = ctx->stream;
 	int64_t rw_tot = 0, tb_tot = 0, cig_tot = 0, carry_tot = 0;
 	std::vector<PrepChunk> chunks;
-	std::vector<int> order[2][5]; // [is_tb][log2 C; 4 = multi-pass]
+	std::vector<int> order[2][9]; // [is_tb][class]: 0..3 block-wide wavefront with 1/2/4/8 warps; 4..7 column passes C = 1/2/4/8; 8 multi-pass
 	for (int k = 0; k < n; ++k) {
 		DpDev &j = jobs[lo + k];
 		const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
-		j.C = pick_C(j.al);
-		const int Wp = 32 * j.C, W8 = (j.al + 7) / 8 * 8, n_pass = (W8 + Wp - 1) / Wp, T = j.nl > 2 ? j.nl - 2 + 32 : 0;
+		const bool v3 = use_v3(j.al);
+		const int nw = v3_warps(j.al);
+		j.C = v3 ? 0 : pick_C(j.al);
+		j.pad_ = v3 ? 32 * nw : 0;
+		const int Wp = v3 ? 32 * nw : 32 * j.C, W8 = (j.al + 7) / 8 * 8, n_pass = v3 ? 1 : (W8 + Wp - 1) / Wp;
+		const int T = v3 ? (j.nl > 2 ? 3 * ((j.nl - 2 + 2) / 3 + Wp + 2) : 0) : (j.nl > 2 ? j.nl - 2 + 32 + 6 : 0); // rows of the wavefront-major traceback buffer
 		j.rw_off = rw_tot, rw_tot += (j.nl + 1 + 3) / 4 * 4;
 		j.tb_off = j.cig_off = 0, j.cig_cap = 0, j.carry_off = 0;
+		(void)0;
 		if (is_tb) {
 			j.tb_off = tb_tot, tb_tot += (int64_t)n_pass * T * Wp;
 			j.cig_cap = j.nl + j.al + 4;
@@ -58,14 +77,14 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		}
 		if (n_pass > 1) j.carry_off = carry_tot, carry_tot += ((int64_t)j.nl + 1) * 4;
 		for (int r = 0; r <= j.nl; r += PREP_ROWS) chunks.push_back(PrepChunk{ k, r, std::min(PREP_ROWS, j.nl + 1 - r), 0 });
-		order[is_tb][n_pass > 1 ? 4 : j.C == 1 ? 0 : j.C == 2 ? 1 : j.C == 4 ? 2 : 3].push_back(k);
+		order[is_tb][v3 ? (nw == 1 ? 0 : nw == 2 ? 1 : nw == 4 ? 2 : 3) : n_pass > 1 ? 8 : j.C == 1 ? 4 : j.C == 2 ? 5 : j.C == 4 ? 6 : 7].push_back(k);
 		(is_tb ? ctx->stats.dp_cells_tb : ctx->stats.dp_cells_ext) += (int64_t)j.nl * j.al;
 		(is_tb ? ctx->stats.n_dp_tb : ctx->stats.n_dp_ext) += 1;
 	}
 	std::vector<int> flat;
-	size_t first[2][5], count[2][5];
+	size_t first[2][9], count[2][9];
 	for (int b = 0; b < 2; ++b)
-		for (int c = 0; c < 5; ++c) {
+		for (int c = 0; c < 9; ++c) {
 			std::vector<int> &v = order[b][c];
 			std::stable_sort(v.begin(), v.end(), [&](int x, int y) { return jobs[lo + x].nl > jobs[lo + y].nl; });
 			first[b][c] = flat.size(), count[b][c] = v.size();
@@ -89,19 +108,26 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	const int *dord = ctx->b_order.as<int>();
 	nasw_launch_prep(st, dj, ctx->b_chunks.as<PrepChunk>(), (int)chunks.size(), packed, cst, ctx->b_rw.as<int4>());
 	ctx->stats.kernel_launches += 1;
-	static const int Cs[5] = { 1, 2, 4, 8, 16 };
+	static const int Cs[9] = { 1, 2, 4, 8, 1, 2, 4, 8, 16 }; // warps per problem (classes 0..3) or columns per lane (4..8)
 	// fork: every (kind, size class) runs on its own stream -- each is bounded by its longest problem
 	MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
 	bool used[mpb_ctx_s::N_SIDE] = { false }, is_ext_sid[mpb_ctx_s::N_SIDE] = { false };
 	for (int b = 0; b < 2; ++b)
-		for (int c = 4; c >= 0; --c) {
+		for (int c = 8; c >= 0; --c) {
 			if (!count[b][c]) continue;
-			const int sid = (b * 5 + c) % mpb_ctx_s::N_SIDE;
+			const int sid = b * 9 + c;
 			cudaStream_t ss = ctx->side[sid];
 			used[sid] = true, is_ext_sid[sid] = b == 0;
 			MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
 			MPB_CUDA_OK(cudaEventRecord(ctx->ev_k0[sid], ss));
-			if (b == 0) {
+			if (c < 4) {
+				nasw_launch_v3(ss, Cs[c], b == 1, dj, dord + first[b][c], (int)count[b][c], ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>());
+				ctx->stats.kernel_launches += 1;
+				if (b == 1) {
+					nasw_launch_bt(ss, dj, dord + first[1][c], (int)count[1][c], ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
+					ctx->stats.kernel_launches += 1;
+				}
+			} else if (b == 0) {
 				nasw_launch_ext(ss, Cs[c], dj, dord + first[0][c], (int)count[0][c], ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>());
 				ctx->stats.kernel_launches += 1;
 			} else {
@@ -152,8 +178,9 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_
 		while (hi < n) {
 			const DpDev &j = jobs[hi];
 			const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
-			const int C = pick_C(j.al), Wp = 32 * C, W8 = (j.al + 7) / 8 * 8, n_pass = (W8 + Wp - 1) / Wp;
-			const size_t tbb = is_tb ? (size_t)n_pass * (size_t)(j.nl + 30) * Wp * 2 : 0, rwb = (size_t)(j.nl + 4) * 32;
+			const bool v3 = use_v3(j.al);
+			const int C = pick_C(j.al), Wp = v3 ? 32 * v3_warps(j.al) : 32 * C, W8 = (j.al + 7) / 8 * 8, n_pass = v3 ? 1 : (W8 + Wp - 1) / Wp;
+			const size_t tbb = is_tb ? (size_t)n_pass * (size_t)(j.nl + 3 * Wp + 64) * Wp * 2 : 0, rwb = (size_t)(j.nl + 4) * 32;
 			if (hi > lo && (tb_bytes + tbb > kTbBudget || rw_bytes + rwb > kRwBudget)) break;
 			tb_bytes += tbb, rw_bytes += rwb, ++hi;
 		}

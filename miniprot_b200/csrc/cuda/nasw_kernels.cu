@@ -232,15 +232,96 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_tb_kernel(const DpDev *j
 	if (lane == 0) out[jid] = make_int4(score, g.nl, g.al, 0);
 }
 
+// ------------------------------------------------------------------ block-wide wavefront (one thread per column, 3 rows per step)
+// CTA = NW warps = 32*NW columns of ONE problem; see nasw_core.cuh::Lane3.  TB = false: score-only extension (result by the
+// last thread's tracker); TB = true: global alignment, one 16-bit word per cell to tb[(3T + r) * 32NW + x].
+template <int NW, bool TB>
+__global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, const int *order, int n_jobs, const int4 *rec, const char *aa, NaswConst cst,
+                                                          int4 *out, uint16_t *tb)
+{
+	extern __shared__ int smem[];
+	constexpr int Wp = 32 * NW, NX = TB ? 12 : 9;
+	__shared__ int xchg[2][NW][12];
+	__shared__ int stop_flag[2]; // written by the last column during macro-step Tm into slot Tm & 1, read by everyone after that step's barrier
+	if ((int)blockIdx.x >= n_jobs) return;
+	const int jid = order[blockIdx.x];
+	const DpDev job = jobs[jid];
+	const int x = threadIdx.x, lane = x & 31, warp = x >> 5;
+	Geo3 g;
+	g.x = x, g.nl = job.nl, g.al = job.al, g.W8 = (job.al + 7) / 8 * 8, g.live = x < g.W8, g.first = x == 0;
+	Par par;
+	par.go = cst.go, par.ge = cst.ge, par.io = job.io, par.fs = cst.fs, par.gei_stop = cst.fs;
+	// profile: 22 x Wp, column x of row a at smem[a * Wp + x]
+	{
+		int rcode = -1;
+		if (x < job.al) rcode = col_residue(aa, cst, job, x);
+		for (int a = 0; a < 22; ++a) smem[a * Wp + x] = rcode >= 0 ? cst.mat[a * 22 + rcode] : NEG;
+	}
+	if (x == 0) stop_flag[0] = stop_flag[1] = 0;
+	__syncthreads();
+	DevEnv env;
+	env.rec = rec + job.rw_off * 2, env.nl = g.nl, env.prof = smem + x, env.Wp = Wp, env.cy = 0;
+	Lane3<TB> L;
+	L.init(g, cst.end_bonus, par.fs, env);
+	ExtTracker trk;
+	trk.init();
+	const int n_macro = g.nl > 2 ? (g.nl - 2 + 2) / 3 + Wp : 0; // rows 2..nl-1 in triples, plus the skew of the last column
+	uint16_t *tbp = TB ? tb + job.tb_off + x : 0;
+#define NSW_V3_MACRO(PH) { \
+		int rH[3], rI[3], rX[3], rS[3]; \
+		_Pragma("unroll") for (int r = 0; r < 3; ++r) { \
+			rH[r] = __shfl_up_sync(0xffffffffu, L.oH[r], 1), rI[r] = __shfl_up_sync(0xffffffffu, L.oI[r], 1), rX[r] = __shfl_up_sync(0xffffffffu, L.oX[r], 1); \
+			rS[r] = TB ? __shfl_up_sync(0xffffffffu, L.oS[r], 1) : 0; \
+		} \
+		if (NW > 1 && lane == 0 && warp > 0) { /* the column to my left lives in the previous warp */ \
+			const int *b = xchg[(T + PH + 1) & 1][warp - 1]; \
+			_Pragma("unroll") for (int r = 0; r < 3; ++r) { rH[r] = b[r], rI[r] = b[3 + r], rX[r] = b[6 + r]; if (TB) rS[r] = b[9 + r]; } \
+		} \
+		uint32_t wd[3]; \
+		bool done[3]; \
+		L.template macro<PH>(g, par, T + PH, rH, rI, rX, rS, env, wd, done); \
+		if (TB) { _Pragma("unroll") for (int r = 0; r < 3; ++r) if (done[r]) tbp[(int64_t)(3 * (T + PH) + r) * Wp] = (uint16_t)wd[r]; } \
+		else { _Pragma("unroll") for (int r = 0; r < 3; ++r) if (done[r]) trk.row(Lane3<TB>::row_of(g, T + PH, r), L.oX[r], g.al * 3, cst.pen, cst.xdrop); } \
+		if (NW > 1) { \
+			if (lane == 31 && warp < NW - 1) { \
+				int *b = xchg[(T + PH) & 1][warp]; \
+				_Pragma("unroll") for (int r = 0; r < 3; ++r) { b[r] = L.oH[r], b[3 + r] = L.oI[r], b[6 + r] = L.oX[r]; if (TB) b[9 + r] = L.oS[r]; } \
+			} \
+			if (!TB && x == Wp - 1) stop_flag[(T + PH) & 1] = trk.stopped ? 1 : 0; \
+			__syncthreads(); \
+		} }
+	for (int T = 0; T < n_macro; T += 2) {
+		NSW_V3_MACRO(0)
+		NSW_V3_MACRO(1)
+		if (!TB) { // x-drop: the last column's tracker decides; rows after the break row are never looked at
+			if (NW > 1) { if (stop_flag[(T + 1) & 1]) break; }
+			else if (__shfl_sync(0xffffffffu, (int)trk.stopped, 31)) break;
+		}
+	}
+#undef NSW_V3_MACRO
+	(void)NX;
+	if (TB) {
+		// the thread that owns column al-1 holds H(nl-1, al-1)
+		if (x == (job.al > 0 ? job.al - 1 : 0)) out[jid] = make_int4(L.score, g.nl, g.al, 0);
+	} else if (x == Wp - 1) {
+		int4 r;
+		r.x = trk.max_sc, r.y = trk.max_i + 1;
+		r.z = (trk.max_i >= 0 && trk.max_code != 0) ? 4095 - trk.max_code + 1 : g.al + 1;
+		r.w = 0;
+		out[jid] = r;
+	}
+}
+
 // ------------------------------------------------------------------ backtrack -> CIGAR
 // One warp per problem.  The walk is sequential, but it proceeds a RUN at a time (nasw_core.cuh::backtrack_runs): the 32
 // lanes fetch the next 32 cells along the current move direction in one round trip and a ballot tells how far the run
 // goes, instead of one dependent L2 access per cell (introns are thousands of cells long).
 struct DevScan {
 	const uint16_t *base;
-	int C, Wp, T, lane;
+	int C, Wp, T, lane; // C == 0: block-wide wavefront layout, word of cell (i, j) at ((i - 2) + 3 j) * Wp + j
 	__device__ __forceinline__ uint32_t at(int i, int j) const
 	{
+		if (C == 0) return base[(int64_t)(i - 2 + 3 * j) * Wp + j];
 		const int pass = j / Wp, jc = j - pass * Wp, ln = jc / C;
 		return base[((int64_t)pass * T + (i - 2 + ln)) * Wp + jc];
 	}
@@ -269,7 +350,7 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_bt_kernel(const DpDev *j
 	const int jid = order[slot];
 	const DpDev job = jobs[jid];
 	DevScan sc;
-	sc.base = tb + job.tb_off, sc.C = job.C, sc.Wp = 32 * job.C, sc.T = job.nl > 2 ? job.nl - 2 + 32 : 0, sc.lane = lane;
+	sc.base = tb + job.tb_off, sc.C = job.C, sc.Wp = job.C ? 32 * job.C : job.pad_, sc.T = job.nl > 2 ? job.nl - 2 + 32 : 0, sc.lane = lane;
 	const int n = backtrack_runs(sc, job.nl, job.al, cigar + job.cig_off, job.cig_cap, lane == 0);
 	if (lane == 0) out[jid].w = n;
 }
@@ -322,6 +403,29 @@ void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order,
 	case 4: launch_tb<4, false>(st, jobs, order, n, rec, aa, cst, out, carry, tb); break;
 	case 8: launch_tb<8, false>(st, jobs, order, n, rec, aa, cst, out, carry, tb); break;
 	default: launch_tb<8, true>(st, jobs, order, n, rec, aa, cst, out, carry, tb); break;
+	}
+}
+
+template <int NW, bool TB>
+static void launch_v3(cudaStream_t st, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, uint16_t *tb)
+{
+	nasw_v3_kernel<NW, TB><<<n, NW * 32, 22 * 32 * NW * (int)sizeof(int), st>>>(jobs, order, n, rec, aa, cst, out, tb);
+}
+
+// block-wide wavefront kernels: nw = warps per problem (1, 2, 4 or 8)
+void nasw_launch_v3(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out,
+                    uint16_t *tb)
+{
+	if (n <= 0) return;
+	switch (nw * 2 + (is_tb ? 1 : 0)) {
+	case 2: launch_v3<1, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	case 3: launch_v3<1, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	case 4: launch_v3<2, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	case 5: launch_v3<2, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	case 8: launch_v3<4, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	case 9: launch_v3<4, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	case 16: launch_v3<8, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	default: launch_v3<8, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
 	}
 }
 

@@ -158,6 +158,81 @@ void run_tb(const Problem &P, int *score, std::vector<uint32_t> &cigar)
 	cigar.assign(buf2.begin() + (cap - n2), buf2.end());
 }
 
+// block-wide wavefront (Lane3): NW*32 threads in lockstep, thread x <- thread x-1 from the previous macro-step
+template <bool TB>
+void run_v3(const Problem &P, int *score, int *nt_len, int *aa_len, std::vector<uint32_t> &cigar)
+{
+	int NW = (P.W8 + 31) / 32;
+	NW = NW <= 1 ? 1 : NW <= 2 ? 2 : NW <= 4 ? 4 : 8;
+	const int Wp = 32 * NW, n_macro = P.nl > 2 ? (P.nl - 2 + 2) / 3 + Wp : 0;
+	std::vector<int> prof(22 * Wp);
+	for (int j = 0; j < Wp; ++j)
+		for (int a = 0; a < 22; ++a) prof[a * Wp + j] = j < P.al ? P.mat[a * 22 + P.aas[j]] : NEG;
+	std::vector<Lane3<TB>> L((size_t)Wp);
+	std::vector<Geo3> g((size_t)Wp);
+	std::vector<EmuEnv> env((size_t)Wp);
+	std::vector<ExtTracker> trk((size_t)Wp);
+	std::vector<uint16_t> tb(TB ? (size_t)(3 * (n_macro + 2)) * Wp : 1, 0xffff);
+	PenTable pt;
+	pen_table_build(P.ie_coef, pt);
+	for (int x = 0; x < Wp; ++x) {
+		g[x].x = x, g[x].nl = P.nl, g[x].al = P.al, g[x].W8 = P.W8, g[x].live = x < P.W8, g[x].first = x == 0;
+		env[x].rec = P.rec.data(), env[x].nl = P.nl, env[x].prof = prof.data() + x, env[x].Wp = Wp, env[x].cy = 0;
+		L[x].init(g[x], P.end_bonus, P.par.fs, env[x]);
+		trk[x].init();
+	}
+	std::vector<int> sH((size_t)Wp * 3), sI((size_t)Wp * 3), sX((size_t)Wp * 3), sS((size_t)Wp * 3);
+	for (int T = 0; T < n_macro + (n_macro & 1); ++T) {
+		for (int x = 0; x < Wp; ++x)
+			for (int r = 0; r < 3; ++r) sH[x * 3 + r] = L[x].oH[r], sI[x * 3 + r] = L[x].oI[r], sX[x * 3 + r] = L[x].oX[r], sS[x * 3 + r] = L[x].oS[r];
+		for (int x = 0; x < Wp; ++x) {
+			const int s = x ? x - 1 : 0; // what __shfl_up_sync(..., 1) / the shared-memory slot delivers
+			uint32_t wd[3];
+			bool done[3];
+			if (T & 1) L[x].template macro<1>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd, done);
+			else L[x].template macro<0>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd, done);
+			for (int r = 0; r < 3; ++r) {
+				if (!done[r]) continue;
+				if (TB) tb[(size_t)(3 * T + r) * Wp + x] = (uint16_t)wd[r];
+				else trk[x].row(Lane3<TB>::row_of(g[x], T, r), L[x].oX[r], P.al * 3, pt, P.xdrop);
+			}
+		}
+		if (!TB && (T & 1) && trk[Wp - 1].stopped) break;
+	}
+	if (TB) {
+		*score = L[P.al > 0 ? P.al - 1 : 0].score;
+		auto at = [&](int i, int j) -> uint32_t { return tb[(size_t)(i - 2 + 3 * j) * Wp + j]; };
+		struct CpuScan {
+			decltype(at) &tbf;
+			uint32_t word(int i, int j) const { return tbf(i, j); }
+			int lead(int kind, int i, int j, int &n_valid) const
+			{
+				const int di = kind == 0 ? 3 : kind == 1 ? 0 : kind == 2 ? 3 : 1, dj = kind <= 1 ? 1 : 0;
+				int c = 0;
+				bool open = true;
+				n_valid = 0;
+				for (int k = 0; k < 32; ++k) {
+					const int ii = i - di * k, jj = j - dj * k;
+					if (ii < 2 || jj < 0) break;
+					++n_valid;
+					const uint32_t x = tbf(ii, jj);
+					const bool ok = kind == 0 ? ((x >> 9 & 1) ? false : (x & 0xf) == 0) : (x >> (kind + 3) & 1);
+					if (open && ok) ++c; else open = false;
+				}
+				return c;
+			}
+		} scan{at};
+		const int cap = P.nl + P.al + 8;
+		std::vector<uint32_t> buf((size_t)cap);
+		const int n = backtrack_runs(scan, P.nl, P.al, buf.data(), cap, true);
+		cigar.assign(buf.begin() + (cap - n), buf.end());
+	} else {
+		const ExtTracker &t = trk[Wp - 1];
+		*score = t.max_sc, *nt_len = t.max_i + 1;
+		*aa_len = (t.max_i >= 0 && t.max_code != 0) ? 4095 - t.max_code + 1 : P.al + 1;
+	}
+}
+
 } // namespace
 
 extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *codon, const int8_t *mat, const int32_t *sp, int go, int ge, int io,
@@ -183,7 +258,13 @@ extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *
 	for (int j = 0; j < al; ++j) P.aas[(size_t)j] = aa20[(uint8_t)as[left ? al - 1 - j : j]];
 	*nt_len = nl, *aa_len = al;
 	int n_cig = 0;
-	if (flag & 6) {
+	if (C == 0) { // block-wide wavefront kernels
+		std::vector<uint32_t> cg;
+		if (flag & 6) run_v3<false>(P, score, nt_len, aa_len, cg);
+		else run_v3<true>(P, score, nt_len, aa_len, cg);
+		n_cig = (int)cg.size();
+		for (int k = 0; k < n_cig && k < cigar_cap; ++k) cigar[k] = cg[(size_t)k];
+	} else if (flag & 6) {
 		switch (C) {
 		case 1: P.W8 <= 32 ? run_ext<1, false>(P, score, nt_len, aa_len) : run_ext<1, true>(P, score, nt_len, aa_len); break;
 		case 2: P.W8 <= 64 ? run_ext<2, false>(P, score, nt_len, aa_len) : run_ext<2, true>(P, score, nt_len, aa_len); break;

@@ -31,7 +31,7 @@ def emu(hc, nt, aa, flag, Ccols, mat, par):
     return sc.value, ntl.value, aal.value, [cig[i] for i in range(n)]
 
 
-@pytest.mark.parametrize("Ccols", [1, 2, 4, 8])
+@pytest.mark.parametrize("Ccols", [0, 1, 2, 4, 8])  # 0 = block-wide wavefront kernels (one thread per column, 3 rows per step)
 def test_emu_matches_oracle(hc, Ccols):
     rng = np.random.default_rng(1000 + Ccols)
     tab, mat = ol.ref_tables(), ol.default_mat()
@@ -39,8 +39,8 @@ def test_emu_matches_oracle(hc, Ccols):
         par = dict(ol.DEFAULT_NASW)
         if it % 5 == 0:
             par["sp"] = (8, 15, 21, 30, 4, 4)
-        al_max = (30, 70, 140, 300)[[1, 2, 4, 8].index(Ccols)]
-        if it % 6 == 0:
+        al_max = (250, 30, 70, 140, 300)[[0, 1, 2, 4, 8].index(Ccols)]
+        if it % 6 == 0 and Ccols:
             al_max = 32 * Ccols * 2 + 20  # force several column passes
         nt, aa = ol.random_dp_problem(rng, al_max=al_max, flank=60)
         if len(nt) < 3:
@@ -64,12 +64,14 @@ def test_emu_xdrop_and_tiny(hc):
         nt, aa = ol.random_dp_problem(rng, al_max=30, intron_max=0, flank=0)
         nt = np.concatenate([nt, np.full(500, 4, np.uint8)])
         assert ol.ora_nasw(tab, nt, aa, 4, mat, par)[:3] == emu(hc, nt, aa, 4, 1, mat, par)[:3]
+        assert ol.ora_nasw(tab, nt, aa, 4, mat, par)[:3] == emu(hc, nt, aa, 4, 0, mat, par)[:3]
     for nl in (0, 1, 2, 3, 4, 5):  # degenerate global problems (no DP rows for nl < 3)
         for al in (1, 2, 9):
             nt = rng.integers(0, 4, size=nl).astype(np.uint8)
             aa = bytes(b"ARNDCQEGH"[:al])
-            a, b = ol.ora_nasw(tab, nt, aa, 1, mat, dict(ol.DEFAULT_NASW)), emu(hc, nt, aa, 1, 1, mat, dict(ol.DEFAULT_NASW))
-            assert a[0] == b[0] and a[3] == b[3], (nl, al, a, b)
+            for cc in (1, 0):
+                a, b = ol.ora_nasw(tab, nt, aa, 1, mat, dict(ol.DEFAULT_NASW)), emu(hc, nt, aa, 1, cc, mat, dict(ol.DEFAULT_NASW))
+                assert a[0] == b[0] and a[3] == b[3], (nl, al, cc, a, b)
 
 
 def test_pen_table_equals_fp_formula(hc):
