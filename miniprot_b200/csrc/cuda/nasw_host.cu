@@ -27,10 +27,15 @@ static inline int pick_C(int al)
 // Kernel family: the block-wide wavefront (one thread per column, nasw_v3_kernel) serves every problem of up to 256 padded
 // columns; wider ones use the column-pass kernels (8 columns per lane, several passes).  MPB_NASW_KERNEL=cols forces the
 // column-pass family for everything (A/B measurements only).
-static inline bool use_v3(int al)
+// Measured on B200 (profiles/README.md): per nucleotide row the block-wide kernel is ~2x faster (it sets the critical path
+// of a wave: 100 k-row extensions), per cell the column-pass kernels are up to 3x more efficient on wide problems (8 columns
+// per lane amortise the per-step overhead).  So long problems take the former, short ones the latter.
+static inline bool use_v3(int al, int nl)
 {
-	static const int forced_cols = [] { const char *e = getenv("MPB_NASW_KERNEL"); return e && strcmp(e, "cols") == 0; }();
-	return !forced_cols && (al + 7) / 8 * 8 <= 256;
+	const char *e = getenv("MPB_NASW_KERNEL"); // A/B switch for tests and measurements: "cols" or "v3" forces one family
+	const int forced = !e ? 0 : strcmp(e, "cols") == 0 ? 1 : strcmp(e, "v3") == 0 ? 2 : 0;
+	if (forced) return forced == 2 && (al + 7) / 8 * 8 <= 256;
+	return nl >= 4096 && (al + 7) / 8 * 8 <= 256;
 }
 static inline int v3_warps(int al)
 {
@@ -61,7 +66,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	for (int k = 0; k < n; ++k) {
 		DpDev &j = jobs[lo + k];
 		const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
-		const bool v3 = use_v3(j.al);
+		const bool v3 = use_v3(j.al, j.nl);
 		const int nw = v3_warps(j.al);
 		j.C = v3 ? 0 : pick_C(j.al);
 		j.pad_ = v3 ? 32 * nw : 0;
@@ -178,7 +183,7 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_
 		while (hi < n) {
 			const DpDev &j = jobs[hi];
 			const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
-			const bool v3 = use_v3(j.al);
+			const bool v3 = use_v3(j.al, j.nl);
 			const int C = pick_C(j.al), Wp = v3 ? 32 * v3_warps(j.al) : 32 * C, W8 = (j.al + 7) / 8 * 8, n_pass = v3 ? 1 : (W8 + Wp - 1) / Wp;
 			const size_t tbb = is_tb ? (size_t)n_pass * (size_t)(j.nl + 3 * Wp + 64) * Wp * 2 : 0, rwb = (size_t)(j.nl + 4) * 32;
 			if (hi > lo && (tb_bytes + tbb > kTbBudget || rw_bytes + rwb > kRwBudget)) break;

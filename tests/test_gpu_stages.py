@@ -31,8 +31,12 @@ def _par(opt):
                 sp_null_bonus=opt.sp_null_bonus, ie_coef=opt.ie_coef)
 
 
-@pytest.mark.parametrize("model", [1, 2])
-def test_nasw_batch_matches_oracle(ctx, model):
+@pytest.mark.parametrize("model,family", [(1, "auto"), (2, "v3"), (1, "v3"), (2, "cols")])
+def test_nasw_batch_matches_oracle(ctx, model, family, monkeypatch):
+    """family: which kernel family serves the problems -- the block-wide wavefront (v3), the column-pass kernels, or the
+    production heuristic (long problems v3, short ones column passes)."""
+    if family != "auto":
+        monkeypatch.setenv("MPB_NASW_KERNEL", family)
     rng = np.random.default_rng(77 + model)
     opt = mp.nsopt()
     mp.lib().ns_opt_set_sp(C.byref(opt), model)
