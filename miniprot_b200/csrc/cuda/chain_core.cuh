@@ -132,8 +132,8 @@ CHN_HD int resolve_chunk(uint32_t rec, uint32_t skip, int32_t max_skip, int32_t 
 CHN_HD uint64_t rec_key(uint64_t r) { return r >> 32; }
 
 // chain.c:8-24.  T is the mark array type (int32 in global memory, or int8 when it lives in shared memory).
-template <class T>
-CHN_HD int64_t bk_end(int32_t max_drop, uint64_t z, const int32_t *f, const int32_t *p, T *t)
+template <class T, class FT, class PT>
+CHN_HD int64_t bk_end(int32_t max_drop, uint64_t z, const FT *f, const PT *p, T *t)
 {
 	const int32_t zx = (int32_t)(z >> 32);
 	int64_t i = (int64_t)(uint32_t)z, end_i = -1, max_i = i;
@@ -142,7 +142,7 @@ CHN_HD int64_t bk_end(int32_t max_drop, uint64_t z, const int32_t *f, const int3
 	do {
 		t[i] = 2;
 		end_i = i = p[i];
-		const int32_t s = i < 0 ? zx : zx - f[i];
+		const int32_t s = i < 0 ? zx : zx - (int32_t)f[i];
 		if (s > max_s) max_s = s, max_i = i;
 		else if (max_s - s > max_drop) break;
 	} while (i >= 0 && t[i] == 0);
@@ -155,8 +155,10 @@ CHN_HD int64_t bk_end(int32_t max_drop, uint64_t z, const int32_t *f, const int3
 // the peeling and serves as the chain-offset table of the compaction).
 // Output: u[0..n_u) = score<<32|cnt, b[0..n_b) = compacted anchors (chains ordered by target start).  Returns n_u.
 // PRESORTED: z[] has already been sorted by the caller (the warp-cooperative sort of the shared-memory kernel).
-template <class T, bool PRESORTED = false>
-CHN_HD int32_t peel_and_compact(const Par &p, int32_t n_z, const uint64_t *a, int32_t *f, const int32_t *pp, T *t, int32_t *v, uint64_t *z,
+// FT / PT: element types of the score and predecessor arrays (int32 in global memory; uint16 / int16 copies in shared
+// memory for problems of fewer than 32768 anchors whose scores fit 16 bits).
+template <class T, bool PRESORTED = false, class FT = int32_t, class PT = int32_t>
+CHN_HD int32_t peel_and_compact(const Par &p, int32_t n_z, const uint64_t *a, FT *f, const PT *pp, T *t, int32_t *v, uint64_t *z,
                                 mpb::FlagRange<uint64_t> *stack, uint64_t *u, uint64_t *b, int32_t *n_b_out)
 {
 	const int32_t max_drop = p.is_spliced ? INT32_MAX : p.bw;
@@ -171,7 +173,7 @@ CHN_HD int32_t peel_and_compact(const Par &p, int32_t n_z, const uint64_t *a, in
 		const int64_t end_i = bk_end(max_drop, z[k], f, pp, t);
 		int64_t i;
 		for (i = zi; i != end_i; i = pp[i]) v[n_v++] = (int32_t)i, t[i] = 1;
-		const int32_t sc = i < 0 ? zx : zx - f[i];
+		const int32_t sc = i < 0 ? zx : zx - (int32_t)f[i];
 		if (sc >= p.min_sc && n_v > n_v0 && n_v - n_v0 >= p.min_cnt) u[n_u++] = (uint64_t)sc << 32 | (uint64_t)(n_v - n_v0);
 		else n_v = n_v0;
 	}
@@ -181,13 +183,13 @@ CHN_HD int32_t peel_and_compact(const Par &p, int32_t n_z, const uint64_t *a, in
 	for (int32_t i = 0; i < n_u; ++i) {
 		const int32_t ni = (int32_t)(uint32_t)u[i];
 		z[i] = (a[v[k + ni - 1]] >> 32) << 32 | (uint32_t)i; // first anchor of the chain after reversal
-		f[i] = k;
+		f[i] = (FT)k;
 		k += ni;
 	}
 	mpb::flag_sort_by(z, z + n_u, [](const uint64_t &e) { return rec_key(e); }, stack);
 	int32_t o = 0;
 	for (int32_t i = 0; i < n_u; ++i) {
-		const int32_t src = (int32_t)(uint32_t)z[i], k0 = f[src], ni = (int32_t)(uint32_t)u[src];
+		const int32_t src = (int32_t)(uint32_t)z[i], k0 = (int32_t)f[src], ni = (int32_t)(uint32_t)u[src];
 		for (int32_t j = 0; j < ni; ++j) b[o++] = a[v[k0 + (ni - j - 1)]];
 	}
 	for (int32_t i = 0; i < n_u; ++i) z[i] = u[(uint32_t)z[i]]; // u2[i] = u[perm[i]]

@@ -9,12 +9,13 @@ namespace cuda {
 
 constexpr int CHAIN_STACK = 1100; // pending ranges of the flag sort per problem (<= 4 significant key bytes)
 
-void chain_launch_fill(cudaStream_t st, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, int n_prob, const chn::Par &par, int32_t *f, int32_t *p,
-                       int32_t *t);
-// backtrack of the problems list[0..n_list): shared-memory warp kernel for problems of at most `cap` anchors ...
-void chain_launch_bt_smem(cudaStream_t st, const int32_t *list, int n_list, int cap, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, const chn::Par &par,
-                          int32_t *f, const int32_t *p, int32_t *v, void *stack, uint64_t *u, uint64_t *b, int32_t *n_u, int32_t *n_b, int resort);
-// ... and the global-memory single-thread kernel for larger ones
+// score fill of the problems list[0..n_prob) (list == NULL: problems 0..n_prob-1), per-anchor state in global memory
+void chain_launch_fill(cudaStream_t st, const int32_t *list, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, int n_prob, const chn::Par &par, int32_t *f,
+                       int32_t *p, int32_t *t);
+// fill + backtrack + compaction of problems of at most `cap` (< 32768) anchors, everything in shared memory
+void chain_launch_smem(cudaStream_t st, const int32_t *list, int n_list, int cap, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, const chn::Par &par,
+                       int32_t *v, void *stack, uint64_t *u, uint64_t *b, int32_t *n_u, int32_t *n_b, int resort);
+// backtrack + compaction for larger problems: one thread each, global memory
 void chain_launch_bt(cudaStream_t st, const int32_t *list, int n_list, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, const chn::Par &par, int32_t *f,
                      const int32_t *p, int32_t *t, int32_t *v, void *z, void *stack, uint64_t *u, uint64_t *b, int32_t *n_u, int32_t *n_b, int resort);
 

@@ -19,12 +19,13 @@ using namespace chn;
 
 constexpr int CHAIN_WARPS = 4;
 
-__global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_fill_kernel(const int64_t *a_off, const int32_t *cnt, const uint64_t *a_all, int n_prob, Par par,
+__global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_fill_kernel(const int32_t *list, const int64_t *a_off, const int32_t *cnt, const uint64_t *a_all, int n_prob, Par par,
                                                                      int32_t *f_all, int32_t *p_all, int32_t *t_all)
 {
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int prob = blockIdx.x * CHAIN_WARPS + warp;
-	if (prob >= n_prob) return;
+	const int slot = blockIdx.x * CHAIN_WARPS + warp;
+	if (slot >= n_prob) return;
+	const int prob = list ? list[slot] : slot;
 	const int64_t base = a_off[prob];
 	const int32_t n = cnt ? cnt[prob] : (int32_t)(a_off[prob + 1] - base);
 	const uint64_t *a = a_all + base;
@@ -144,13 +145,14 @@ __device__ void flag_sort_warp(uint64_t *rec, int n, KeyFn key, FlagRange<uint64
 	}
 }
 
-// Backtrack + compaction, one WARP per problem, sort records and marks in shared memory.
-// Lanes cooperate on the parallel parts (clearing marks, gathering the (score, index) records in order, re-sorting the
-// kept anchors' staging copies); lane 0 runs the order-dependent part (flag sort, best-first peeling, chain ordering)
-// against shared memory instead of one dependent L2 access per step.
-__global__ void __launch_bounds__(32) chain_bt_smem_kernel(const int32_t *list, int n_list, int cap, const int64_t *a_off, const int32_t *cnt, const uint64_t *a_all,
-                                                          Par par, int32_t *f_all, const int32_t *p_all, int32_t *v_all, FlagRange<uint64_t> *stack_all,
-                                                          uint64_t *u_all, uint64_t *b_all, int32_t *n_u_out, int32_t *n_b_out, int resort)
+// Whole mp_chain for one problem in ONE warp with all per-anchor state in shared memory: scores f (int32), predecessors p
+// and scan marks t (int16: fewer than 32768 anchors), sort records (8 B).  Phase 1 is the score fill of chain_fill_kernel
+// with shared-memory state (an L2 round trip per dependent access otherwise dominates: ~2 us per anchor), phase 2 the
+// backtrack: lanes gather the (score, index) records and clear the marks, the warp-cooperative flag sort orders them with
+// the reference's tie order, lane 0 peels chains best-first and compacts; the pre-chain re-sorts the kept anchors.
+__global__ void __launch_bounds__(32) chain_smem_kernel(const int32_t *list, int n_list, int cap, const int64_t *a_off, const int32_t *cnt, const uint64_t *a_all,
+                                                       Par par, int32_t *v_all, FlagRange<uint64_t> *stack_all, uint64_t *u_all, uint64_t *b_all,
+                                                       int32_t *n_u_out, int32_t *n_b_out, int resort)
 {
 	extern __shared__ uint64_t zs[];
 	__shared__ WarpSortScratch ws;
@@ -158,13 +160,64 @@ __global__ void __launch_bounds__(32) chain_bt_smem_kernel(const int32_t *list, 
 	const int prob = list[blockIdx.x], lane = threadIdx.x;
 	const int64_t base = a_off[prob];
 	const int32_t n = cnt ? cnt[prob] : (int32_t)(a_off[prob + 1] - base);
-	int8_t *ts = (int8_t*)(zs + cap);
-	int32_t *f = f_all + base;
+	const uint64_t *a = a_all + base;
+	int32_t *f = (int32_t*)(zs + cap);
+	int16_t *p = (int16_t*)(f + cap), *t = p + cap;
+	for (int32_t i = lane; i < n; i += 32) t[i] = 0;
+	__syncwarp();
+	// ---- phase 1: fill (chain.c:181-209), identical logic to chain_fill_kernel
+	int32_t st = 0, hi = -1, hf = 0;
+	for (int32_t i = 0; i < n; ++i) {
+		const uint64_t ai = a[i];
+		const int64_t xi = (int64_t)(ai >> 32);
+		while (st < i && ((xi - (int64_t)(a[st] >> 32)) << par.bbit) > par.max_dist_x) ++st;
+		int32_t max_f = par.kmer, max_j = -1, n_skip = 0;
+		if (hi >= 0 && hi >= st) {
+			const int32_t sc = hf + pair_score(par, ai, a[hi]);
+			if (sc > max_f) max_f = sc, max_j = hi;
+		} else hf = 0, hi = -1;
+		if (i - st > par.max_iter) st = i - par.max_iter;
+		for (int32_t jb = i - 1; jb >= st; jb -= 32) {
+			const int32_t j = jb - lane;
+			bool ok = j >= st;
+			int32_t sc = INT32_MIN, pj = -1;
+			if (ok) {
+				sc = pair_score(par, ai, a[j]);
+				ok = sc != INT32_MIN;
+				if (ok) sc += f[j], pj = p[j];
+			}
+			if (ok && pj >= 0) t[pj] = (int16_t)i;
+			__syncwarp();
+			const bool marked = ok && t[j] == (int16_t)i;
+			int32_t pm = ok ? sc : INT32_MIN;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int32_t o = __shfl_up_sync(0xffffffffu, pm, d);
+				if (lane >= d) pm = pm > o ? pm : o;
+			}
+			int32_t before = __shfl_up_sync(0xffffffffu, pm, 1);
+			if (lane == 0) before = INT32_MIN;
+			before = before > max_f ? before : max_f;
+			const bool rec = ok && sc > before;
+			const uint32_t R = __ballot_sync(0xffffffffu, rec), S = __ballot_sync(0xffffffffu, ok && !rec && marked);
+			const int brk = resolve_chunk(R, S, par.max_skip, n_skip);
+			const uint32_t Rb = brk >= 32 ? R : (R & ((1u << brk) - 1u));
+			if (Rb) {
+				const int top = 31 - __clz(Rb);
+				max_f = __shfl_sync(0xffffffffu, sc, top), max_j = jb - top;
+			}
+			if (brk < 32) break;
+		}
+		if (lane == 0) f[i] = max_f, p[i] = (int16_t)max_j;
+		__syncwarp();
+		if (hf < max_f) hf = max_f, hi = i;
+	}
+	// ---- phase 2: backtrack + compaction (chain.c:26-110)
 	int32_t n_z = 0;
 	for (int32_t i0 = 0; i0 < n; i0 += 32) {
 		const int32_t i = i0 + lane;
 		const bool keep = i < n && f[i] >= par.min_sc;
-		if (i < n) ts[i] = 0;
+		if (i < n) t[i] = 0;
 		const uint32_t m = __ballot_sync(0xffffffffu, keep);
 		if (keep) zs[n_z + __popc(m & ((1u << lane) - 1u))] = (uint64_t)(uint32_t)f[i] << 32 | (uint32_t)i;
 		n_z += __popc(m);
@@ -172,12 +225,13 @@ __global__ void __launch_bounds__(32) chain_bt_smem_kernel(const int32_t *list, 
 	__syncwarp();
 	int32_t n_u = 0, n_b = 0;
 	FlagRange<uint64_t> *stack = stack_all + (int64_t)prob * CHAIN_STACK;
-	flag_sort_warp(zs, n_z, [](const uint64_t &e) { return rec_key(e); }, stack, &ws, lane); // chain ends by score, reference tie order
+	flag_sort_warp(zs, n_z, [](const uint64_t &e) { return rec_key(e); }, stack, &ws, lane);
 	if (lane == 0 && n > 0)
-		n_u = peel_and_compact<int8_t, true>(par, n_z, a_all + base, f, p_all + base, ts, v_all + base, zs, stack, u_all + base, b_all + base, &n_b);
+		n_u = peel_and_compact<int16_t, true, int32_t, int16_t>(par, n_z, a, f, p, t, v_all + base, zs, stack, u_all + base, b_all + base, &n_b);
 	n_b = __shfl_sync(0xffffffffu, n_b, 0);
 	if (resort && n_b > 1) { // map.c:191: the anchors kept by the pre-chain go back into plain sorted order
 		uint64_t *b = b_all + base;
+		__syncwarp();
 		for (int32_t i = lane; i < n_b; i += 32) zs[i] = b[i];
 		__syncwarp();
 		flag_sort_warp(zs, n_b, [](const uint64_t &x) { return x; }, stack, &ws, lane);
@@ -206,19 +260,20 @@ __global__ void __launch_bounds__(32) chain_bt_kernel(const int32_t *list, int n
 	n_u_out[prob] = n_u, n_b_out[prob] = n_b;
 }
 
-void chain_launch_fill(cudaStream_t st, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, int n_prob, const Par &par, int32_t *f, int32_t *p, int32_t *t)
+void chain_launch_fill(cudaStream_t st, const int32_t *list, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, int n_prob, const Par &par, int32_t *f, int32_t *p,
+                       int32_t *t)
 {
-	if (n_prob > 0) chain_fill_kernel<<<(n_prob + CHAIN_WARPS - 1) / CHAIN_WARPS, CHAIN_WARPS * 32, 0, st>>>(a_off, cnt, a, n_prob, par, f, p, t);
+	if (n_prob > 0) chain_fill_kernel<<<(n_prob + CHAIN_WARPS - 1) / CHAIN_WARPS, CHAIN_WARPS * 32, 0, st>>>(list, a_off, cnt, a, n_prob, par, f, p, t);
 }
 
-void chain_launch_bt_smem(cudaStream_t st, const int32_t *list, int n_list, int cap, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, const Par &par,
-                          int32_t *f, const int32_t *p, int32_t *v, void *stack, uint64_t *u, uint64_t *b, int32_t *n_u, int32_t *n_b, int resort)
+void chain_launch_smem(cudaStream_t st, const int32_t *list, int n_list, int cap, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, const Par &par, int32_t *v,
+                       void *stack, uint64_t *u, uint64_t *b, int32_t *n_u, int32_t *n_b, int resort)
 {
 	if (n_list <= 0) return;
-	const int smem = cap * 9 + 16;
+	const int smem = cap * 16 + 16;
 	static int attr_max = 0;
-	if (smem > attr_max) { cudaFuncSetAttribute(chain_bt_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_max = smem; }
-	chain_bt_smem_kernel<<<n_list, 32, smem, st>>>(list, n_list, cap, a_off, cnt, a, par, f, p, v, (FlagRange<uint64_t>*)stack, u, b, n_u, n_b, resort);
+	if (smem > attr_max) { cudaFuncSetAttribute(chain_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_max = smem; }
+	chain_smem_kernel<<<n_list, 32, smem, st>>>(list, n_list, cap, a_off, cnt, a, par, v, (FlagRange<uint64_t>*)stack, u, b, n_u, n_b, resort);
 }
 
 void chain_launch_bt(cudaStream_t st, const int32_t *list, int n_list, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, const Par &par, int32_t *f,

@@ -78,9 +78,10 @@ static void chain_problems(mpb_ctx_s *ctx, int n_prob, const std::vector<int64_t
 	ctx->b_c[8].reserve(carve_size(layout));
 	Carver cv(ctx->b_c[8].p);
 	layout(cv);
-	// size classes of the backtrack kernel (anchors per problem -> shared memory per warp); sizes are taken from the
-	// offsets, an upper bound for the main chain that follows a pre-chain
-	static const int caps[3] = { 2048, 8192, 25000 };
+	// size classes: problems whose per-anchor state fits in shared memory (16 B per anchor) run fill + backtrack fused in
+	// one warp-per-problem kernel; larger ones use the global-memory fill + single-thread backtrack.  Sizes come from the
+	// offsets (an upper bound for the main chain that follows a pre-chain).  Classes run concurrently on side streams.
+	static const int caps[3] = { 4096, 8192, 13312 }; // 64 / 128 / 208 KB of shared memory per warp
 	std::vector<int32_t> lists[4];
 	for (int i = 0; i < n_prob; ++i) {
 		const int64_t n = h_off[(size_t)i + 1] - h_off[(size_t)i];
@@ -90,32 +91,32 @@ static void chain_problems(mpb_ctx_s *ctx, int n_prob, const std::vector<int64_t
 	size_t lfirst[4];
 	for (int c = 0; c < 4; ++c) lfirst[c] = flat.size(), flat.insert(flat.end(), lists[c].begin(), lists[c].end());
 	MPB_CUDA_OK(cudaMemcpyAsync(d_list, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice, st));
-	auto backtrack = [&](const int32_t *cnt, const uint64_t *in, const chn::Par &par, uint64_t *uo, uint64_t *bo, int32_t *nuo, int32_t *nbo, int resort) {
-		// the classes are independent: run them on side streams (each is bounded by its slowest problem)
+	auto chain_once = [&](const int32_t *cnt, const uint64_t *in, const chn::Par &par, uint64_t *uo, uint64_t *bo, int32_t *nuo, int32_t *nbo, int resort) {
 		MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
 		for (int c = 0; c < 4; ++c) {
 			if (lists[c].empty()) continue;
 			cudaStream_t ss = ctx->side[c];
 			MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
-			if (c < 3) chain_launch_bt_smem(ss, d_list + lfirst[c], (int)lists[c].size(), caps[c], d_off, cnt, in, par, f, p, v, stack, uo, bo, nuo, nbo, resort);
-			else chain_launch_bt(ss, d_list + lfirst[c], (int)lists[c].size(), d_off, cnt, in, par, f, p, t, v, z, stack, uo, bo, nuo, nbo, resort);
+			if (c < 3) {
+				chain_launch_smem(ss, d_list + lfirst[c], (int)lists[c].size(), caps[c], d_off, cnt, in, par, v, stack, uo, bo, nuo, nbo, resort);
+				ctx->stats.kernel_launches += 1;
+			} else {
+				chain_launch_fill(ss, d_list + lfirst[c], d_off, cnt, in, (int)lists[c].size(), par, f, p, t);
+				chain_launch_bt(ss, d_list + lfirst[c], (int)lists[c].size(), d_off, cnt, in, par, f, p, t, v, z, stack, uo, bo, nuo, nbo, resort);
+				ctx->stats.kernel_launches += 2;
+			}
 			MPB_CUDA_OK(cudaEventRecord(ctx->ev_join[c], ss));
 			MPB_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_join[c], 0));
-			ctx->stats.kernel_launches += 1;
 		}
 	};
 	ctx->time_begin();
 	const uint64_t *in = d_a;
 	const int32_t *cnt = 0;
 	if (pre) {
-		chain_launch_fill(st, d_off, 0, d_a, n_prob, *pre, f, p, t);
-		backtrack(0, d_a, *pre, du, db, d_nu, d_nb, 1);
+		chain_once(0, d_a, *pre, du, db, d_nu, d_nb, 1);
 		in = db, cnt = d_nb;
-		ctx->stats.kernel_launches += 1;
 	}
-	chain_launch_fill(st, d_off, cnt, in, n_prob, mainp, f, p, t);
-	backtrack(cnt, in, mainp, du2, db2, d_nu2, d_nb2, 0);
-	ctx->stats.kernel_launches += 1;
+	chain_once(cnt, in, mainp, du2, db2, d_nu2, d_nb2, 0);
 	MPB_CUDA_OK(cudaMemcpyAsync(n_u.data(), d_nu2, sizeof(int32_t) * (size_t)n_prob, cudaMemcpyDeviceToHost, st));
 	MPB_CUDA_OK(cudaMemcpyAsync(n_b.data(), d_nb2, sizeof(int32_t) * (size_t)n_prob, cudaMemcpyDeviceToHost, st));
 	MPB_CUDA_OK(cudaStreamSynchronize(st));

@@ -95,3 +95,16 @@ def test_chain_batch_matches_oracle(ctx, mode):
         for a, (u, b) in zip(lists, got):
             wu, wb = ol.ora_chain(par, a)
             assert len(wu) == len(u) and (wu == u).all() and len(wb) == len(b) and (wb == b).all(), (mode, over, len(a))
+
+
+def test_chain_batch_large_problems(ctx):
+    """Problems that land in the larger shared-memory classes (<= 8192, <= 13312 anchors) and in the global-memory path."""
+    rng = np.random.default_rng(99)
+    for mode in ("pre", "main"):
+        par = ol.chain_par(mode)
+        lists = [ol.random_chain_problem(rng, n, mode) for n in (5000, 7000, 9000, 12000, 15000, 22000, 300)]
+        mpar = mp.ChainPar(**{f: getattr(par, f) for f, _ in mp.ChainPar._fields_})
+        got = mp.chain_batch(ctx, mpar, lists)
+        for a, (u, b) in zip(lists, got):
+            wu, wb = ol.ora_chain(par, a)
+            assert len(wu) == len(u) and (wu == u).all() and len(wb) == len(b) and (wb == b).all(), (mode, len(a))
