@@ -15,7 +15,11 @@ void chain_launch_fill(cudaStream_t st, const int32_t *list, const int64_t *a_of
 // fill + backtrack + compaction of problems of at most `cap` (< 32768) anchors, everything in shared memory
 void chain_launch_smem(cudaStream_t st, const int32_t *list, int n_list, int cap, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, const chn::Par &par,
                        int32_t *v, void *stack, uint64_t *u, uint64_t *b, int32_t *n_u, int32_t *n_b, int resort);
-// backtrack + compaction for larger problems: one thread each, global memory
+// backtrack + compaction after a global-memory fill: one warp per problem, records / marks / 16-bit copies of f and p in
+// shared memory (13 B per anchor)
+void chain_launch_bt_smem(cudaStream_t st, const int32_t *list, int n_list, int cap, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, const chn::Par &par,
+                          int32_t *f, const int32_t *p, int32_t *v, void *stack, uint64_t *u, uint64_t *b, int32_t *n_u, int32_t *n_b, int resort);
+// backtrack + compaction for the largest problems: one thread each, global memory
 void chain_launch_bt(cudaStream_t st, const int32_t *list, int n_list, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, const chn::Par &par, int32_t *f,
                      const int32_t *p, int32_t *t, int32_t *v, void *z, void *stack, uint64_t *u, uint64_t *b, int32_t *n_u, int32_t *n_b, int resort);
 

@@ -240,6 +240,48 @@ __global__ void __launch_bounds__(32) chain_smem_kernel(const int32_t *list, int
 	if (lane == 0) n_u_out[prob] = n_u, n_b_out[prob] = n_b;
 }
 
+// Backtrack + compaction, one WARP per problem, sort records and marks in shared memory.
+// Lanes cooperate on the parallel parts (clearing marks, gathering the (score, index) records in order, re-sorting the
+// kept anchors' staging copies); lane 0 runs the order-dependent part (flag sort, best-first peeling, chain ordering)
+// against shared memory instead of one dependent L2 access per step.
+__global__ void __launch_bounds__(32) chain_bt_smem_kernel(const int32_t *list, int n_list, int cap, const int64_t *a_off, const int32_t *cnt, const uint64_t *a_all,
+                                                          Par par, int32_t *f_all, const int32_t *p_all, int32_t *v_all, FlagRange<uint64_t> *stack_all,
+                                                          uint64_t *u_all, uint64_t *b_all, int32_t *n_u_out, int32_t *n_b_out, int resort)
+{
+	extern __shared__ uint64_t zs[];
+	__shared__ WarpSortScratch ws;
+	if ((int)blockIdx.x >= n_list) return;
+	const int prob = list[blockIdx.x], lane = threadIdx.x;
+	const int64_t base = a_off[prob];
+	const int32_t n = cnt ? cnt[prob] : (int32_t)(a_off[prob + 1] - base);
+	int8_t *ts = (int8_t*)(zs + cap);
+	int32_t *f = f_all + base;
+	int32_t n_z = 0;
+	for (int32_t i0 = 0; i0 < n; i0 += 32) {
+		const int32_t i = i0 + lane;
+		const bool keep = i < n && f[i] >= par.min_sc;
+		if (i < n) ts[i] = 0;
+		const uint32_t m = __ballot_sync(0xffffffffu, keep);
+		if (keep) zs[n_z + __popc(m & ((1u << lane) - 1u))] = (uint64_t)(uint32_t)f[i] << 32 | (uint32_t)i;
+		n_z += __popc(m);
+	}
+	__syncwarp();
+	int32_t n_u = 0, n_b = 0;
+	FlagRange<uint64_t> *stack = stack_all + (int64_t)prob * CHAIN_STACK;
+	flag_sort_warp(zs, n_z, [](const uint64_t &e) { return rec_key(e); }, stack, &ws, lane); // chain ends by score, reference tie order
+	if (lane == 0 && n > 0)
+		n_u = peel_and_compact<int8_t, true>(par, n_z, a_all + base, f, p_all + base, ts, v_all + base, zs, stack, u_all + base, b_all + base, &n_b);
+	n_b = __shfl_sync(0xffffffffu, n_b, 0);
+	if (resort && n_b > 1) { // map.c:191: the anchors kept by the pre-chain go back into plain sorted order
+		uint64_t *b = b_all + base;
+		for (int32_t i = lane; i < n_b; i += 32) zs[i] = b[i];
+		__syncwarp();
+		flag_sort_warp(zs, n_b, [](const uint64_t &x) { return x; }, stack, &ws, lane);
+		for (int32_t i = lane; i < n_b; i += 32) b[i] = zs[i];
+	}
+	if (lane == 0) n_u_out[prob] = n_u, n_b_out[prob] = n_b;
+}
+
 // same for problems that do not fit in shared memory: one thread, everything in global memory
 __global__ void __launch_bounds__(32) chain_bt_kernel(const int32_t *list, int n_list, const int64_t *a_off, const int32_t *cnt, const uint64_t *a_all, Par par,
                                                      int32_t *f_all, const int32_t *p_all, int32_t *t_all, int32_t *v_all, uint64_t *z_all,
@@ -274,6 +316,16 @@ void chain_launch_smem(cudaStream_t st, const int32_t *list, int n_list, int cap
 	static int attr_max = 0;
 	if (smem > attr_max) { cudaFuncSetAttribute(chain_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_max = smem; }
 	chain_smem_kernel<<<n_list, 32, smem, st>>>(list, n_list, cap, a_off, cnt, a, par, v, (FlagRange<uint64_t>*)stack, u, b, n_u, n_b, resort);
+}
+
+void chain_launch_bt_smem(cudaStream_t st, const int32_t *list, int n_list, int cap, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, const Par &par,
+                          int32_t *f, const int32_t *p, int32_t *v, void *stack, uint64_t *u, uint64_t *b, int32_t *n_u, int32_t *n_b, int resort)
+{
+	if (n_list <= 0) return;
+	const int smem = cap * 9 + 16;
+	static int attr_max = 0;
+	if (smem > attr_max) { cudaFuncSetAttribute(chain_bt_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_max = smem; }
+	chain_bt_smem_kernel<<<n_list, 32, smem, st>>>(list, n_list, cap, a_off, cnt, a, par, f, p, v, (FlagRange<uint64_t>*)stack, u, b, n_u, n_b, resort);
 }
 
 void chain_launch_bt(cudaStream_t st, const int32_t *list, int n_list, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, const Par &par, int32_t *f,

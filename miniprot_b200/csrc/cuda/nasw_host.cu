@@ -29,13 +29,16 @@ static inline int pick_C(int al)
 // column-pass family for everything (A/B measurements only).
 // Measured on B200 (profiles/README.md): per nucleotide row the block-wide kernel is ~2x faster (it sets the critical path
 // of a wave: 100 k-row extensions), per cell the column-pass kernels are up to 3x more efficient on wide problems (8 columns
-// per lane amortise the per-step overhead).  So long problems take the former, short ones the latter.
+// per lane amortise the per-step overhead).  A mini-batch of the benchmark's size is latency bound (its waves last as long
+// as their longest problem), and there the block-wide kernel wins on every class; MPB_NASW_KERNEL=cols selects the
+// throughput-oriented family.
 static inline bool use_v3(int al, int nl)
 {
 	const char *e = getenv("MPB_NASW_KERNEL"); // A/B switch for tests and measurements: "cols" or "v3" forces one family
 	const int forced = !e ? 0 : strcmp(e, "cols") == 0 ? 1 : strcmp(e, "v3") == 0 ? 2 : 0;
 	if (forced) return forced == 2 && (al + 7) / 8 * 8 <= 256;
-	return nl >= 4096 && (al + 7) / 8 * 8 <= 256;
+	(void)nl;
+	return (al + 7) / 8 * 8 <= 256; // default: latency first (a mini-batch wave is bounded by its longest problems)
 }
 static inline int v3_warps(int al)
 {

@@ -78,31 +78,41 @@ static void chain_problems(mpb_ctx_s *ctx, int n_prob, const std::vector<int64_t
 	ctx->b_c[8].reserve(carve_size(layout));
 	Carver cv(ctx->b_c[8].p);
 	layout(cv);
-	// size classes: problems whose per-anchor state fits in shared memory (16 B per anchor) run fill + backtrack fused in
-	// one warp-per-problem kernel; larger ones use the global-memory fill + single-thread backtrack.  Sizes come from the
-	// offsets (an upper bound for the main chain that follows a pre-chain).  Classes run concurrently on side streams.
-	static const int caps[3] = { 4096, 8192, 13312 }; // 64 / 128 / 208 KB of shared memory per warp
-	std::vector<int32_t> lists[4];
-	for (int i = 0; i < n_prob; ++i) {
-		const int64_t n = h_off[(size_t)i + 1] - h_off[(size_t)i];
-		lists[n <= caps[0] ? 0 : n <= caps[1] ? 1 : n <= caps[2] ? 2 : 3].push_back(i);
-	}
-	std::vector<int32_t> flat;
-	size_t lfirst[4];
-	for (int c = 0; c < 4; ++c) lfirst[c] = flat.size(), flat.insert(flat.end(), lists[c].begin(), lists[c].end());
-	MPB_CUDA_OK(cudaMemcpyAsync(d_list, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice, st));
+	// Size classes (from the offsets: an upper bound for a main chain that follows a pre-chain), run concurrently on side
+	// streams:  0: <= 2048 anchors   fill + backtrack fused in one warp with ALL state in shared memory (32 KB, 7 warps per SM)
+	//           1-3: <= 5120 / 8192 / 16384   global-memory fill (every problem its own warp, ~1000 in flight) followed by
+	//                the shared-memory backtrack (13 B per anchor)
+	//           4: larger   global-memory fill + single-thread global backtrack
+	static const int caps[4] = { 2048, 5120, 8192, 16384 };
+	std::vector<int32_t> lists[5], flat, sizes((size_t)n_prob);
+	size_t lfirst[5];
+	for (int i = 0; i < n_prob; ++i) sizes[(size_t)i] = (int32_t)(h_off[(size_t)i + 1] - h_off[(size_t)i]);
+	auto classify = [&]() { // sizes[] -> per-class problem lists on the device
+		flat.clear();
+		for (int c = 0; c < 5; ++c) lists[c].clear();
+		for (int i = 0; i < n_prob; ++i) {
+			const int32_t n = sizes[(size_t)i];
+			lists[n <= caps[0] ? 0 : n <= caps[1] ? 1 : n <= caps[2] ? 2 : n <= caps[3] ? 3 : 4].push_back(i);
+		}
+		for (int c = 0; c < 5; ++c) lfirst[c] = flat.size(), flat.insert(flat.end(), lists[c].begin(), lists[c].end());
+		MPB_CUDA_OK(cudaMemcpyAsync(d_list, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice, st));
+	};
+	classify();
 	auto chain_once = [&](const int32_t *cnt, const uint64_t *in, const chn::Par &par, uint64_t *uo, uint64_t *bo, int32_t *nuo, int32_t *nbo, int resort) {
 		MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
-		for (int c = 0; c < 4; ++c) {
+		for (int c = 0; c < 5; ++c) {
 			if (lists[c].empty()) continue;
 			cudaStream_t ss = ctx->side[c];
+			const int32_t *lst = d_list + lfirst[c];
+			const int nl = (int)lists[c].size();
 			MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
-			if (c < 3) {
-				chain_launch_smem(ss, d_list + lfirst[c], (int)lists[c].size(), caps[c], d_off, cnt, in, par, v, stack, uo, bo, nuo, nbo, resort);
+			if (c == 0) {
+				chain_launch_smem(ss, lst, nl, caps[0], d_off, cnt, in, par, v, stack, uo, bo, nuo, nbo, resort);
 				ctx->stats.kernel_launches += 1;
 			} else {
-				chain_launch_fill(ss, d_list + lfirst[c], d_off, cnt, in, (int)lists[c].size(), par, f, p, t);
-				chain_launch_bt(ss, d_list + lfirst[c], (int)lists[c].size(), d_off, cnt, in, par, f, p, t, v, z, stack, uo, bo, nuo, nbo, resort);
+				chain_launch_fill(ss, lst, d_off, cnt, in, nl, par, f, p, t);
+				if (c < 4) chain_launch_bt_smem(ss, lst, nl, caps[c], d_off, cnt, in, par, f, p, v, stack, uo, bo, nuo, nbo, resort);
+				else chain_launch_bt(ss, lst, nl, d_off, cnt, in, par, f, p, t, v, z, stack, uo, bo, nuo, nbo, resort);
 				ctx->stats.kernel_launches += 2;
 			}
 			MPB_CUDA_OK(cudaEventRecord(ctx->ev_join[c], ss));
@@ -115,6 +125,10 @@ static void chain_problems(mpb_ctx_s *ctx, int n_prob, const std::vector<int64_t
 	if (pre) {
 		chain_once(0, d_a, *pre, du, db, d_nu, d_nb, 1);
 		in = db, cnt = d_nb;
+		// the pre-chain usually keeps a small fraction of the anchors: re-classify by the true sizes (a 4 B/problem copy)
+		MPB_CUDA_OK(cudaMemcpyAsync(sizes.data(), d_nb, sizeof(int32_t) * (size_t)n_prob, cudaMemcpyDeviceToHost, st));
+		MPB_CUDA_OK(cudaStreamSynchronize(st));
+		classify();
 	}
 	chain_once(cnt, in, mainp, du2, db2, d_nu2, d_nb2, 0);
 	MPB_CUDA_OK(cudaMemcpyAsync(n_u.data(), d_nu2, sizeof(int32_t) * (size_t)n_prob, cudaMemcpyDeviceToHost, st));
