@@ -414,18 +414,49 @@ struct Lane3 {
 	}
 
 	// One macro-step.  PH = T mod 2 selects the half of the record buffer.  rH/rI/rX/rS[r]: outputs of thread x-1 for row r.
-	// wd[r] receives the traceback word of row r (TB) and done[r] tells whether row r was a real row of this thread.
+	// wd[r] receives the traceback word of row r (TB); returns a bit mask of the rows that were real rows of this thread.
+	// Almost every macro-step of almost every thread has three real rows of a live column: that case is straight-line code;
+	// the ramp-up / ramp-down steps, dead columns and the very first row take the general path.
 	template <int PH, class Env>
-	NSW_HD void macro(const Geo3 &g, const Par &par, int T, const int *rH, const int *rI, const int *rX, const int *rS, Env &env, uint32_t *wd, bool *done)
+	NSW_HD uint32_t macro(const Geo3 &g, const Par &par, int T, const int *rH, const int *rI, const int *rX, const int *rS, Env &env, uint32_t *wd)
 	{
+		const int i0 = row_of(g, T, 0);
+		const RowRec rc0 = rec[3 * PH], rc1 = rec[3 * PH + 1], rc2 = rec[3 * PH + 2];
+		env.row_rec3(i0 + 6, rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2]);
+		if (g.first) env.prefetch_row(i0 + 72);
+		uint32_t done = 0;
+		if (g.live && i0 > 2 && i0 + 2 < g.nl) {
+			const int *ps = env.profile(0);
+			const int W = env.profile_stride();
+			int l0, it, lx, ls;
+#define NSW_ROW(R, RC, H1S, H2S, H3S) \
+			l0 = g.first ? NEG : rH[R], it = g.first ? NEG : rI[R], lx = g.first ? (TB ? NEG : INT32_MIN) : rX[R], ls = g.first ? NEG : (TB ? rS[R] : 0); \
+			{ \
+				const int s = ps[RC.nas * W]; \
+				int d_new; \
+				if (TB) { \
+					int f0 = seg_start ? NEG : lx, iseg = seg_start ? NEG : ls, hf; \
+					const int h = cell_trace(par, RC, s, H[H1S], H[H2S], H[H3S], D[H3S], d_new, A, B, Cc, l0, f0, L[H1S], L[H2S], L[H3S], iseg, it, hf, wd[R]); \
+					H[H3S] = h, D[H3S] = d_new, oH[R] = h, oI[R] = it, oX[R] = hf, oS[R] = iseg; \
+				} else { \
+					const int h = cell_score(par, RC, s, H[H1S], H[H2S], H[H3S], D[H3S], d_new, A, B, Cc, l0, L[H1S], L[H2S], L[H3S], it); \
+					H[H3S] = h, D[H3S] = d_new, oH[R] = h, oI[R] = it, oX[R] = imax(lx, (h + bonus) * 4096 + code); \
+				} \
+				if (!g.first) L[H3S] = rH[R]; \
+			}
+			NSW_ROW(0, rc0, 2, 1, 0)
+			NSW_ROW(1, rc1, 0, 2, 1)
+			NSW_ROW(2, rc2, 1, 0, 2)
+#undef NSW_ROW
+			if (TB && end_col && i0 + 2 == g.nl - 1) score = H[2];
+			return 7u;
+		}
 #pragma unroll
 		for (int r = 0; r < 3; ++r) {
 			const int h3 = r, h2 = (r + 1) % 3, h1 = (r + 2) % 3;
-			const int i = row_of(g, T, r);
-			const RowRec rc = rec[3 * PH + r];
-			rec[3 * PH + r] = env.row_rec(i + 6);
+			const int i = i0 + r;
+			const RowRec &rc = r == 0 ? rc0 : r == 1 ? rc1 : rc2;
 			const bool row_ok = i >= 2 && i < g.nl;
-			done[r] = false;
 			if (!row_ok) continue;
 			int l0 = rH[r], it = rI[r], lx = rX[r], ls = TB ? rS[r] : 0;
 			if (g.first) l0 = NEG, it = NEG, lx = TB ? NEG : INT32_MIN, ls = NEG;
@@ -444,12 +475,12 @@ struct Lane3 {
 					H[h3] = h, D[h3] = d_new;
 					oH[r] = h, oI[r] = it, oX[r] = imax(lx, (h + bonus) * 4096 + code);
 				}
-				done[r] = true;
-			} else if (!TB) oX[r] = lx, done[r] = true; // dead columns only hand the row maximum on
+				done |= 1u << r;
+			} else if (!TB) oX[r] = lx, done |= 1u << r; // dead columns only hand the row maximum on
 			if (!g.first) L[h3] = rH[r];
 			else if (i == 2) L[0] = L[1] = L[2] = NEG; // the boundary column is -32768 for every later row (nasw-sse.c:266-270)
 		}
-		if (g.nl > 0 && g.first) env.prefetch_row(row_of(g, T, 0) + 72);
+		return done;
 	}
 };
 

@@ -99,6 +99,18 @@ struct DevEnv {
 		r.cA = a.x, r.cB = a.y, r.cC = a.z, r.gei = a.w, r.aA = b.x, r.aB = b.y, r.aC = b.z, r.nas = b.w;
 		return r;
 	}
+	// records of rows i, i+1, i+2 with one clamp: exact whenever a real row (2 <= row < nl) is among them; the record array
+	// carries three padding rows after row nl
+	__device__ __forceinline__ void row_rec3(int i, RowRec &r0, RowRec &r1, RowRec &r2) const
+	{
+		i = i < 0 ? 0 : (i > nl ? nl : i);
+		const int4 *q = rec + 2 * i;
+		const int4 a0 = __ldg(q), b0 = __ldg(q + 1), a1 = __ldg(q + 2), b1 = __ldg(q + 3), a2 = __ldg(q + 4), b2 = __ldg(q + 5);
+		r0.cA = a0.x, r0.cB = a0.y, r0.cC = a0.z, r0.gei = a0.w, r0.aA = b0.x, r0.aB = b0.y, r0.aC = b0.z, r0.nas = b0.w;
+		r1.cA = a1.x, r1.cB = a1.y, r1.cC = a1.z, r1.gei = a1.w, r1.aA = b1.x, r1.aB = b1.y, r1.aC = b1.z, r1.nas = b1.w;
+		r2.cA = a2.x, r2.cB = a2.y, r2.cC = a2.z, r2.gei = a2.w, r2.aA = b2.x, r2.aB = b2.y, r2.aC = b2.z, r2.nas = b2.w;
+	}
+	__device__ __forceinline__ int profile_stride() const { return Wp; }
 	__device__ __forceinline__ void prefetch_row(int i) const
 	{
 		if (i <= nl) asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + 2 * (i < 0 ? 0 : i)));
@@ -278,10 +290,10 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 			_Pragma("unroll") for (int r = 0; r < 3; ++r) { rH[r] = b[r], rI[r] = b[3 + r], rX[r] = b[6 + r]; if (TB) rS[r] = b[9 + r]; } \
 		} \
 		uint32_t wd[3]; \
-		bool done[3]; \
-		L.template macro<PH>(g, par, T + PH, rH, rI, rX, rS, env, wd, done); \
-		if (TB) { _Pragma("unroll") for (int r = 0; r < 3; ++r) if (done[r]) tbp[(int64_t)(3 * (T + PH) + r) * Wp] = (uint16_t)wd[r]; } \
-		else { _Pragma("unroll") for (int r = 0; r < 3; ++r) if (done[r]) trk.row(Lane3<TB>::row_of(g, T + PH, r), L.oX[r], g.al * 3, cst.pen, cst.xdrop); } \
+		const uint32_t done = L.template macro<PH>(g, par, T + PH, rH, rI, rX, rS, env, wd); \
+		if (TB) { _Pragma("unroll") for (int r = 0; r < 3; ++r) if (done >> r & 1) tbp[(int64_t)(3 * (T + PH) + r) * Wp] = (uint16_t)wd[r]; } \
+		else if (x == Wp - 1) { /* the last column sees the complete row maxima */ \
+			_Pragma("unroll") for (int r = 0; r < 3; ++r) if (done >> r & 1) trk.row(Lane3<TB>::row_of(g, T + PH, r), L.oX[r], g.al * 3, cst.pen, cst.xdrop); } \
 		if (NW > 1) { \
 			if (lane == 31 && warp < NW - 1) { \
 				int *b = xchg[(T + PH) & 1][warp]; \

@@ -23,6 +23,8 @@ struct EmuEnv {
 	int *cy;
 	RowRec row_rec(int i) const { i = i < 0 ? 0 : (i > nl ? nl : i); return rec[i]; }
 	void prefetch_row(int) const {}
+	void row_rec3(int i, RowRec &r0, RowRec &r1, RowRec &r2) const { i = i < 0 ? 0 : (i > nl ? nl : i); r0 = rec[i], r1 = rec[i + 1], r2 = rec[i + 2]; }
+	int profile_stride() const { return Wp; }
 	const int *profile(int nas) const { return prof + nas * Wp; }
 	void carry_load3(int i, int &a, int &b, int &c) const { a = cy[(int64_t)i * 3], b = cy[(int64_t)i * 3 + 1], c = cy[(int64_t)i * 3 + 2]; }
 	void carry_store3(int i, int a, int b, int c) const { cy[(int64_t)i * 3] = a, cy[(int64_t)i * 3 + 1] = b, cy[(int64_t)i * 3 + 2] = c; }
@@ -187,12 +189,11 @@ void run_v3(const Problem &P, int *score, int *nt_len, int *aa_len, std::vector<
 			for (int r = 0; r < 3; ++r) sH[x * 3 + r] = L[x].oH[r], sI[x * 3 + r] = L[x].oI[r], sX[x * 3 + r] = L[x].oX[r], sS[x * 3 + r] = L[x].oS[r];
 		for (int x = 0; x < Wp; ++x) {
 			const int s = x ? x - 1 : 0; // what __shfl_up_sync(..., 1) / the shared-memory slot delivers
-			uint32_t wd[3];
-			bool done[3];
-			if (T & 1) L[x].template macro<1>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd, done);
-			else L[x].template macro<0>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd, done);
+			uint32_t wd[3], done;
+			if (T & 1) done = L[x].template macro<1>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd);
+			else done = L[x].template macro<0>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd);
 			for (int r = 0; r < 3; ++r) {
-				if (!done[r]) continue;
+				if (!(done >> r & 1)) continue;
 				if (TB) tb[(size_t)(3 * T + r) * Wp + x] = (uint16_t)wd[r];
 				else trk[x].row(Lane3<TB>::row_of(g[x], T, r), L[x].oX[r], P.al * 3, pt, P.xdrop);
 			}
@@ -252,7 +253,7 @@ extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *
 		r = r < 0 ? 0 : (r > nl ? nl : r);
 		w[(size_t)x] = left ? prep_row_left(c, nl, r, sp, codon, aa20['X']) : prep_row_forward(c, nl, r, sp, codon, aa20['X']);
 	}
-	P.rec.resize((size_t)nl + 1);
+	P.rec.resize((size_t)nl + 4); // three padding rows after row nl, like the device buffer
 	for (int r = 0; r <= nl; ++r) P.rec[(size_t)r] = make_row_rec(P.par, w[(size_t)r], w[(size_t)r + 1], w[(size_t)r + 2], w[(size_t)r + 3]);
 	P.aas.resize((size_t)al);
 	for (int j = 0; j < al; ++j) P.aas[(size_t)j] = aa20[(uint8_t)as[left ? al - 1 - j : j]];
