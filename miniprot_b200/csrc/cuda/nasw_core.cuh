@@ -413,44 +413,64 @@ struct Lane3 {
 		for (int k = 0; k < 6; ++k) rec[k] = env.row_rec(i0 + k);
 	}
 
-	// One macro-step.  PH = T mod 2 selects the half of the record buffer.  rH/rI/rX/rS[r]: outputs of thread x-1 for row r.
-	// wd[r] receives the traceback word of row r (TB); returns a bit mask of the rows that were real rows of this thread.
-	// Almost every macro-step of almost every thread has three real rows of a live column: that case is straight-line code;
-	// the ramp-up / ramp-down steps, dead columns and the very first row take the general path.
+	// Three real rows of a live column, straight-line (no per-row validity checks): the body of every steady-state step.
+	NSW_HD void rows3(const Geo3 &g, const Par &par, const RowRec &rc0, const RowRec &rc1, const RowRec &rc2, const int *rH, const int *rI, const int *rX,
+	                  const int *rS, const int *ps, int W, uint32_t *wd)
+	{
+		int l0, it, lx, ls;
+#define NSW_ROW(R, RC, H1S, H2S, H3S) \
+		l0 = g.first ? NEG : rH[R], it = g.first ? NEG : rI[R], lx = g.first ? (TB ? NEG : INT32_MIN) : rX[R], ls = g.first ? NEG : (TB ? rS[R] : 0); \
+		{ \
+			const int s = ps[RC.nas * W]; \
+			int d_new; \
+			if (TB) { \
+				int f0 = seg_start ? NEG : lx, iseg = seg_start ? NEG : ls, hf; \
+				const int h = cell_trace(par, RC, s, H[H1S], H[H2S], H[H3S], D[H3S], d_new, A, B, Cc, l0, f0, L[H1S], L[H2S], L[H3S], iseg, it, hf, wd[R]); \
+				H[H3S] = h, D[H3S] = d_new, oH[R] = h, oI[R] = it, oX[R] = hf, oS[R] = iseg; \
+			} else { \
+				const int h = cell_score(par, RC, s, H[H1S], H[H2S], H[H3S], D[H3S], d_new, A, B, Cc, l0, L[H1S], L[H2S], L[H3S], it); \
+				H[H3S] = h, D[H3S] = d_new, oH[R] = h, oI[R] = it, oX[R] = imax(lx, (h + bonus) * 4096 + code); \
+			} \
+			if (!g.first) L[H3S] = rH[R]; \
+		}
+		NSW_ROW(0, rc0, 2, 1, 0)
+		NSW_ROW(1, rc1, 0, 2, 1)
+		NSW_ROW(2, rc2, 1, 0, 2)
+#undef NSW_ROW
+	}
+
+	// Steady-state macro-step: EVERY thread of the block has three real rows (the kernel guarantees T is in that range), so
+	// there is nothing to check; dead columns (x >= W8) only hand the row maxima on.  The next records come from a running
+	// pointer without clamping (the record array is padded).
+	template <int PH, class Env>
+	NSW_HD void macro_steady(const Geo3 &g, const Par &par, int T, const int *rH, const int *rI, const int *rX, const int *rS, Env &env, uint32_t *wd)
+	{
+		const int i0 = row_of(g, T, 0);
+		const RowRec rc0 = rec[3 * PH], rc1 = rec[3 * PH + 1], rc2 = rec[3 * PH + 2];
+		env.row_rec3_noclamp(i0 + 6, rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2]);
+		if (g.first) env.prefetch_row(i0 + 72);
+		if (g.live) rows3(g, par, rc0, rc1, rc2, rH, rI, rX, rS, env.profile(0), env.profile_stride(), wd);
+		else if (!TB) oX[0] = rX[0], oX[1] = rX[1], oX[2] = rX[2];
+	}
+	// macro-steps [lo, hi) are steady for a block of Wp columns: every column has three rows inside [3, nl) (lo, hi even)
+	NSW_HD static void steady_range(int nl, int Wp, int &lo, int &hi)
+	{
+		lo = Wp;
+		hi = nl >= 5 ? (nl - 5) / 3 + 1 : 0;
+		if (hi < lo) hi = lo;
+		hi = lo + ((hi - lo) & ~1);
+	}
+
+	// General macro-step (ramp-up, ramp-down, tiny problems).  PH = T mod 2 selects the half of the record buffer.
+	// rH/rI/rX/rS[r]: outputs of thread x-1 for row r.  wd[r] receives the traceback word of row r (TB); returns a bit mask
+	// of the rows that were real rows of this thread.
 	template <int PH, class Env>
 	NSW_HD uint32_t macro(const Geo3 &g, const Par &par, int T, const int *rH, const int *rI, const int *rX, const int *rS, Env &env, uint32_t *wd)
 	{
 		const int i0 = row_of(g, T, 0);
 		const RowRec rc0 = rec[3 * PH], rc1 = rec[3 * PH + 1], rc2 = rec[3 * PH + 2];
 		env.row_rec3(i0 + 6, rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2]);
-		if (g.first) env.prefetch_row(i0 + 72);
 		uint32_t done = 0;
-		if (g.live && i0 > 2 && i0 + 2 < g.nl) {
-			const int *ps = env.profile(0);
-			const int W = env.profile_stride();
-			int l0, it, lx, ls;
-#define NSW_ROW(R, RC, H1S, H2S, H3S) \
-			l0 = g.first ? NEG : rH[R], it = g.first ? NEG : rI[R], lx = g.first ? (TB ? NEG : INT32_MIN) : rX[R], ls = g.first ? NEG : (TB ? rS[R] : 0); \
-			{ \
-				const int s = ps[RC.nas * W]; \
-				int d_new; \
-				if (TB) { \
-					int f0 = seg_start ? NEG : lx, iseg = seg_start ? NEG : ls, hf; \
-					const int h = cell_trace(par, RC, s, H[H1S], H[H2S], H[H3S], D[H3S], d_new, A, B, Cc, l0, f0, L[H1S], L[H2S], L[H3S], iseg, it, hf, wd[R]); \
-					H[H3S] = h, D[H3S] = d_new, oH[R] = h, oI[R] = it, oX[R] = hf, oS[R] = iseg; \
-				} else { \
-					const int h = cell_score(par, RC, s, H[H1S], H[H2S], H[H3S], D[H3S], d_new, A, B, Cc, l0, L[H1S], L[H2S], L[H3S], it); \
-					H[H3S] = h, D[H3S] = d_new, oH[R] = h, oI[R] = it, oX[R] = imax(lx, (h + bonus) * 4096 + code); \
-				} \
-				if (!g.first) L[H3S] = rH[R]; \
-			}
-			NSW_ROW(0, rc0, 2, 1, 0)
-			NSW_ROW(1, rc1, 0, 2, 1)
-			NSW_ROW(2, rc2, 1, 0, 2)
-#undef NSW_ROW
-			if (TB && end_col && i0 + 2 == g.nl - 1) score = H[2];
-			return 7u;
-		}
 #pragma unroll
 		for (int r = 0; r < 3; ++r) {
 			const int h3 = r, h2 = (r + 1) % 3, h1 = (r + 2) % 3;

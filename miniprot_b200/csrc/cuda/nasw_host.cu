@@ -75,7 +75,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		j.pad_ = v3 ? 32 * nw : 0;
 		const int Wp = v3 ? 32 * nw : 32 * j.C, W8 = (j.al + 7) / 8 * 8, n_pass = v3 ? 1 : (W8 + Wp - 1) / Wp;
 		const int T = v3 ? (j.nl > 2 ? 3 * ((j.nl - 2 + 2) / 3 + Wp + 2) : 0) : (j.nl > 2 ? j.nl - 2 + 32 + 6 : 0); // rows of the wavefront-major traceback buffer
-		j.rw_off = rw_tot, rw_tot += (j.nl + 1 + 3 + 3) / 4 * 4; // + 3 padding rows read (never used) by the 3-row fetch
+		j.rw_off = rw_tot, rw_tot += (j.nl + 1 + 8 + 3) / 4 * 4; // + 8 padding rows read (never used) by the look-ahead 3-row fetch
 		j.tb_off = j.cig_off = 0, j.cig_cap = 0, j.carry_off = 0;
 		(void)0;
 		if (is_tb) {
@@ -188,7 +188,7 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_
 			const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
 			const bool v3 = use_v3(j.al, j.nl);
 			const int C = pick_C(j.al), Wp = v3 ? 32 * v3_warps(j.al) : 32 * C, W8 = (j.al + 7) / 8 * 8, n_pass = v3 ? 1 : (W8 + Wp - 1) / Wp;
-			const size_t tbb = is_tb ? (size_t)n_pass * (size_t)(j.nl + 3 * Wp + 64) * Wp * 2 : 0, rwb = (size_t)(j.nl + 8) * 32;
+			const size_t tbb = is_tb ? (size_t)n_pass * (size_t)(j.nl + 3 * Wp + 64) * Wp * 2 : 0, rwb = (size_t)(j.nl + 12) * 32;
 			if (hi > lo && (tb_bytes + tbb > kTbBudget || rw_bytes + rwb > kRwBudget)) break;
 			tb_bytes += tbb, rw_bytes += rwb, ++hi;
 		}

@@ -23,6 +23,7 @@ struct EmuEnv {
 	int *cy;
 	RowRec row_rec(int i) const { i = i < 0 ? 0 : (i > nl ? nl : i); return rec[i]; }
 	void prefetch_row(int) const {}
+	void row_rec3_noclamp(int i, RowRec &r0, RowRec &r1, RowRec &r2) const { r0 = rec[i], r1 = rec[i + 1], r2 = rec[i + 2]; }
 	void row_rec3(int i, RowRec &r0, RowRec &r1, RowRec &r2) const { i = i < 0 ? 0 : (i > nl ? nl : i); r0 = rec[i], r1 = rec[i + 1], r2 = rec[i + 2]; }
 	int profile_stride() const { return Wp; }
 	const int *profile(int nas) const { return prof + nas * Wp; }
@@ -184,13 +185,20 @@ void run_v3(const Problem &P, int *score, int *nt_len, int *aa_len, std::vector<
 		trk[x].init();
 	}
 	std::vector<int> sH((size_t)Wp * 3), sI((size_t)Wp * 3), sX((size_t)Wp * 3), sS((size_t)Wp * 3);
+	int t_lo, t_hi;
+	Lane3<TB>::steady_range(P.nl, Wp, t_lo, t_hi);
 	for (int T = 0; T < n_macro + (n_macro & 1); ++T) {
+		const bool steady = T >= t_lo && T < t_hi; // the kernel's middle loop
 		for (int x = 0; x < Wp; ++x)
 			for (int r = 0; r < 3; ++r) sH[x * 3 + r] = L[x].oH[r], sI[x * 3 + r] = L[x].oI[r], sX[x * 3 + r] = L[x].oX[r], sS[x * 3 + r] = L[x].oS[r];
 		for (int x = 0; x < Wp; ++x) {
 			const int s = x ? x - 1 : 0; // what __shfl_up_sync(..., 1) / the shared-memory slot delivers
 			uint32_t wd[3], done;
-			if (T & 1) done = L[x].template macro<1>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd);
+			if (steady) {
+				if (T & 1) L[x].template macro_steady<1>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd);
+				else L[x].template macro_steady<0>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd);
+				done = TB ? (g[x].live ? 7u : 0u) : 7u;
+			} else if (T & 1) done = L[x].template macro<1>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd);
 			else done = L[x].template macro<0>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd);
 			for (int r = 0; r < 3; ++r) {
 				if (!(done >> r & 1)) continue;
@@ -253,7 +261,7 @@ extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *
 		r = r < 0 ? 0 : (r > nl ? nl : r);
 		w[(size_t)x] = left ? prep_row_left(c, nl, r, sp, codon, aa20['X']) : prep_row_forward(c, nl, r, sp, codon, aa20['X']);
 	}
-	P.rec.resize((size_t)nl + 4); // three padding rows after row nl, like the device buffer
+	P.rec.resize((size_t)nl + 9); // eight padding rows after row nl, like the device buffer
 	for (int r = 0; r <= nl; ++r) P.rec[(size_t)r] = make_row_rec(P.par, w[(size_t)r], w[(size_t)r + 1], w[(size_t)r + 2], w[(size_t)r + 3]);
 	P.aas.resize((size_t)al);
 	for (int j = 0; j < al; ++j) P.aas[(size_t)j] = aa20[(uint8_t)as[left ? al - 1 - j : j]];
