@@ -414,44 +414,51 @@ struct Lane3 {
 	}
 
 	// Three real rows of a live column, straight-line (no per-row validity checks): the body of every steady-state step.
-	NSW_HD void rows3(const Geo3 &g, const Par &par, const RowRec &rc0, const RowRec &rc1, const RowRec &rc2, const int *rH, const int *rI, const int *rX,
+	// pH[r] / rH[r]: H of the column to the left for row r of the previous / of this macro-step (the first column gets NEG).
+	NSW_HD void rows3(const Par &par, const RowRec &rc0, const RowRec &rc1, const RowRec &rc2, const int *pH, const int *rH, const int *rI, const int *rX,
 	                  const int *rS, const int *ps, int W, uint32_t *wd)
 	{
-		int l0, it, lx, ls;
-#define NSW_ROW(R, RC, H1S, H2S, H3S) \
-		l0 = g.first ? NEG : rH[R], it = g.first ? NEG : rI[R], lx = g.first ? (TB ? NEG : INT32_MIN) : rX[R], ls = g.first ? NEG : (TB ? rS[R] : 0); \
+#define NSW_ROW(R, RC, H1S, H2S, H3S, L1, L2, L3) \
 		{ \
 			const int s = ps[RC.nas * W]; \
-			int d_new; \
+			int d_new, it = rI[R]; \
 			if (TB) { \
-				int f0 = seg_start ? NEG : lx, iseg = seg_start ? NEG : ls, hf; \
-				const int h = cell_trace(par, RC, s, H[H1S], H[H2S], H[H3S], D[H3S], d_new, A, B, Cc, l0, f0, L[H1S], L[H2S], L[H3S], iseg, it, hf, wd[R]); \
+				int f0 = seg_start ? NEG : rX[R], iseg = seg_start ? NEG : rS[R], hf; \
+				const int h = cell_trace(par, RC, s, H[H1S], H[H2S], H[H3S], D[H3S], d_new, A, B, Cc, rH[R], f0, L1, L2, L3, iseg, it, hf, wd[R]); \
 				H[H3S] = h, D[H3S] = d_new, oH[R] = h, oI[R] = it, oX[R] = hf, oS[R] = iseg; \
 			} else { \
-				const int h = cell_score(par, RC, s, H[H1S], H[H2S], H[H3S], D[H3S], d_new, A, B, Cc, l0, L[H1S], L[H2S], L[H3S], it); \
-				H[H3S] = h, D[H3S] = d_new, oH[R] = h, oI[R] = it, oX[R] = imax(lx, (h + bonus) * 4096 + code); \
+				const int h = cell_score(par, RC, s, H[H1S], H[H2S], H[H3S], D[H3S], d_new, A, B, Cc, rH[R], L1, L2, L3, it); \
+				H[H3S] = h, D[H3S] = d_new, oH[R] = h, oI[R] = it, oX[R] = imax(rX[R], (h + bonus) * 4096 + code); \
 			} \
-			if (!g.first) L[H3S] = rH[R]; \
 		}
-		NSW_ROW(0, rc0, 2, 1, 0)
-		NSW_ROW(1, rc1, 0, 2, 1)
-		NSW_ROW(2, rc2, 1, 0, 2)
+		NSW_ROW(0, rc0, 2, 1, 0, pH[2], pH[1], pH[0])
+		NSW_ROW(1, rc1, 0, 2, 1, rH[0], pH[2], pH[1])
+		NSW_ROW(2, rc2, 1, 0, 2, rH[1], rH[0], pH[2])
 #undef NSW_ROW
 	}
 
 	// Steady-state macro-step: EVERY thread of the block has three real rows (the kernel guarantees T is in that range), so
-	// there is nothing to check; dead columns (x >= W8) only hand the row maxima on.  The next records come from a running
-	// pointer without clamping (the record array is padded).
+	// there is nothing to check; dead columns (x >= W8) only hand the row maxima on.  The caller keeps the left column's H of
+	// the previous step (pH) and of this one (rH) in two alternating buffers, which replaces L[]; the records of step T+2 are
+	// fetched through the environment's running cursor AFTER the rows that used the old ones (no register copies).
 	template <int PH, class Env>
-	NSW_HD void macro_steady(const Geo3 &g, const Par &par, int T, const int *rH, const int *rI, const int *rX, const int *rS, Env &env, uint32_t *wd)
+	NSW_HD void macro_steady(const Geo3 &g, const Par &par, const int *pH, const int *rH, const int *rI, const int *rX, const int *rS, Env &env, uint32_t *wd)
 	{
-		const int i0 = row_of(g, T, 0);
-		const RowRec rc0 = rec[3 * PH], rc1 = rec[3 * PH + 1], rc2 = rec[3 * PH + 2];
-		env.row_rec3_noclamp(i0 + 6, rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2]);
-		if (g.first) env.prefetch_row(i0 + 72);
-		if (g.live) rows3(g, par, rc0, rc1, rc2, rH, rI, rX, rS, env.profile(0), env.profile_stride(), wd);
-		else if (!TB) oX[0] = rX[0], oX[1] = rX[1], oX[2] = rX[2];
+		if (g.live) {
+			rows3(par, rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2], pH, rH, rI, rX, rS, env.profile(0), env.profile_stride(), wd);
+			env.next3(rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2]);
+			if (g.first) env.prefetch_ahead();
+		} else if (!TB) oX[0] = rX[0], oX[1] = rX[1], oX[2] = rX[2];
 	}
+	// entering the steady range at macro-step T: hand L[] over as the first "previous" buffer and point the record cursor
+	// at the rows step T will fetch
+	template <class Env>
+	NSW_HD void steady_enter(const Geo3 &g, int T, int *pH, Env &env) const
+	{
+		pH[0] = L[0], pH[1] = L[1], pH[2] = L[2];
+		env.seek(row_of(g, T, 0) + 6);
+	}
+	NSW_HD void steady_leave(const int *pH) { L[0] = pH[0], L[1] = pH[1], L[2] = pH[2]; }
 	// macro-steps [lo, hi) are steady for a block of Wp columns: every column has three rows inside [3, nl) (lo, hi even)
 	NSW_HD static void steady_range(int nl, int Wp, int &lo, int &hi)
 	{

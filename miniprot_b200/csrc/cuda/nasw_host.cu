@@ -152,11 +152,20 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	if (cig_tot) MPB_CUDA_OK(cudaMemcpyAsync(ctx->h_cigar.p, ctx->b_cigar.p, sizeof(uint32_t) * (size_t)cig_tot, cudaMemcpyDeviceToHost, st));
 	MPB_CUDA_OK(cudaStreamSynchronize(st));
 	MPB_CUDA_OK(cudaGetLastError());
+	static const bool trace = getenv("MPB_TRACE") != 0; // per-class durations of every wave on stderr (diagnostics only)
 	for (int sid = 0; sid < mpb_ctx_s::N_SIDE; ++sid)
 		if (used[sid]) { // sum of the classes' own durations (they overlap in time; the wave's wall time is what the step pays)
 			float ms = 0;
 			cudaEventElapsedTime(&ms, ctx->ev_k0[sid], ctx->ev_k1[sid]);
 			(is_ext_sid[sid] ? ctx->stats.ms_dp_ext : ctx->stats.ms_dp_tb) += ms;
+			if (trace) {
+				const int b = sid / 9, c = sid % 9;
+				const DpDev &j0 = jobs[lo + flat[first[b][c]]];
+				int64_t cells = 0;
+				for (size_t k = 0; k < count[b][c]; ++k) cells += (int64_t)jobs[lo + flat[first[b][c] + k]].nl * jobs[lo + flat[first[b][c] + k]].al;
+				fprintf(stderr, "[mpb-trace] nasw %s class %d: %zu jobs, longest nl=%d al=%d, %.1f Mcell, %.2f ms\n", b ? "tb " : "ext", c, count[b][c],
+				        j0.nl, j0.al, cells * 1e-6, ms);
+			}
 		}
 	ctx->stats.d2h_bytes += sizeof(int4) * n + sizeof(uint32_t) * (size_t)cig_tot;
 	const int4 *ho = ctx->h_out.as<int4>();

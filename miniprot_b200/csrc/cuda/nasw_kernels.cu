@@ -110,9 +110,16 @@ struct DevEnv {
 		r1.cA = a1.x, r1.cB = a1.y, r1.cC = a1.z, r1.gei = a1.w, r1.aA = b1.x, r1.aB = b1.y, r1.aC = b1.z, r1.nas = b1.w;
 		r2.cA = a2.x, r2.cB = a2.y, r2.cC = a2.z, r2.gei = a2.w, r2.aA = b2.x, r2.aB = b2.y, r2.aC = b2.z, r2.nas = b2.w;
 	}
-	__device__ __forceinline__ void row_rec3_noclamp(int i, RowRec &r0, RowRec &r1, RowRec &r2) const
+	const int4 *cur;     // steady-state cursor: the next three records to fetch
+	__device__ __forceinline__ void seek(int i) { cur = rec + 2 * i; }
+	__device__ __forceinline__ void prefetch_ahead() const // 66 rows past the cursor (the first column runs ahead of everyone)
 	{
-		const int4 *q = rec + 2 * i;
+		if (cur + 2 * 66 <= rec + 2 * nl) asm volatile("prefetch.global.L1 [%0];" :: "l"(cur + 2 * 66));
+	}
+	__device__ __forceinline__ void next3(RowRec &r0, RowRec &r1, RowRec &r2)
+	{
+		const int4 *q = cur;
+		cur += 6;
 		const int4 a0 = __ldg(q), b0 = __ldg(q + 1), a1 = __ldg(q + 2), b1 = __ldg(q + 3), a2 = __ldg(q + 4), b2 = __ldg(q + 5);
 		r0.cA = a0.x, r0.cB = a0.y, r0.cC = a0.z, r0.gei = a0.w, r0.aA = b0.x, r0.aB = b0.y, r0.aC = b0.z, r0.nas = b0.w;
 		r1.cA = a1.x, r1.cB = a1.y, r1.cC = a1.z, r1.gei = a1.w, r1.aA = b1.x, r1.aB = b1.y, r1.aC = b1.z, r1.nas = b1.w;
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 {
 	extern __shared__ int smem[];
 	constexpr int Wp = 32 * NW, NX = TB ? 12 : 9;
-	__shared__ int xchg[2][NW][12];
+	__shared__ int xchg[2][NW + 1][12]; // [parity][warp + 1]: last column of each warp; slot 0 = the constant boundary left of column 0
 	__shared__ int stop_flag[2]; // written by the last column during macro-step Tm into slot Tm & 1, read by everyone after that step's barrier
 	if ((int)blockIdx.x >= n_jobs) return;
 	const int jid = order[blockIdx.x];
@@ -278,6 +285,7 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 		for (int a = 0; a < 22; ++a) smem[a * Wp + x] = rcode >= 0 ? cst.mat[a * 22 + rcode] : NEG;
 	}
 	if (x == 0) stop_flag[0] = stop_flag[1] = 0;
+	if (x < 24) xchg[x / 12][0][x % 12] = (!TB && x % 12 >= 6 && x % 12 < 9) ? INT32_MIN : NEG;
 	__syncthreads();
 	DevEnv env;
 	env.rec = rec + job.rw_off * 2, env.nl = g.nl, env.prof = smem + x, env.Wp = Wp, env.cy = 0;
@@ -287,27 +295,29 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 	trk.init();
 	const int n_macro = g.nl > 2 ? (g.nl - 2 + 2) / 3 + Wp : 0; // rows 2..nl-1 in triples, plus the skew of the last column
 	uint16_t *tbp = TB ? tb + job.tb_off + x : 0;
-#define NSW_V3_RECV(PH) \
-		int rH[3], rI[3], rX[3], rS[3]; \
+	// (T is even at every loop head, so the parity of macro-step T + PH is PH: all exchange slots are static)
+#define NSW_V3_RECV(PH, RH) \
+		int rI[3], rX[3], rS[3]; \
 		_Pragma("unroll") for (int r = 0; r < 3; ++r) { \
-			rH[r] = __shfl_up_sync(0xffffffffu, L.oH[r], 1), rI[r] = __shfl_up_sync(0xffffffffu, L.oI[r], 1), rX[r] = __shfl_up_sync(0xffffffffu, L.oX[r], 1); \
+			RH[r] = __shfl_up_sync(0xffffffffu, L.oH[r], 1), rI[r] = __shfl_up_sync(0xffffffffu, L.oI[r], 1), rX[r] = __shfl_up_sync(0xffffffffu, L.oX[r], 1); \
 			rS[r] = TB ? __shfl_up_sync(0xffffffffu, L.oS[r], 1) : 0; \
 		} \
-		if (NW > 1 && lane == 0 && warp > 0) { /* the column to my left lives in the previous warp */ \
-			const int *b = xchg[(T + PH + 1) & 1][warp - 1]; \
-			_Pragma("unroll") for (int r = 0; r < 3; ++r) { rH[r] = b[r], rI[r] = b[3 + r], rX[r] = b[6 + r]; if (TB) rS[r] = b[9 + r]; } \
+		if (lane == 0) { /* the column to my left lives in the previous warp; slot 0 holds the constant left boundary */ \
+			const int *b = xchg[PH ^ 1][warp]; \
+			_Pragma("unroll") for (int r = 0; r < 3; ++r) { RH[r] = b[r], rI[r] = b[3 + r], rX[r] = b[6 + r]; if (TB) rS[r] = b[9 + r]; } \
 		}
 #define NSW_V3_SEND(PH) \
 		if (NW > 1) { \
 			if (lane == 31 && warp < NW - 1) { \
-				int *b = xchg[(T + PH) & 1][warp]; \
+				int *b = xchg[PH][warp + 1]; \
 				_Pragma("unroll") for (int r = 0; r < 3; ++r) { b[r] = L.oH[r], b[3 + r] = L.oI[r], b[6 + r] = L.oX[r]; if (TB) b[9 + r] = L.oS[r]; } \
 			} \
-			if (!TB && x == Wp - 1) stop_flag[(T + PH) & 1] = trk.stopped ? 1 : 0; \
+			if (!TB && x == Wp - 1) stop_flag[PH] = trk.stopped ? 1 : 0; \
 			__syncthreads(); \
 		}
 #define NSW_V3_MACRO(PH) { /* general step: ramp-up, ramp-down */ \
-		NSW_V3_RECV(PH) \
+		int rH[3]; \
+		NSW_V3_RECV(PH, rH) \
 		uint32_t wd[3]; \
 		const uint32_t done = L.template macro<PH>(g, par, T + PH, rH, rI, rX, rS, env, wd); \
 		if (TB) { _Pragma("unroll") for (int r = 0; r < 3; ++r) if (done >> r & 1) tbp[(int64_t)(3 * (T + PH) + r) * Wp] = (uint16_t)wd[r]; } \
@@ -315,33 +325,38 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 			_Pragma("unroll") for (int r = 0; r < 3; ++r) if (done >> r & 1) trk.row(Lane3<TB>::row_of(g, T + PH, r), L.oX[r], g.al * 3, cst.pen, cst.xdrop); } \
 		NSW_V3_SEND(PH) }
 #define NSW_V3_STEADY(PH) { /* every column has three real rows: nothing to check */ \
-		NSW_V3_RECV(PH) \
+		NSW_V3_RECV(PH, hb[PH]) \
 		uint32_t wd[3]; \
-		L.template macro_steady<PH>(g, par, T + PH, rH, rI, rX, rS, env, wd); \
-		if (TB) { if (g.live) { _Pragma("unroll") for (int r = 0; r < 3; ++r) tbp[(int64_t)(3 * (T + PH) + r) * Wp] = (uint16_t)wd[r]; } } \
+		L.template macro_steady<PH>(g, par, hb[PH ^ 1], hb[PH], rI, rX, rS, env, wd); \
+		if (TB) { if (g.live) { _Pragma("unroll") for (int r = 0; r < 3; ++r) tbs[r * Wp] = (uint16_t)wd[r]; } tbs += 3 * Wp; } \
 		else if (x == Wp - 1) { _Pragma("unroll") for (int r = 0; r < 3; ++r) trk.row(Lane3<TB>::row_of(g, T + PH, r), L.oX[r], g.al * 3, cst.pen, cst.xdrop); } \
 		NSW_V3_SEND(PH) }
 #define NSW_V3_CHECK_STOP \
 		if (!TB) { /* x-drop: the last column's tracker decides; rows after the break row are never looked at */ \
-			if (NW > 1) { if (stop_flag[(T + 1) & 1]) break; } \
+			if (NW > 1) { if (stop_flag[1]) break; } \
 			else if (__shfl_sync(0xffffffffu, (int)trk.stopped, 31)) break; \
 		}
 	int t_lo, t_hi;
 	Lane3<TB>::steady_range(g.nl, Wp, t_lo, t_hi);
-	bool stopped = false;
 	int T = 0;
 	for (; T < t_lo && T < n_macro; T += 2) { NSW_V3_MACRO(0) NSW_V3_MACRO(1) NSW_V3_CHECK_STOP }
 	if (T >= t_lo) {
+		int hb[2][3]; // H of the column to the left: this macro-step's and the previous one's, alternating
+		L.steady_enter(g, T, hb[1], env);
+		uint16_t *tbs = TB ? tbp + (int64_t)3 * T * Wp : 0;
+		(void)tbs;
 		for (; T < t_hi; T += 2) { NSW_V3_STEADY(0) NSW_V3_STEADY(1) NSW_V3_CHECK_STOP }
-		stopped = T < t_hi; // left the steady loop through the x-drop break
-		if (!stopped) for (; T < n_macro; T += 2) { NSW_V3_MACRO(0) NSW_V3_MACRO(1) NSW_V3_CHECK_STOP }
+		if (T >= t_hi) { // not left through the x-drop break
+			L.steady_leave(hb[1]);
+			for (; T < n_macro; T += 2) { NSW_V3_MACRO(0) NSW_V3_MACRO(1) NSW_V3_CHECK_STOP }
+		}
 	}
 #undef NSW_V3_RECV
 #undef NSW_V3_SEND
 #undef NSW_V3_STEADY
 #undef NSW_V3_CHECK_STOP
 #undef NSW_V3_MACRO
-	(void)NX; (void)stopped;
+	(void)NX;
 	if (TB) {
 		// the thread that owns column al-1 holds H(nl-1, al-1)
 		if (x == (job.al > 0 ? job.al - 1 : 0)) out[jid] = make_int4(L.score, g.nl, g.al, 0);

@@ -23,7 +23,10 @@ struct EmuEnv {
 	int *cy;
 	RowRec row_rec(int i) const { i = i < 0 ? 0 : (i > nl ? nl : i); return rec[i]; }
 	void prefetch_row(int) const {}
-	void row_rec3_noclamp(int i, RowRec &r0, RowRec &r1, RowRec &r2) const { r0 = rec[i], r1 = rec[i + 1], r2 = rec[i + 2]; }
+	int cur;
+	void seek(int i) { cur = i; }
+	void prefetch_ahead() const {}
+	void next3(RowRec &r0, RowRec &r1, RowRec &r2) { r0 = rec[cur], r1 = rec[cur + 1], r2 = rec[cur + 2], cur += 3; }
 	void row_rec3(int i, RowRec &r0, RowRec &r1, RowRec &r2) const { i = i < 0 ? 0 : (i > nl ? nl : i); r0 = rec[i], r1 = rec[i + 1], r2 = rec[i + 2]; }
 	int profile_stride() const { return Wp; }
 	const int *profile(int nas) const { return prof + nas * Wp; }
@@ -195,8 +198,18 @@ void run_v3(const Problem &P, int *score, int *nt_len, int *aa_len, std::vector<
 			const int s = x ? x - 1 : 0; // what __shfl_up_sync(..., 1) / the shared-memory slot delivers
 			uint32_t wd[3], done;
 			if (steady) {
-				if (T & 1) L[x].template macro_steady<1>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd);
-				else L[x].template macro_steady<0>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd);
+				// the kernel's alternating buffers: "previous" = what L[] would hold, "this" = the values just received;
+				// the first column receives the constant boundary slot
+				int pH[3], rH[3], rI[3], rX[3], rS[3];
+				if (T == t_lo) L[x].steady_enter(g[x], T, pH, env[x]);
+				else for (int r = 0; r < 3; ++r) pH[r] = L[x].L[r];
+				for (int r = 0; r < 3; ++r) {
+					rH[r] = x ? sH[s * 3 + r] : NEG, rI[r] = x ? sI[s * 3 + r] : NEG, rS[r] = x ? sS[s * 3 + r] : NEG;
+					rX[r] = x ? sX[s * 3 + r] : TB ? NEG : INT32_MIN;
+				}
+				if (T & 1) L[x].template macro_steady<1>(g[x], P.par, pH, rH, rI, rX, rS, env[x], wd);
+				else L[x].template macro_steady<0>(g[x], P.par, pH, rH, rI, rX, rS, env[x], wd);
+				L[x].steady_leave(rH);
 				done = TB ? (g[x].live ? 7u : 0u) : 7u;
 			} else if (T & 1) done = L[x].template macro<1>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd);
 			else done = L[x].template macro<0>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd);
