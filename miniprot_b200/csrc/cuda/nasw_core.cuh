@@ -390,6 +390,12 @@ struct TbLane {
 // ------------------------------------------------------------------------------------------------
 struct Geo3 { int x, nl, al, W8; bool live, first; };
 
+// Row records of a block-wide problem are stored per TRIPLE of rows (triple m = rows 3m+2 .. 3m+4, the unit of a macro-step)
+// and field-major: six arrays of M 16-byte fields (record halves a/b of the three rows).  Column x works on triple T - x at
+// macro-step T, so the 32 lanes of a warp read 32 CONSECUTIVE fields with each load (512 contiguous bytes) instead of 32
+// records 96 bytes apart.  M covers every real row (2 .. nl-1) plus the look-ahead of the pipeline.
+NSW_HD int v3_triples(int nl) { return (nl > 2 ? (nl - 2 + 2) / 3 : 0) + 4; }
+
 template <bool TB>
 struct Lane3 {
 	int H[3], D[3], A, B, Cc, L[3];
@@ -409,8 +415,7 @@ struct Lane3 {
 		if (g.first) L[0] = 0, L[1] = L[2] = -fs; // H(-1,-1), H(0,-1), H(1,-1): seen by row 2 only (nasw-sse.c:253-258)
 		code = g.x < g.al ? 4095 - g.x : 0, bonus = g.x == g.al - 1 ? end_bonus : 0;
 		seg_start = slen > 0 && g.x % slen == 0, end_col = g.x == g.al - 1, score = NEG;
-		const int i0 = row_of(g, 0, 0);
-		for (int k = 0; k < 6; ++k) rec[k] = env.row_rec(i0 + k);
+		env.rec3(-g.x, rec[0], rec[1], rec[2]), env.rec3(1 - g.x, rec[3], rec[4], rec[5]);
 	}
 
 	// Three real rows of a live column, straight-line (no per-row validity checks): the body of every steady-state step.
@@ -438,17 +443,18 @@ struct Lane3 {
 	}
 
 	// Steady-state macro-step: EVERY thread of the block has three real rows (the kernel guarantees T is in that range), so
-	// there is nothing to check; dead columns (x >= W8) only hand the row maxima on.  The caller keeps the left column's H of
+	// there is nothing to check.  The caller keeps the left column's H of
 	// the previous step (pH) and of this one (rH) in two alternating buffers, which replaces L[]; the records of step T+2 are
 	// fetched through the environment's running cursor AFTER the rows that used the old ones (no register copies).
 	template <int PH, class Env>
 	NSW_HD void macro_steady(const Geo3 &g, const Par &par, const int *pH, const int *rH, const int *rI, const int *rX, const int *rS, Env &env, uint32_t *wd)
 	{
-		if (g.live) {
-			rows3(par, rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2], pH, rH, rI, rX, rS, env.profile(0), env.profile_stride(), wd);
-			env.next3(rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2]);
-			if (g.first) env.prefetch_ahead();
-		} else if (!TB) oX[0] = rX[0], oX[1] = rX[1], oX[2] = rX[2];
+		// dead columns (x >= W8) run the same arithmetic on their all-NEG profile columns -- nothing to their right is real, so
+		// whatever they produce is never used -- and only hand the row maxima on: no divergent branch inside the warp
+		rows3(par, rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2], pH, rH, rI, rX, rS, env.profile(0), env.profile_stride(), wd);
+		env.next3(rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2]);
+		if (g.x < 6) env.prefetch_ahead(g.x);
+		if (!TB && !g.live) oX[0] = rX[0], oX[1] = rX[1], oX[2] = rX[2];
 	}
 	// entering the steady range at macro-step T: hand L[] over as the first "previous" buffer and point the record cursor
 	// at the rows step T will fetch
@@ -456,7 +462,7 @@ struct Lane3 {
 	NSW_HD void steady_enter(const Geo3 &g, int T, int *pH, Env &env) const
 	{
 		pH[0] = L[0], pH[1] = L[1], pH[2] = L[2];
-		env.seek(row_of(g, T, 0) + 6);
+		env.seek3(T - g.x + 2);
 	}
 	NSW_HD void steady_leave(const int *pH) { L[0] = pH[0], L[1] = pH[1], L[2] = pH[2]; }
 	// macro-steps [lo, hi) are steady for a block of Wp columns: every column has three rows inside [3, nl) (lo, hi even)
@@ -476,7 +482,7 @@ struct Lane3 {
 	{
 		const int i0 = row_of(g, T, 0);
 		const RowRec rc0 = rec[3 * PH], rc1 = rec[3 * PH + 1], rc2 = rec[3 * PH + 2];
-		env.row_rec3(i0 + 6, rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2]);
+		env.rec3(T - g.x + 2, rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2]);
 		uint32_t done = 0;
 #pragma unroll
 		for (int r = 0; r < 3; ++r) {

@@ -75,7 +75,9 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		j.pad_ = v3 ? 32 * nw : 0;
 		const int Wp = v3 ? 32 * nw : 32 * j.C, W8 = (j.al + 7) / 8 * 8, n_pass = v3 ? 1 : (W8 + Wp - 1) / Wp;
 		const int T = v3 ? (j.nl > 2 ? 3 * ((j.nl - 2 + 2) / 3 + Wp + 2) : 0) : (j.nl > 2 ? j.nl - 2 + 32 + 6 : 0); // rows of the wavefront-major traceback buffer
-		j.rw_off = rw_tot, rw_tot += (j.nl + 1 + 8 + 3) / 4 * 4; // + 8 padding rows read (never used) by the look-ahead 3-row fetch
+		// row records: 32 B per row; block-wide problems store them per triple of rows, field-major (nasw_core.cuh v3_triples)
+		const int rec_rows = v3 ? 2 + 3 * nsw::v3_triples(j.nl) : j.nl + 1;
+		j.rw_off = rw_tot, rw_tot += (rec_rows + 3) / 4 * 4;
 		j.tb_off = j.cig_off = 0, j.cig_cap = 0, j.carry_off = 0;
 		(void)0;
 		if (is_tb) {
@@ -84,7 +86,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 			j.cig_off = cig_tot, cig_tot += j.cig_cap;
 		}
 		if (n_pass > 1) j.carry_off = carry_tot, carry_tot += ((int64_t)j.nl + 1) * 4;
-		for (int r = 0; r <= j.nl; r += PREP_ROWS) chunks.push_back(PrepChunk{ k, r, std::min(PREP_ROWS, j.nl + 1 - r), 0 });
+		for (int r = 0; r < rec_rows; r += PREP_ROWS) chunks.push_back(PrepChunk{ k, r, std::min(PREP_ROWS, rec_rows - r), 0 });
 		order[is_tb][v3 ? (nw == 1 ? 0 : nw == 2 ? 1 : nw == 4 ? 2 : 3) : n_pass > 1 ? 8 : j.C == 1 ? 4 : j.C == 2 ? 5 : j.C == 4 ? 6 : 7].push_back(k);
 		(is_tb ? ctx->stats.dp_cells_tb : ctx->stats.dp_cells_ext) += (int64_t)j.nl * j.al;
 		(is_tb ? ctx->stats.n_dp_tb : ctx->stats.n_dp_ext) += 1;
@@ -118,55 +120,60 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	ctx->stats.kernel_launches += 1;
 	static const int Cs[9] = { 1, 2, 4, 8, 1, 2, 4, 8, 16 }; // warps per problem (classes 0..3) or columns per lane (4..8)
 	// fork: every (kind, size class) runs on its own stream -- each is bounded by its longest problem
-	MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
-	bool used[mpb_ctx_s::N_SIDE] = { false }, is_ext_sid[mpb_ctx_s::N_SIDE] = { false };
+	struct Group { int sid, b, c; size_t first, count; };
+	std::vector<Group> groups;
 	for (int b = 0; b < 2; ++b)
 		for (int c = 8; c >= 0; --c) {
-			if (!count[b][c]) continue;
-			const int sid = b * 9 + c;
-			cudaStream_t ss = ctx->side[sid];
-			used[sid] = true, is_ext_sid[sid] = b == 0;
-			MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
-			MPB_CUDA_OK(cudaEventRecord(ctx->ev_k0[sid], ss));
-			if (c < 4) {
-				nasw_launch_v3(ss, Cs[c], b == 1, dj, dord + first[b][c], (int)count[b][c], ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>());
-				ctx->stats.kernel_launches += 1;
-				if (b == 1) {
-					nasw_launch_bt(ss, dj, dord + first[1][c], (int)count[1][c], ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
-					ctx->stats.kernel_launches += 1;
-				}
-			} else if (b == 0) {
-				nasw_launch_ext(ss, Cs[c], dj, dord + first[0][c], (int)count[0][c], ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>());
-				ctx->stats.kernel_launches += 1;
-			} else {
-				nasw_launch_tb(ss, Cs[c], dj, dord + first[1][c], (int)count[1][c], ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>(),
-				               ctx->b_tb.as<uint16_t>());
-				nasw_launch_bt(ss, dj, dord + first[1][c], (int)count[1][c], ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
-				ctx->stats.kernel_launches += 2;
-			}
-			MPB_CUDA_OK(cudaEventRecord(ctx->ev_k1[sid], ss));
-			MPB_CUDA_OK(cudaEventRecord(ctx->ev_join[sid], ss));
-			MPB_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_join[sid], 0));
+			if (count[b][c]) groups.push_back(Group{ b * 9 + c, b, c, first[b][c], count[b][c] });
 		}
+	MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
+	for (const Group &g : groups) {
+		cudaStream_t ss = ctx->side[g.sid];
+		const int b = g.b, c = g.c, cnt = (int)g.count;
+		const int *ord = dord + g.first;
+		MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
+		MPB_CUDA_OK(cudaEventRecord(ctx->ev_k0[g.sid], ss));
+		if (c < 4) {
+			nasw_launch_v3(ss, Cs[c], b == 1, dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>());
+			ctx->stats.kernel_launches += 1;
+			if (b == 1) {
+				nasw_launch_bt(ss, dj, ord, cnt, ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
+				ctx->stats.kernel_launches += 1;
+			}
+		} else if (b == 0) {
+			nasw_launch_ext(ss, Cs[c], dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>());
+			ctx->stats.kernel_launches += 1;
+		} else {
+			nasw_launch_tb(ss, Cs[c], dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>(), ctx->b_tb.as<uint16_t>());
+			nasw_launch_bt(ss, dj, ord, cnt, ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
+			ctx->stats.kernel_launches += 2;
+		}
+		MPB_CUDA_OK(cudaEventRecord(ctx->ev_k1[g.sid], ss));
+		MPB_CUDA_OK(cudaEventRecord(ctx->ev_join[g.sid], ss));
+		MPB_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_join[g.sid], 0));
+	}
 	MPB_CUDA_OK(cudaMemcpyAsync(ctx->h_out.p, ctx->b_out.p, sizeof(int4) * n, cudaMemcpyDeviceToHost, st));
 	if (cig_tot) MPB_CUDA_OK(cudaMemcpyAsync(ctx->h_cigar.p, ctx->b_cigar.p, sizeof(uint32_t) * (size_t)cig_tot, cudaMemcpyDeviceToHost, st));
 	MPB_CUDA_OK(cudaStreamSynchronize(st));
 	MPB_CUDA_OK(cudaGetLastError());
 	static const bool trace = getenv("MPB_TRACE") != 0; // per-class durations of every wave on stderr (diagnostics only)
-	for (int sid = 0; sid < mpb_ctx_s::N_SIDE; ++sid)
-		if (used[sid]) { // sum of the classes' own durations (they overlap in time; the wave's wall time is what the step pays)
-			float ms = 0;
-			cudaEventElapsedTime(&ms, ctx->ev_k0[sid], ctx->ev_k1[sid]);
-			(is_ext_sid[sid] ? ctx->stats.ms_dp_ext : ctx->stats.ms_dp_tb) += ms;
-			if (trace) {
-				const int b = sid / 9, c = sid % 9;
-				const DpDev &j0 = jobs[lo + flat[first[b][c]]];
-				int64_t cells = 0;
-				for (size_t k = 0; k < count[b][c]; ++k) cells += (int64_t)jobs[lo + flat[first[b][c] + k]].nl * jobs[lo + flat[first[b][c] + k]].al;
-				fprintf(stderr, "[mpb-trace] nasw %s class %d: %zu jobs, longest nl=%d al=%d, %.1f Mcell, %.2f ms\n", b ? "tb " : "ext", c, count[b][c],
-				        j0.nl, j0.al, cells * 1e-6, ms);
+	for (const Group &g : groups) { // sum of the classes' own durations (they overlap in time; the wave's wall time is what the step pays)
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ctx->ev_k0[g.sid], ctx->ev_k1[g.sid]);
+		(g.b == 0 ? ctx->stats.ms_dp_ext : ctx->stats.ms_dp_tb) += ms;
+		if (trace) {
+			int hist[5] = { 0 };
+			double hc[5] = { 0 }, cells = 0;
+			for (size_t k = 0; k < g.count; ++k) {
+				const DpDev &jj = jobs[lo + flat[g.first + k]];
+				const int q = jj.nl >= 65536 ? 0 : jj.nl >= 32768 ? 1 : jj.nl >= 16384 ? 2 : jj.nl >= 8192 ? 3 : 4;
+				++hist[q], hc[q] += (double)jj.nl * jj.al * 1e-6, cells += (double)jj.nl * jj.al * 1e-6;
 			}
+			const DpDev &j0 = jobs[lo + flat[g.first]];
+			fprintf(stderr, "[mpb-trace] nasw %s class %d%s: %zu jobs, longest nl=%d al=%d, %.1f Mcell, %.2f ms | nl>=64k %d (%.0f Mc), >=32k %d (%.0f), >=16k %d (%.0f), >=8k %d (%.0f), <8k %d (%.0f)\n",
+			        g.b ? "tb " : "ext", g.c, "", g.count, j0.nl, j0.al, cells, ms, hist[0], hc[0], hist[1], hc[1], hist[2], hc[2], hist[3], hc[3], hist[4], hc[4]);
 		}
+	}
 	ctx->stats.d2h_bytes += sizeof(int4) * n + sizeof(uint32_t) * (size_t)cig_tot;
 	const int4 *ho = ctx->h_out.as<int4>();
 	const uint32_t *hc = ctx->h_cigar.as<uint32_t>();
@@ -197,7 +204,7 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_
 			const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
 			const bool v3 = use_v3(j.al, j.nl);
 			const int C = pick_C(j.al), Wp = v3 ? 32 * v3_warps(j.al) : 32 * C, W8 = (j.al + 7) / 8 * 8, n_pass = v3 ? 1 : (W8 + Wp - 1) / Wp;
-			const size_t tbb = is_tb ? (size_t)n_pass * (size_t)(j.nl + 3 * Wp + 64) * Wp * 2 : 0, rwb = (size_t)(j.nl + 12) * 32;
+			const size_t tbb = is_tb ? (size_t)n_pass * (size_t)(j.nl + 3 * Wp + 64) * Wp * 2 : 0, rwb = (size_t)(j.nl + 20) * 32;
 			if (hi > lo && (tb_bytes + tbb > kTbBudget || rw_bytes + rwb > kRwBudget)) break;
 			tb_bytes += tbb, rw_bytes += rwb, ++hi;
 		}

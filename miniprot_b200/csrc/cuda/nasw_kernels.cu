@@ -55,11 +55,18 @@ __global__ void __launch_bounds__(256) nasw_prep_kernel(const DpDev *jobs, const
 	__syncthreads();
 	Par par;
 	par.go = cst.go, par.ge = cst.ge, par.io = job.io, par.fs = cst.fs, par.gei_stop = cst.fs;
+	const int M = v3_triples(job.nl);
 	for (int x = threadIdx.x; x < c.n_rows; x += blockDim.x) {
 		const RowRec r = make_row_rec(par, w[x], w[x + 1], w[x + 2], w[x + 3]);
-		int4 *dst = rec + (job.rw_off + c.row0 + x) * 2;
-		dst[0] = make_int4(r.cA, r.cB, r.cC, r.gei);
-		dst[1] = make_int4(r.aA, r.aB, r.aC, r.nas);
+		const int i = c.row0 + x;
+		int4 *dst, *dst2;
+		if (job.C == 0) { // block-wide kernels: triple-major, field-major (nasw_core.cuh v3_triples); rows 0 and 1 are never read
+			if (i < 2) continue;
+			const int m = (i - 2) / 3, k = (i - 2) - 3 * m;
+			dst = rec + job.rw_off * 2 + (int64_t)(2 * k) * M + m, dst2 = dst + M;
+		} else dst = rec + (job.rw_off + i) * 2, dst2 = dst + 1;
+		*dst = make_int4(r.cA, r.cB, r.cC, r.gei);
+		*dst2 = make_int4(r.aA, r.aB, r.aC, r.nas);
 	}
 }
 
@@ -84,6 +91,52 @@ __device__ __forceinline__ void build_profile(int *prof, int Wp, int pass, const
 	__syncwarp();
 }
 
+// shared-memory accesses through 32-bit shared-window addresses computed once (the generic form makes the compiler rebuild
+// the window base -- S2R + LEA -- next to every access of the loop)
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts32(uint32_t a, int v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ int lds32(uint32_t a)
+{
+	int v;
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, int4 v) { asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+__device__ __forceinline__ int4 lds128(uint32_t a)
+{
+	int4 v;
+	asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+	return v;
+}
+
+// environment of one column of the block-wide kernels: triple-major row records (nasw_core.cuh v3_triples) and the profile
+struct DevEnv3 {
+	const int4 *rec;     // field 0 of triple 0
+	int M;               // triples per field array
+	const int *prof;     // profile in shared memory, already offset to this column
+	int Wp;
+	const int4 *cur;     // steady-state cursor: field 0 of the next triple to fetch
+	__device__ __forceinline__ void load3(const int4 *q, RowRec &r0, RowRec &r1, RowRec &r2) const
+	{
+		const int4 a0 = __ldg(q), b0 = __ldg(q + M), a1 = __ldg(q + 2 * M), b1 = __ldg(q + 3 * M), a2 = __ldg(q + 4 * M), b2 = __ldg(q + 5 * M);
+		r0.cA = a0.x, r0.cB = a0.y, r0.cC = a0.z, r0.gei = a0.w, r0.aA = b0.x, r0.aB = b0.y, r0.aC = b0.z, r0.nas = b0.w;
+		r1.cA = a1.x, r1.cB = a1.y, r1.cC = a1.z, r1.gei = a1.w, r1.aA = b1.x, r1.aB = b1.y, r1.aC = b1.z, r1.nas = b1.w;
+		r2.cA = a2.x, r2.cB = a2.y, r2.cC = a2.z, r2.gei = a2.w, r2.aA = b2.x, r2.aB = b2.y, r2.aC = b2.z, r2.nas = b2.w;
+	}
+	// triple m (clamped: whatever a clamped index delivers belongs to rows that are never computed)
+	__device__ __forceinline__ void rec3(int m, RowRec &r0, RowRec &r1, RowRec &r2) const { load3(rec + (m < 0 ? 0 : (m >= M ? M - 1 : m)), r0, r1, r2); }
+	__device__ __forceinline__ void seek3(int m) { cur = rec + m; }
+	__device__ __forceinline__ void next3(RowRec &r0, RowRec &r1, RowRec &r2) { load3(cur, r0, r1, r2), ++cur; }
+	// columns 0..5 pull one field array each towards L1, 24 triples ahead of the front (column x's cursor + x = column 0's)
+	__device__ __forceinline__ void prefetch_ahead(int x) const
+	{
+		const int4 *q = cur + x + 24;
+		if (q < rec + M) asm volatile("prefetch.global.L1 [%0];" :: "l"(q + (int64_t)x * M));
+	}
+	__device__ __forceinline__ int profile_stride() const { return Wp; }
+	__device__ __forceinline__ const int *profile(int nas) const { return prof + nas * Wp; }
+};
+
 // what a lane needs from its surroundings (see nasw_core.cuh ExtLane/TbLane)
 struct DevEnv {
 	const int4 *rec;     // row records of this problem (2 x int4 per row)
@@ -98,32 +151,6 @@ struct DevEnv {
 		RowRec r;
 		r.cA = a.x, r.cB = a.y, r.cC = a.z, r.gei = a.w, r.aA = b.x, r.aB = b.y, r.aC = b.z, r.nas = b.w;
 		return r;
-	}
-	// records of rows i, i+1, i+2 with one clamp: exact whenever a real row (2 <= row < nl) is among them; the record array
-	// carries three padding rows after row nl
-	__device__ __forceinline__ void row_rec3(int i, RowRec &r0, RowRec &r1, RowRec &r2) const
-	{
-		i = i < 0 ? 0 : (i > nl ? nl : i);
-		const int4 *q = rec + 2 * i;
-		const int4 a0 = __ldg(q), b0 = __ldg(q + 1), a1 = __ldg(q + 2), b1 = __ldg(q + 3), a2 = __ldg(q + 4), b2 = __ldg(q + 5);
-		r0.cA = a0.x, r0.cB = a0.y, r0.cC = a0.z, r0.gei = a0.w, r0.aA = b0.x, r0.aB = b0.y, r0.aC = b0.z, r0.nas = b0.w;
-		r1.cA = a1.x, r1.cB = a1.y, r1.cC = a1.z, r1.gei = a1.w, r1.aA = b1.x, r1.aB = b1.y, r1.aC = b1.z, r1.nas = b1.w;
-		r2.cA = a2.x, r2.cB = a2.y, r2.cC = a2.z, r2.gei = a2.w, r2.aA = b2.x, r2.aB = b2.y, r2.aC = b2.z, r2.nas = b2.w;
-	}
-	const int4 *cur;     // steady-state cursor: the next three records to fetch
-	__device__ __forceinline__ void seek(int i) { cur = rec + 2 * i; }
-	__device__ __forceinline__ void prefetch_ahead() const // 66 rows past the cursor (the first column runs ahead of everyone)
-	{
-		if (cur + 2 * 66 <= rec + 2 * nl) asm volatile("prefetch.global.L1 [%0];" :: "l"(cur + 2 * 66));
-	}
-	__device__ __forceinline__ void next3(RowRec &r0, RowRec &r1, RowRec &r2)
-	{
-		const int4 *q = cur;
-		cur += 6;
-		const int4 a0 = __ldg(q), b0 = __ldg(q + 1), a1 = __ldg(q + 2), b1 = __ldg(q + 3), a2 = __ldg(q + 4), b2 = __ldg(q + 5);
-		r0.cA = a0.x, r0.cB = a0.y, r0.cC = a0.z, r0.gei = a0.w, r0.aA = b0.x, r0.aB = b0.y, r0.aC = b0.z, r0.nas = b0.w;
-		r1.cA = a1.x, r1.cB = a1.y, r1.cC = a1.z, r1.gei = a1.w, r1.aA = b1.x, r1.aB = b1.y, r1.aC = b1.z, r1.nas = b1.w;
-		r2.cA = a2.x, r2.cB = a2.y, r2.cC = a2.z, r2.gei = a2.w, r2.aA = b2.x, r2.aB = b2.y, r2.aC = b2.z, r2.nas = b2.w;
 	}
 	__device__ __forceinline__ int profile_stride() const { return Wp; }
 	__device__ __forceinline__ void prefetch_row(int i) const
@@ -259,6 +286,54 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_tb_kernel(const DpDev *j
 	if (lane == 0) out[jid] = make_int4(score, g.nl, g.al, 0);
 }
 
+// Extension bookkeeping of the block-wide kernel, 30 rows at a time.  ExtTracker::row (nasw_core.cuh) is the specification: a
+// running maximum of (row best - length penalty) with first-occurrence ties, and a stop at the first row that falls more than
+// xdrop below it.  Fed row by row it costs the warp that owns the last column ~15 divergent instructions per row on the
+// critical path; here the last column only drops its row maxima into a ring and, once 30 or more wait there, the 32 lanes
+// of that warp evaluate the rows together (prefix maximum by shuffles, ballots for the stop row and the winner).  The stop
+// is noticed up to ten macro-steps late, which is harmless: rows after the stop row are never looked at.
+struct WarpTracker {
+	int max_sc, max_log, max_i, max_code; // warp-uniform
+	bool stopped;
+	int n_ring, i_base;                   // rows [i_base, i_base + n_ring) wait in the ring
+	int pen, pk, next_thr;                // per lane: lane r follows the rows i_base + r of successive batches
+	__device__ __forceinline__ void init() { max_sc = INT32_MIN, max_log = INT32_MIN, max_i = -1, max_code = 0, stopped = false, n_ring = 0, i_base = 2, pen = 0, pk = 0, next_thr = 2; }
+	// the ring is [slot][lane]: every lane of the warp stores its own value (no divergent branch on the critical path) and
+	// only lane 31's column -- the last column of the problem -- is read back.  ring_w = address of (slot 0, this lane),
+	// ring_r = address of (slot = this lane, lane 31)
+	__device__ __forceinline__ void push(uint32_t ring_w, int v) { sts32(ring_w + n_ring * 128, v), ++n_ring; }
+	__device__ __forceinline__ void flush(uint32_t ring_r, int lane, int pen_base, const PenTable &pt, int xdrop)
+	{
+		__syncwarp();
+		if (!stopped) {
+			const bool valid = lane < n_ring;
+			const int i = i_base + lane, best = valid ? lds32(ring_r) : 0, x = i - pen_base;
+			if (valid && x >= next_thr) {
+				while (pk < pt.n && x >= pt.thr[pk]) pen = pt.val[pk], ++pk;
+				next_thr = pk < pt.n ? pt.thr[pk] : INT32_MAX;
+			}
+			const int tsc = best >> 12, tlog = valid ? tsc - pen : INT32_MIN;
+			int pm = tlog; // inclusive prefix maximum over the batch
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int o = __shfl_up_sync(0xffffffffu, pm, d);
+				if (lane >= d) pm = max(pm, o);
+			}
+			const int run = max(pm, max_log);
+			const unsigned sm = __ballot_sync(0xffffffffu, valid && run - tlog > xdrop);
+			const int last = sm ? __ffs(sm) - 1 : n_ring - 1; // the last row that is still looked at
+			const int bm = __shfl_sync(0xffffffffu, pm, last);
+			if (bm > max_log) {
+				const int w = __ffs(__ballot_sync(0xffffffffu, lane <= last && tlog == bm)) - 1;
+				max_log = bm, max_sc = __shfl_sync(0xffffffffu, tsc, w), max_code = __shfl_sync(0xffffffffu, best & 4095, w), max_i = i_base + w;
+			}
+			stopped = sm != 0;
+		}
+		i_base += n_ring, n_ring = 0;
+		__syncwarp();
+	}
+};
+
 // ------------------------------------------------------------------ block-wide wavefront (one thread per column, 3 rows per step)
 // CTA = NW warps = 32*NW columns of ONE problem; see nasw_core.cuh::Lane3.  TB = false: score-only extension (result by the
 // last thread's tracker); TB = true: global alignment, one 16-bit word per cell to tb[(3T + r) * 32NW + x].
@@ -267,8 +342,9 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
                                                           int4 *out, uint16_t *tb)
 {
 	extern __shared__ int smem[];
-	constexpr int Wp = 32 * NW, NX = TB ? 12 : 9;
-	__shared__ int xchg[2][NW + 1][12]; // [parity][warp + 1]: last column of each warp; slot 0 = the constant boundary left of column 0
+	constexpr int Wp = 32 * NW;
+	__shared__ __align__(16) int xchg[2][NW + 1][12]; // [parity][warp + 1]: last column of each warp; slot 0 = the constant boundary left of column 0
+	__shared__ int ring[TB ? 32 : 32 * 32];           // [slot][lane] row maxima waiting for the warp tracker (WarpTracker)
 	__shared__ int stop_flag[2]; // written by the last column during macro-step Tm into slot Tm & 1, read by everyone after that step's barrier
 	if ((int)blockIdx.x >= n_jobs) return;
 	const int jid = order[blockIdx.x];
@@ -287,11 +363,15 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 	if (x == 0) stop_flag[0] = stop_flag[1] = 0;
 	if (x < 24) xchg[x / 12][0][x % 12] = (!TB && x % 12 >= 6 && x % 12 < 9) ? INT32_MIN : NEG;
 	__syncthreads();
-	DevEnv env;
-	env.rec = rec + job.rw_off * 2, env.nl = g.nl, env.prof = smem + x, env.Wp = Wp, env.cy = 0;
+	const uint32_t xr[2] = { smem_addr(&xchg[0][warp][0]), smem_addr(&xchg[1][warp][0]) };         // what lane 0 receives from
+	const uint32_t xw[2] = { smem_addr(&xchg[0][warp + (warp < NW - 1)][0]), smem_addr(&xchg[1][warp + (warp < NW - 1)][0]) }; // what lane 31 sends to
+	const uint32_t sf = smem_addr(stop_flag), ring_w = smem_addr(ring) + lane * 4, ring_r = smem_addr(ring) + lane * 128 + 124;
+	(void)xw, (void)ring_w, (void)ring_r;
+	DevEnv3 env;
+	env.rec = rec + job.rw_off * 2, env.M = v3_triples(g.nl), env.prof = smem + x, env.Wp = Wp, env.cur = env.rec;
 	Lane3<TB> L;
 	L.init(g, cst.end_bonus, par.fs, env);
-	ExtTracker trk;
+	WarpTracker trk; // meaningful in the warp that owns the last column
 	trk.init();
 	const int n_macro = g.nl > 2 ? (g.nl - 2 + 2) / 3 + Wp : 0; // rows 2..nl-1 in triples, plus the skew of the last column
 	uint16_t *tbp = TB ? tb + job.tb_off + x : 0;
@@ -303,16 +383,17 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 			rS[r] = TB ? __shfl_up_sync(0xffffffffu, L.oS[r], 1) : 0; \
 		} \
 		if (lane == 0) { /* the column to my left lives in the previous warp; slot 0 holds the constant left boundary */ \
-			const int *b = xchg[PH ^ 1][warp]; \
-			_Pragma("unroll") for (int r = 0; r < 3; ++r) { RH[r] = b[r], rI[r] = b[3 + r], rX[r] = b[6 + r]; if (TB) rS[r] = b[9 + r]; } \
+			const int4 b0 = lds128(xr[PH ^ 1]), b1 = lds128(xr[PH ^ 1] + 16), b2 = lds128(xr[PH ^ 1] + 32); \
+			RH[0] = b0.x, RH[1] = b0.y, RH[2] = b0.z, rI[0] = b0.w, rI[1] = b1.x, rI[2] = b1.y, rX[0] = b1.z, rX[1] = b1.w, rX[2] = b2.x; \
+			if (TB) rS[0] = b2.y, rS[1] = b2.z, rS[2] = b2.w; \
 		}
 #define NSW_V3_SEND(PH) \
 		if (NW > 1) { \
 			if (lane == 31 && warp < NW - 1) { \
-				int *b = xchg[PH][warp + 1]; \
-				_Pragma("unroll") for (int r = 0; r < 3; ++r) { b[r] = L.oH[r], b[3 + r] = L.oI[r], b[6 + r] = L.oX[r]; if (TB) b[9 + r] = L.oS[r]; } \
+				sts128(xw[PH], make_int4(L.oH[0], L.oH[1], L.oH[2], L.oI[0])), sts128(xw[PH] + 16, make_int4(L.oI[1], L.oI[2], L.oX[0], L.oX[1])); \
+				sts128(xw[PH] + 32, make_int4(L.oX[2], TB ? L.oS[0] : 0, TB ? L.oS[1] : 0, TB ? L.oS[2] : 0)); \
 			} \
-			if (!TB && x == Wp - 1) stop_flag[PH] = trk.stopped ? 1 : 0; \
+			if (!TB && x == Wp - 1) sts32(sf + 4 * PH, trk.stopped ? 1 : 0); \
 			__syncthreads(); \
 		}
 #define NSW_V3_MACRO(PH) { /* general step: ramp-up, ramp-down */ \
@@ -321,20 +402,28 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 		uint32_t wd[3]; \
 		const uint32_t done = L.template macro<PH>(g, par, T + PH, rH, rI, rX, rS, env, wd); \
 		if (TB) { _Pragma("unroll") for (int r = 0; r < 3; ++r) if (done >> r & 1) tbp[(int64_t)(3 * (T + PH) + r) * Wp] = (uint16_t)wd[r]; } \
-		else if (x == Wp - 1) { /* the last column sees the complete row maxima */ \
-			_Pragma("unroll") for (int r = 0; r < 3; ++r) if (done >> r & 1) trk.row(Lane3<TB>::row_of(g, T + PH, r), L.oX[r], g.al * 3, cst.pen, cst.xdrop); } \
+		else if (warp == NW - 1) { /* the last column sees the complete row maxima; its rows are real when 2 <= i < nl */ \
+			(void)done; \
+			_Pragma("unroll") for (int r = 0; r < 3; ++r) { \
+				const int il = 3 * (T + PH - (Wp - 1)) + 2 + r; \
+				if (il >= 2 && il < g.nl) trk.push(ring_w, L.oX[r]); \
+			} \
+			if (trk.n_ring >= 30) trk.flush(ring_r, lane, g.al * 3, cst.pen, cst.xdrop); } \
 		NSW_V3_SEND(PH) }
 #define NSW_V3_STEADY(PH) { /* every column has three real rows: nothing to check */ \
 		NSW_V3_RECV(PH, hb[PH]) \
 		uint32_t wd[3]; \
 		L.template macro_steady<PH>(g, par, hb[PH ^ 1], hb[PH], rI, rX, rS, env, wd); \
 		if (TB) { if (g.live) { _Pragma("unroll") for (int r = 0; r < 3; ++r) tbs[r * Wp] = (uint16_t)wd[r]; } tbs += 3 * Wp; } \
-		else if (x == Wp - 1) { _Pragma("unroll") for (int r = 0; r < 3; ++r) trk.row(Lane3<TB>::row_of(g, T + PH, r), L.oX[r], g.al * 3, cst.pen, cst.xdrop); } \
+		else if (warp == NW - 1) { \
+			_Pragma("unroll") for (int r = 0; r < 3; ++r) sts32(ring_w + (trk.n_ring + r) * 128, L.oX[r]); \
+			trk.n_ring += 3; \
+			if (trk.n_ring == 30) trk.flush(ring_r, lane, g.al * 3, cst.pen, cst.xdrop); } \
 		NSW_V3_SEND(PH) }
 #define NSW_V3_CHECK_STOP \
 		if (!TB) { /* x-drop: the last column's tracker decides; rows after the break row are never looked at */ \
-			if (NW > 1) { if (stop_flag[1]) break; } \
-			else if (__shfl_sync(0xffffffffu, (int)trk.stopped, 31)) break; \
+			if (NW > 1) { if (lds32(sf + 4)) break; } \
+			else if (trk.stopped) break; \
 		}
 	int t_lo, t_hi;
 	Lane3<TB>::steady_range(g.nl, Wp, t_lo, t_hi);
@@ -356,7 +445,7 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 #undef NSW_V3_STEADY
 #undef NSW_V3_CHECK_STOP
 #undef NSW_V3_MACRO
-	(void)NX;
+	if (!TB && warp == NW - 1 && trk.n_ring > 0) trk.flush(ring_r, lane, g.al * 3, cst.pen, cst.xdrop); // the last, partial batch
 	if (TB) {
 		// the thread that owns column al-1 holds H(nl-1, al-1)
 		if (x == (job.al > 0 ? job.al - 1 : 0)) out[jid] = make_int4(L.score, g.nl, g.al, 0);

@@ -23,11 +23,13 @@ struct EmuEnv {
 	int *cy;
 	RowRec row_rec(int i) const { i = i < 0 ? 0 : (i > nl ? nl : i); return rec[i]; }
 	void prefetch_row(int) const {}
-	int cur;
-	void seek(int i) { cur = i; }
-	void prefetch_ahead() const {}
-	void next3(RowRec &r0, RowRec &r1, RowRec &r2) { r0 = rec[cur], r1 = rec[cur + 1], r2 = rec[cur + 2], cur += 3; }
-	void row_rec3(int i, RowRec &r0, RowRec &r1, RowRec &r2) const { i = i < 0 ? 0 : (i > nl ? nl : i); r0 = rec[i], r1 = rec[i + 1], r2 = rec[i + 2]; }
+	// block-wide kernels: records by triple of rows (triple m = rows 3m+2..3m+4); the device stores them field-major, which
+	// changes the addresses, not the values
+	int cur, M;
+	void rec3(int m, RowRec &r0, RowRec &r1, RowRec &r2) const { m = m < 0 ? 0 : (m >= M ? M - 1 : m); r0 = rec[3 * m + 2], r1 = rec[3 * m + 3], r2 = rec[3 * m + 4]; }
+	void seek3(int m) { cur = m; }
+	void prefetch_ahead(int) const {}
+	void next3(RowRec &r0, RowRec &r1, RowRec &r2) { r0 = rec[3 * cur + 2], r1 = rec[3 * cur + 3], r2 = rec[3 * cur + 4], ++cur; }
 	int profile_stride() const { return Wp; }
 	const int *profile(int nas) const { return prof + nas * Wp; }
 	void carry_load3(int i, int &a, int &b, int &c) const { a = cy[(int64_t)i * 3], b = cy[(int64_t)i * 3 + 1], c = cy[(int64_t)i * 3 + 2]; }
@@ -183,7 +185,7 @@ void run_v3(const Problem &P, int *score, int *nt_len, int *aa_len, std::vector<
 	pen_table_build(P.ie_coef, pt);
 	for (int x = 0; x < Wp; ++x) {
 		g[x].x = x, g[x].nl = P.nl, g[x].al = P.al, g[x].W8 = P.W8, g[x].live = x < P.W8, g[x].first = x == 0;
-		env[x].rec = P.rec.data(), env[x].nl = P.nl, env[x].prof = prof.data() + x, env[x].Wp = Wp, env[x].cy = 0;
+		env[x].rec = P.rec.data(), env[x].nl = P.nl, env[x].prof = prof.data() + x, env[x].Wp = Wp, env[x].cy = 0, env[x].M = v3_triples(P.nl), env[x].cur = 0;
 		L[x].init(g[x], P.end_bonus, P.par.fs, env[x]);
 		trk[x].init();
 	}
@@ -268,14 +270,15 @@ extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *
 	std::vector<int> code((size_t)nl);
 	for (int k = 0; k < nl; ++k) code[(size_t)k] = nt4[ns[left ? nl - 1 - k : k]];
 	auto c = [&](int k) { return code[(size_t)k]; };
-	std::vector<uint32_t> w((size_t)nl + 4);
-	for (int x = 0; x < nl + 4; ++x) { // slot x <-> row x - 2, clamped like the prep kernel
+	const int n_rec = std::max(nl + 1, 2 + 3 * v3_triples(nl)); // rows past nl repeat the clamped rules, like the prep kernel
+	std::vector<uint32_t> w((size_t)n_rec + 3);
+	for (int x = 0; x < n_rec + 3; ++x) { // slot x <-> row x - 2, clamped like the prep kernel
 		int r = x - 2;
 		r = r < 0 ? 0 : (r > nl ? nl : r);
 		w[(size_t)x] = left ? prep_row_left(c, nl, r, sp, codon, aa20['X']) : prep_row_forward(c, nl, r, sp, codon, aa20['X']);
 	}
-	P.rec.resize((size_t)nl + 9); // eight padding rows after row nl, like the device buffer
-	for (int r = 0; r <= nl; ++r) P.rec[(size_t)r] = make_row_rec(P.par, w[(size_t)r], w[(size_t)r + 1], w[(size_t)r + 2], w[(size_t)r + 3]);
+	P.rec.resize((size_t)n_rec);
+	for (int r = 0; r < n_rec; ++r) P.rec[(size_t)r] = make_row_rec(P.par, w[(size_t)r], w[(size_t)r + 1], w[(size_t)r + 2], w[(size_t)r + 3]);
 	P.aas.resize((size_t)al);
 	for (int j = 0; j < al; ++j) P.aas[(size_t)j] = aa20[(uint8_t)as[left ? al - 1 - j : j]];
 	*nt_len = nl, *aa_len = al;
