@@ -1,5 +1,6 @@
 // backend.cu -- the CUDA implementation of the stage interface (mpb::Stages) and the C ABI of the batch API.
 // This is the ONLY implementation of the stages in the product: there is no CPU fallback.
+#include <algorithm>
 #include <stdio.h>
 #include <mutex>
 #include "ctx.hpp"
@@ -114,8 +115,12 @@ mpb_ctx_t *mpb_ctx_create(int device)
 	MPB_CUDA_OK(cudaEventCreate(&c->ev0));
 	MPB_CUDA_OK(cudaEventCreate(&c->ev1));
 	MPB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+	int prio_lo = 0, prio_hi = 0;
+	MPB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
 	for (int i = 0; i < mpb_ctx_s::N_SIDE; ++i) {
-		MPB_CUDA_OK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+		// (numerically lower = more urgent) widest extension class first, then the other extension classes, then the rest
+		const int prio = i == 3 ? prio_hi : i < 9 ? std::min(prio_hi + 1, prio_lo) : prio_lo;
+		MPB_CUDA_OK(cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, prio));
 		MPB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
 		MPB_CUDA_OK(cudaEventCreate(&c->ev_k0[i]));
 		MPB_CUDA_OK(cudaEventCreate(&c->ev_k1[i]));

@@ -50,7 +50,7 @@ void nasw_launch_ext(cudaStream_t st, int C, const DpDev *jobs, const int *order
 void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, int *carry,
                     uint16_t *tb);
 void nasw_launch_v3(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out,
-                    uint16_t *tb);
+                    uint16_t *tb, int warps_per_sm = 0);
 void nasw_launch_bt(cudaStream_t st, const DpDev *jobs, const int *order, int n, const uint16_t *tb, uint32_t *cigar, int4 *out);
 
 } // namespace cuda

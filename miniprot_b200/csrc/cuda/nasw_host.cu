@@ -119,13 +119,19 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	nasw_launch_prep(st, dj, ctx->b_chunks.as<PrepChunk>(), (int)chunks.size(), packed, cst, ctx->b_rw.as<int4>());
 	ctx->stats.kernel_launches += 1;
 	static const int Cs[9] = { 1, 2, 4, 8, 1, 2, 4, 8, 16 }; // warps per problem (classes 0..3) or columns per lane (4..8)
+	// Scheduling of a big wave.  It is bounded by its longest extensions (100 k rows next to thousands of short problems):
+	//  * the extension classes run on high-priority streams and are ordered longest first, so those problems start at once;
+	//  * the widest class (8 warps that meet at a barrier every macro-step) loses half its speed when foreign warps share
+	//    its issue slots, and it holds only a handful of problems: its blocks get an SM each (residency cap, nasw_launch_v3).
+	// MPB_NASW_WSM=<warps per SM> caps every block-wide launch instead (measurements only).
+	static const int wsm_env = getenv("MPB_NASW_WSM") ? atoi(getenv("MPB_NASW_WSM")) : -1;
+	const bool big_wave = n >= 296;
 	// fork: every (kind, size class) runs on its own stream -- each is bounded by its longest problem
 	struct Group { int sid, b, c; size_t first, count; };
 	std::vector<Group> groups;
 	for (int b = 0; b < 2; ++b)
-		for (int c = 8; c >= 0; --c) {
+		for (int c = 8; c >= 0; --c)
 			if (count[b][c]) groups.push_back(Group{ b * 9 + c, b, c, first[b][c], count[b][c] });
-		}
 	MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
 	for (const Group &g : groups) {
 		cudaStream_t ss = ctx->side[g.sid];
@@ -134,7 +140,8 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
 		MPB_CUDA_OK(cudaEventRecord(ctx->ev_k0[g.sid], ss));
 		if (c < 4) {
-			nasw_launch_v3(ss, Cs[c], b == 1, dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>());
+			nasw_launch_v3(ss, Cs[c], b == 1, dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>(),
+			               wsm_env >= 0 ? wsm_env : (big_wave && b == 0 && c == 3 && cnt <= 148) ? 8 : 0);
 			ctx->stats.kernel_launches += 1;
 			if (b == 1) {
 				nasw_launch_bt(ss, dj, ord, cnt, ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());

@@ -16,6 +16,7 @@
 //
 // Problems wider than 32*C columns are processed in column passes of 32*C; the last lane spills its per-row
 // outputs to a carry array that lane 0 of the next pass reads back (rows stay in wavefront order).
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "nasw_core.cuh"
@@ -552,26 +553,44 @@ void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order,
 	}
 }
 
+// warps_per_sm > 0: pad the dynamic shared memory request to nw / warps_per_sm of an SM's shared memory, so that at most that
+// many warps of such launches are resident per SM and the hardware dispatches the remaining blocks -- in index order, i.e.
+// longest problem first -- as earlier ones retire (list scheduling by decreasing length).  Without the cap every block of a
+// wave is resident from the start and the few 100 k-row problems that set the critical path share their issue slots with
+// thousands of short ones.  (228 KB per SM, 1 KB reserved per block, static arrays included.)
 template <int NW, bool TB>
-static void launch_v3(cudaStream_t st, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, uint16_t *tb)
+static void launch_v3(cudaStream_t st, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, uint16_t *tb,
+                      int warps_per_sm)
 {
-	nasw_v3_kernel<NW, TB><<<n, NW * 32, 22 * 32 * NW * (int)sizeof(int), st>>>(jobs, order, n, rec, aa, cst, out, tb);
+	int smem = 22 * 32 * NW * (int)sizeof(int);
+	if (warps_per_sm > 0) {
+		static int stat = -1;
+		if (stat < 0) {
+			cudaFuncAttributes fa;
+			cudaFuncGetAttributes(&fa, nasw_v3_kernel<NW, TB>);
+			stat = ((int)fa.sharedSizeBytes + 15) & ~15;
+			cudaFuncSetAttribute(nasw_v3_kernel<NW, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - stat);
+		}
+		const int share = (int)((int64_t)233472 * NW / warps_per_sm) - 1024 - stat;
+		smem = std::max(smem, std::min(share, 232448 - stat)) & ~15;
+	}
+	nasw_v3_kernel<NW, TB><<<n, NW * 32, smem, st>>>(jobs, order, n, rec, aa, cst, out, tb);
 }
 
 // block-wide wavefront kernels: nw = warps per problem (1, 2, 4 or 8)
 void nasw_launch_v3(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out,
-                    uint16_t *tb)
+                    uint16_t *tb, int warps_per_sm)
 {
 	if (n <= 0) return;
 	switch (nw * 2 + (is_tb ? 1 : 0)) {
-	case 2: launch_v3<1, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	case 3: launch_v3<1, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	case 4: launch_v3<2, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	case 5: launch_v3<2, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	case 8: launch_v3<4, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	case 9: launch_v3<4, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	case 16: launch_v3<8, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	default: launch_v3<8, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	case 2: launch_v3<1, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
+	case 3: launch_v3<1, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
+	case 4: launch_v3<2, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
+	case 5: launch_v3<2, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
+	case 8: launch_v3<4, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
+	case 9: launch_v3<4, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
+	case 16: launch_v3<8, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
+	default: launch_v3<8, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
 	}
 }
 
