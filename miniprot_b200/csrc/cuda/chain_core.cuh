@@ -151,19 +151,24 @@ CHN_HD int64_t bk_end(int32_t max_drop, uint64_t z, const FT *f, const PT *p, T 
 }
 
 // Sequential tail of mp_chain for ONE problem, after z[0..n_z) has been filled with (f<<32 | index) records in index
-// order and t[0..n) cleared.  Scratch: t[n] marks, v[n], z[>=n], stack[>=CHAIN_STACK]; f[] is OVERWRITTEN (it is dead after
-// the peeling and serves as the chain-offset table of the compaction).
-// Output: u[0..n_u) = score<<32|cnt, b[0..n_b) = compacted anchors (chains ordered by target start).  Returns n_u.
-// PRESORTED: z[] has already been sorted by the caller (the warp-cooperative sort of the shared-memory kernel).
-// FT / PT: element types of the score and predecessor arrays (int32 in global memory; uint16 / int16 copies in shared
-// memory for problems of fewer than 32768 anchors whose scores fit 16 bits).
+// order and t[0..n) cleared, in two parts.
+//
+// peel_chains (chain.c:26-75): best-first peeling, inherently sequential -- three dependent accesses per visited anchor, so
+//   the kernels keep z/f/p/t in shared memory for it.  Scratch: t[n] marks, v[n], z[>=n], stack[>=CHAIN_STACK].
+//   Output: u[0..n_u) = score<<32|cnt and v[0..n_v) = the chains' anchor indices, chain after chain.  Returns n_u.
+//   PRESORTED: z[] has already been sorted by the caller (the warp-cooperative sort of the shared-memory kernels).
+//   FT / PT: element types of the score and predecessor arrays (int32 in global memory; narrower copies in shared memory).
+// compact_chains (chain.c:77-110): chains reversed to ascending order and ordered by first target coordinate.  The copy is
+//   data parallel: `lane` of `n_lanes` threads share it (1 on the CPU and in the single-thread kernel, 32 in the warp
+//   kernels), sync() is their barrier.  f[] is OVERWRITTEN (dead after the peeling, it serves as the chain-offset table).
+//   Output: b[0..n_b) = compacted anchors, u[] permuted accordingly.
 template <class T, bool PRESORTED = false, class FT = int32_t, class PT = int32_t>
-CHN_HD int32_t peel_and_compact(const Par &p, int32_t n_z, const uint64_t *a, FT *f, const PT *pp, T *t, int32_t *v, uint64_t *z,
-                                mpb::FlagRange<uint64_t> *stack, uint64_t *u, uint64_t *b, int32_t *n_b_out)
+CHN_HD int32_t peel_chains(const Par &p, int32_t n_z, const FT *f, const PT *pp, T *t, int32_t *v, uint64_t *z, mpb::FlagRange<uint64_t> *stack, uint64_t *u,
+                           int32_t *n_v_out = 0)
 {
 	const int32_t max_drop = p.is_spliced ? INT32_MAX : p.bw;
 	int32_t n_u = 0, n_v = 0;
-	*n_b_out = 0;
+	if (n_v_out) *n_v_out = 0;
 	if (n_z == 0) return 0;
 	if (!PRESORTED) mpb::flag_sort_by(z, z + n_z, [](const uint64_t &e) { return rec_key(e); }, stack);
 	for (int32_t k = n_z - 1; k >= 0; --k) {
@@ -177,24 +182,49 @@ CHN_HD int32_t peel_and_compact(const Par &p, int32_t n_z, const uint64_t *a, FT
 		if (sc >= p.min_sc && n_v > n_v0 && n_v - n_v0 >= p.min_cnt) u[n_u++] = (uint64_t)sc << 32 | (uint64_t)(n_v - n_v0);
 		else n_v = n_v0;
 	}
-	if (n_u == 0) return 0;
-	// compact (chain.c:77-110): chains reversed to ascending order, then ordered by first target coordinate
-	int32_t k = 0;
-	for (int32_t i = 0; i < n_u; ++i) {
-		const int32_t ni = (int32_t)(uint32_t)u[i];
-		z[i] = (a[v[k + ni - 1]] >> 32) << 32 | (uint32_t)i; // first anchor of the chain after reversal
-		f[i] = (FT)k;
-		k += ni;
+	if (n_v_out) *n_v_out = n_v;
+	return n_u;
+}
+
+template <class FT, class Sync>
+CHN_HD void compact_chains(int32_t n_u, const uint64_t *a, FT *f, const int32_t *v, uint64_t *z, mpb::FlagRange<uint64_t> *stack, uint64_t *u, uint64_t *b,
+                           int32_t *n_b_out, int lane, int n_lanes, Sync sync)
+{
+	if (n_u == 0) {
+		if (lane == 0) *n_b_out = 0;
+		return;
 	}
-	mpb::flag_sort_by(z, z + n_u, [](const uint64_t &e) { return rec_key(e); }, stack);
+	if (lane == 0) {
+		int32_t k = 0;
+		for (int32_t i = 0; i < n_u; ++i) {
+			const int32_t ni = (int32_t)(uint32_t)u[i];
+			z[i] = (a[v[k + ni - 1]] >> 32) << 32 | (uint32_t)i; // first anchor of the chain after reversal
+			f[i] = (FT)k;
+			k += ni;
+		}
+		mpb::flag_sort_by(z, z + n_u, [](const uint64_t &e) { return rec_key(e); }, stack);
+	}
+	sync();
 	int32_t o = 0;
 	for (int32_t i = 0; i < n_u; ++i) {
 		const int32_t src = (int32_t)(uint32_t)z[i], k0 = (int32_t)f[src], ni = (int32_t)(uint32_t)u[src];
-		for (int32_t j = 0; j < ni; ++j) b[o++] = a[v[k0 + (ni - j - 1)]];
+		for (int32_t j = lane; j < ni; j += n_lanes) b[o + j] = a[v[k0 + (ni - j - 1)]];
+		o += ni;
 	}
-	for (int32_t i = 0; i < n_u; ++i) z[i] = u[(uint32_t)z[i]]; // u2[i] = u[perm[i]]
-	for (int32_t i = 0; i < n_u; ++i) u[i] = z[i];
-	*n_b_out = o;
+	sync();
+	for (int32_t i = lane; i < n_u; i += n_lanes) z[i] = u[(uint32_t)z[i]]; // u2[i] = u[perm[i]]
+	sync();
+	for (int32_t i = lane; i < n_u; i += n_lanes) u[i] = z[i];
+	if (lane == 0) *n_b_out = o;
+}
+
+// both parts by one thread
+template <class T, bool PRESORTED = false, class FT = int32_t, class PT = int32_t>
+CHN_HD int32_t peel_and_compact(const Par &p, int32_t n_z, const uint64_t *a, FT *f, const PT *pp, T *t, int32_t *v, uint64_t *z,
+                                mpb::FlagRange<uint64_t> *stack, uint64_t *u, uint64_t *b, int32_t *n_b_out)
+{
+	const int32_t n_u = peel_chains<T, PRESORTED, FT, PT>(p, n_z, f, pp, t, v, z, stack, u);
+	compact_chains(n_u, a, f, v, z, stack, u, b, n_b_out, 0, 1, [] {});
 	return n_u;
 }
 

@@ -145,6 +145,27 @@ __device__ void flag_sort_warp(uint64_t *rec, int n, KeyFn key, FlagRange<uint64
 	}
 }
 
+// Result of the block-level pre-chain (map.c:189-192): the reference compacts the accepted chains and then re-sorts the kept
+// anchors with a plain 64-bit radix sort whose key is the WHOLE anchor -- i.e. it ends up with the accepted anchors in
+// their original sorted order.  So: mark them (v[0..n_v) from the peeling) and stream-compact the sorted input.
+template <class T>
+__device__ int32_t keep_filter_warp(int32_t n, int32_t n_v, const int32_t *v, T *t, const uint64_t *a, uint64_t *b, int lane)
+{
+	for (int32_t i = lane; i < n; i += 32) t[i] = 0;
+	__syncwarp();
+	for (int32_t k = lane; k < n_v; k += 32) t[v[k]] = 1;
+	__syncwarp();
+	int32_t o = 0;
+	for (int32_t i0 = 0; i0 < n; i0 += 32) {
+		const int32_t i = i0 + lane;
+		const bool keep = i < n && t[i] != 0;
+		const uint32_t m = __ballot_sync(0xffffffffu, keep);
+		if (keep) b[o + __popc(m & ((1u << lane) - 1u))] = a[i];
+		o += __popc(m);
+	}
+	return o;
+}
+
 // Whole mp_chain for one problem in ONE warp with all per-anchor state in shared memory: scores f (int32), predecessors p
 // and scan marks t (int16: fewer than 32768 anchors), sort records (8 B).  Phase 1 is the score fill of chain_fill_kernel
 // with shared-memory state (an L2 round trip per dependent access otherwise dominates: ~2 us per anchor), phase 2 the
@@ -226,24 +247,25 @@ __global__ void __launch_bounds__(32) chain_smem_kernel(const int32_t *list, int
 	int32_t n_u = 0, n_b = 0;
 	FlagRange<uint64_t> *stack = stack_all + (int64_t)prob * CHAIN_STACK;
 	flag_sort_warp(zs, n_z, [](const uint64_t &e) { return rec_key(e); }, stack, &ws, lane);
-	if (lane == 0 && n > 0)
-		n_u = peel_and_compact<int16_t, true, int32_t, int16_t>(par, n_z, a, f, p, t, v_all + base, zs, stack, u_all + base, b_all + base, &n_b);
-	n_b = __shfl_sync(0xffffffffu, n_b, 0);
-	if (resort && n_b > 1) { // map.c:191: the anchors kept by the pre-chain go back into plain sorted order
-		uint64_t *b = b_all + base;
+	int32_t n_v = 0;
+	if (lane == 0 && n > 0) n_u = peel_chains<int16_t, true, int32_t, int16_t>(par, n_z, f, p, t, v_all + base, zs, stack, u_all + base, &n_v);
+	n_u = __shfl_sync(0xffffffffu, n_u, 0), n_v = __shfl_sync(0xffffffffu, n_v, 0);
+	__syncwarp();
+	if (resort) n_b = keep_filter_warp(n, n_v, v_all + base, t, a, b_all + base, lane); // pre-chain: accepted anchors in sorted order
+	else {
+		if (n > 0) compact_chains(n_u, a, f, v_all + base, zs, stack, u_all + base, b_all + base, &n_b, lane, 32, [] { __syncwarp(); });
 		__syncwarp();
-		for (int32_t i = lane; i < n_b; i += 32) zs[i] = b[i];
-		__syncwarp();
-		flag_sort_warp(zs, n_b, [](const uint64_t &x) { return x; }, stack, &ws, lane);
-		for (int32_t i = lane; i < n_b; i += 32) b[i] = zs[i];
+		n_b = __shfl_sync(0xffffffffu, n_b, 0);
 	}
 	if (lane == 0) n_u_out[prob] = n_u, n_b_out[prob] = n_b;
 }
 
-// Backtrack + compaction, one WARP per problem, sort records and marks in shared memory.
-// Lanes cooperate on the parallel parts (clearing marks, gathering the (score, index) records in order, re-sorting the
-// kept anchors' staging copies); lane 0 runs the order-dependent part (flag sort, best-first peeling, chain ordering)
-// against shared memory instead of one dependent L2 access per step.
+// Backtrack + compaction, one WARP per problem, after the global-memory fill.  The peeling is a chain of dependent
+// accesses (predecessor -> mark -> score, three passes over every chain), so everything it touches sits in shared memory:
+// sort records (8 B), scores as uint16 (2 B), predecessors as int16 (2 B), marks (1 B) -- 13 B per anchor.  A problem
+// with a chain score of 65536 or more (never seen; a protein would need > 10^4 residues in one chain) reads its scores from
+// global memory instead.  Lanes cooperate on the parallel parts (loading, gathering the (score, index) records in order,
+// the flag sort, the compaction copy, re-sorting the kept anchors); lane 0 peels.
 __global__ void __launch_bounds__(32) chain_bt_smem_kernel(const int32_t *list, int n_list, int cap, const int64_t *a_off, const int32_t *cnt, const uint64_t *a_all,
                                                           Par par, int32_t *f_all, const int32_t *p_all, int32_t *v_all, FlagRange<uint64_t> *stack_all,
                                                           uint64_t *u_all, uint64_t *b_all, int32_t *n_u_out, int32_t *n_b_out, int resort)
@@ -254,30 +276,45 @@ __global__ void __launch_bounds__(32) chain_bt_smem_kernel(const int32_t *list, 
 	const int prob = list[blockIdx.x], lane = threadIdx.x;
 	const int64_t base = a_off[prob];
 	const int32_t n = cnt ? cnt[prob] : (int32_t)(a_off[prob + 1] - base);
-	int8_t *ts = (int8_t*)(zs + cap);
-	int32_t *f = f_all + base;
+	uint16_t *fs = (uint16_t*)(zs + cap);
+	int16_t *ps = (int16_t*)(fs + cap);
+	int8_t *ts = (int8_t*)(ps + cap);
+	int32_t *fg = f_all + base;
+	const int32_t *pg = p_all + base;
 	int32_t n_z = 0;
+	bool wide = false;
 	for (int32_t i0 = 0; i0 < n; i0 += 32) {
 		const int32_t i = i0 + lane;
-		const bool keep = i < n && f[i] >= par.min_sc;
-		if (i < n) ts[i] = 0;
+		const int32_t fi = i < n ? fg[i] : 0;
+		const bool keep = i < n && fi >= par.min_sc;
+		if (i < n) ts[i] = 0, ps[i] = (int16_t)pg[i], fs[i] = (uint16_t)fi;
+		wide |= fi > 65535;
 		const uint32_t m = __ballot_sync(0xffffffffu, keep);
-		if (keep) zs[n_z + __popc(m & ((1u << lane) - 1u))] = (uint64_t)(uint32_t)f[i] << 32 | (uint32_t)i;
+		if (keep) zs[n_z + __popc(m & ((1u << lane) - 1u))] = (uint64_t)(uint32_t)fi << 32 | (uint32_t)i;
 		n_z += __popc(m);
 	}
+	wide = __any_sync(0xffffffffu, wide);
 	__syncwarp();
 	int32_t n_u = 0, n_b = 0;
 	FlagRange<uint64_t> *stack = stack_all + (int64_t)prob * CHAIN_STACK;
+	int32_t *v = v_all + base;
+	uint64_t *u = u_all + base, *b = b_all + base;
 	flag_sort_warp(zs, n_z, [](const uint64_t &e) { return rec_key(e); }, stack, &ws, lane); // chain ends by score, reference tie order
-	if (lane == 0 && n > 0)
-		n_u = peel_and_compact<int8_t, true>(par, n_z, a_all + base, f, p_all + base, ts, v_all + base, zs, stack, u_all + base, b_all + base, &n_b);
-	n_b = __shfl_sync(0xffffffffu, n_b, 0);
-	if (resort && n_b > 1) { // map.c:191: the anchors kept by the pre-chain go back into plain sorted order
-		uint64_t *b = b_all + base;
-		for (int32_t i = lane; i < n_b; i += 32) zs[i] = b[i];
+	int32_t n_v = 0;
+	if (lane == 0 && n > 0) {
+		if (!wide) n_u = peel_chains<int8_t, true, uint16_t, int16_t>(par, n_z, fs, ps, ts, v, zs, stack, u, &n_v);
+		else n_u = peel_chains<int8_t, true, int32_t, int16_t>(par, n_z, fg, ps, ts, v, zs, stack, u, &n_v);
+	}
+	n_u = __shfl_sync(0xffffffffu, n_u, 0), n_v = __shfl_sync(0xffffffffu, n_v, 0);
+	__syncwarp();
+	if (resort) n_b = keep_filter_warp(n, n_v, v, ts, a_all + base, b, lane); // pre-chain: accepted anchors in sorted order
+	else {
+		if (n > 0) {
+			if (!wide) compact_chains(n_u, a_all + base, fs, v, zs, stack, u, b, &n_b, lane, 32, [] { __syncwarp(); });
+			else compact_chains(n_u, a_all + base, fg, v, zs, stack, u, b, &n_b, lane, 32, [] { __syncwarp(); });
+		}
 		__syncwarp();
-		flag_sort_warp(zs, n_b, [](const uint64_t &x) { return x; }, stack, &ws, lane);
-		for (int32_t i = lane; i < n_b; i += 32) b[i] = zs[i];
+		n_b = __shfl_sync(0xffffffffu, n_b, 0);
 	}
 	if (lane == 0) n_u_out[prob] = n_u, n_b_out[prob] = n_b;
 }
@@ -322,7 +359,7 @@ void chain_launch_bt_smem(cudaStream_t st, const int32_t *list, int n_list, int 
                           int32_t *f, const int32_t *p, int32_t *v, void *stack, uint64_t *u, uint64_t *b, int32_t *n_u, int32_t *n_b, int resort)
 {
 	if (n_list <= 0) return;
-	const int smem = cap * 9 + 16;
+	const int smem = cap * 13 + 16;
 	static int attr_max = 0;
 	if (smem > attr_max) { cudaFuncSetAttribute(chain_bt_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_max = smem; }
 	chain_bt_smem_kernel<<<n_list, 32, smem, st>>>(list, n_list, cap, a_off, cnt, a, par, f, p, v, (FlagRange<uint64_t>*)stack, u, b, n_u, n_b, resort);

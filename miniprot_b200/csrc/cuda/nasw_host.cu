@@ -159,10 +159,24 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		MPB_CUDA_OK(cudaEventRecord(ctx->ev_join[g.sid], ss));
 		MPB_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_join[g.sid], 0));
 	}
+	// results: scores first; the CIGARs are packed back to back on the device and only what was produced is copied
+	if (cig_tot) {
+		ctx->b_cigpack.reserve(sizeof(uint32_t) * (size_t)(cig_tot + 4));
+		ctx->b_cigoff.reserve(sizeof(int64_t) * (size_t)(n + 1));
+		nasw_launch_pack(st, dj, n, ctx->b_out.as<int4>(), ctx->b_cigar.as<uint32_t>(), ctx->b_cigoff.as<int64_t>(), ctx->b_cigpack.as<uint32_t>());
+		ctx->stats.kernel_launches += 2;
+	}
 	MPB_CUDA_OK(cudaMemcpyAsync(ctx->h_out.p, ctx->b_out.p, sizeof(int4) * n, cudaMemcpyDeviceToHost, st));
-	if (cig_tot) MPB_CUDA_OK(cudaMemcpyAsync(ctx->h_cigar.p, ctx->b_cigar.p, sizeof(uint32_t) * (size_t)cig_tot, cudaMemcpyDeviceToHost, st));
 	MPB_CUDA_OK(cudaStreamSynchronize(st));
 	MPB_CUDA_OK(cudaGetLastError());
+	const int4 *ho = ctx->h_out.as<int4>();
+	int64_t cig_used = 0;
+	for (int k = 0; k < n; ++k)
+		if (jobs[lo + k].cig_cap > 0) cig_used += ho[k].w;
+	if (cig_used) {
+		MPB_CUDA_OK(cudaMemcpyAsync(ctx->h_cigar.p, ctx->b_cigpack.p, sizeof(uint32_t) * (size_t)cig_used, cudaMemcpyDeviceToHost, st));
+		MPB_CUDA_OK(cudaStreamSynchronize(st));
+	}
 	static const bool trace = getenv("MPB_TRACE") != 0; // per-class durations of every wave on stderr (diagnostics only)
 	for (const Group &g : groups) { // sum of the classes' own durations (they overlap in time; the wave's wall time is what the step pays)
 		float ms = 0;
@@ -181,15 +195,15 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 			        g.b ? "tb " : "ext", g.c, "", g.count, j0.nl, j0.al, cells, ms, hist[0], hc[0], hist[1], hc[1], hist[2], hc[2], hist[3], hc[3], hist[4], hc[4]);
 		}
 	}
-	ctx->stats.d2h_bytes += sizeof(int4) * n + sizeof(uint32_t) * (size_t)cig_tot;
-	const int4 *ho = ctx->h_out.as<int4>();
+	ctx->stats.d2h_bytes += sizeof(int4) * n + sizeof(uint32_t) * (size_t)cig_used;
 	const uint32_t *hc = ctx->h_cigar.as<uint32_t>();
+	int64_t off = 0;
 	for (int k = 0; k < n; ++k) {
 		const DpDev &j = jobs[lo + k];
 		out.score[lo + k] = ho[k].x, out.nt_len[lo + k] = ho[k].y, out.aa_len[lo + k] = ho[k].z;
 		if (j.cig_cap > 0 && ho[k].w > 0) {
-			const uint32_t *c = hc + j.cig_off + j.cig_cap - ho[k].w;
-			out.cig.insert(out.cig.end(), c, c + ho[k].w);
+			out.cig.insert(out.cig.end(), hc + off, hc + off + ho[k].w);
+			off += ho[k].w;
 		}
 		out.cig_off[lo + k + 1] = (int64_t)out.cig.size();
 	}

@@ -594,6 +594,46 @@ void nasw_launch_v3(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, cons
 	}
 }
 
+// ------------------------------------------------------------------ CIGAR packing
+// exclusive prefix sum of the CIGAR lengths (out[k].w, zero for extension problems) by one block; offs[n] = total
+__global__ void __launch_bounds__(1024) nasw_cigoff_kernel(const DpDev *jobs, int n, const int4 *out, int64_t *offs)
+{
+	__shared__ int64_t part[1024];
+	const int t = threadIdx.x, per = (n + 1023) / 1024, k0 = t * per, k1 = min(n, k0 + per);
+	int64_t sum = 0;
+	for (int k = k0; k < k1; ++k) sum += jobs[k].cig_cap > 0 ? out[k].w : 0;
+	part[t] = sum;
+	__syncthreads();
+	for (int d = 1; d < 1024; d <<= 1) { // Hillis-Steele inclusive scan of the per-thread sums
+		const int64_t v = t >= d ? part[t - d] : 0;
+		__syncthreads();
+		part[t] += v;
+		__syncthreads();
+	}
+	int64_t run = part[t] - sum;
+	for (int k = k0; k < k1; ++k) offs[k] = run, run += jobs[k].cig_cap > 0 ? out[k].w : 0;
+	if (t == 1023) offs[n] = part[1023];
+}
+
+__global__ void __launch_bounds__(256) nasw_cigpack_kernel(const DpDev *jobs, int n, const int4 *out, const uint32_t *cigar, const int64_t *offs, uint32_t *packed)
+{
+	const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+	if (k >= n) return;
+	const DpDev j = jobs[k];
+	if (j.cig_cap <= 0) return;
+	const int nc = out[k].w;
+	const uint32_t *src = cigar + j.cig_off + j.cig_cap - nc;
+	uint32_t *dst = packed + offs[k];
+	for (int i = lane; i < nc; i += 32) dst[i] = src[i];
+}
+
+void nasw_launch_pack(cudaStream_t st, const DpDev *jobs, int n, const int4 *out, const uint32_t *cigar, int64_t *offs, uint32_t *packed)
+{
+	if (n <= 0) return;
+	nasw_cigoff_kernel<<<1, 1024, 0, st>>>(jobs, n, out, offs);
+	nasw_cigpack_kernel<<<(n + 7) / 8, 256, 0, st>>>(jobs, n, out, cigar, offs, packed);
+}
+
 void nasw_launch_bt(cudaStream_t st, const DpDev *jobs, const int *order, int n, const uint16_t *tb, uint32_t *cigar, int4 *out)
 {
 	if (n > 0) nasw_bt_kernel<<<(n + NASW_WARPS - 1) / NASW_WARPS, NASW_WARPS * 32, 0, st>>>(jobs, order, n, tb, cigar, out);

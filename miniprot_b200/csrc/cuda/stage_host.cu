@@ -80,27 +80,31 @@ static void chain_problems(mpb_ctx_s *ctx, int n_prob, const std::vector<int64_t
 	layout(cv);
 	// Size classes (from the offsets: an upper bound for a main chain that follows a pre-chain), run concurrently on side
 	// streams:  0: <= 2048 anchors   fill + backtrack fused in one warp with ALL state in shared memory (32 KB, 7 warps per SM)
-	//           1-3: <= 5120 / 8192 / 16384   global-memory fill (every problem its own warp, ~1000 in flight) followed by
-	//                the shared-memory backtrack (13 B per anchor)
-	//           4: larger   global-memory fill + single-thread global backtrack
-	static const int caps[4] = { 2048, 5120, 8192, 16384 };
-	std::vector<int32_t> lists[5], flat, sizes((size_t)n_prob);
-	size_t lfirst[5];
+	//           1..NC-1: up to 16384 anchors in steps of ~1 K   global-memory fill (every problem its own warp, ~1000 in
+	//                flight) followed by the shared-memory backtrack (13 B per anchor of the class capacity: the finer the
+	//                classes, the more problems fit an SM's shared memory together)
+	//           NC: larger   global-memory fill + single-thread global backtrack
+	static const int NC = 10;
+	static const int caps[NC] = { 2048, 3072, 4096, 5120, 6144, 7168, 8192, 10240, 12288, 16384 };
+	std::vector<int32_t> lists[NC + 1], flat, sizes((size_t)n_prob);
+	size_t lfirst[NC + 1];
 	for (int i = 0; i < n_prob; ++i) sizes[(size_t)i] = (int32_t)(h_off[(size_t)i + 1] - h_off[(size_t)i]);
 	auto classify = [&]() { // sizes[] -> per-class problem lists on the device
 		flat.clear();
-		for (int c = 0; c < 5; ++c) lists[c].clear();
+		for (int c = 0; c <= NC; ++c) lists[c].clear();
 		for (int i = 0; i < n_prob; ++i) {
 			const int32_t n = sizes[(size_t)i];
-			lists[n <= caps[0] ? 0 : n <= caps[1] ? 1 : n <= caps[2] ? 2 : n <= caps[3] ? 3 : 4].push_back(i);
+			int c = 0;
+			while (c < NC && n > caps[c]) ++c;
+			lists[c].push_back(i);
 		}
-		for (int c = 0; c < 5; ++c) lfirst[c] = flat.size(), flat.insert(flat.end(), lists[c].begin(), lists[c].end());
+		for (int c = 0; c <= NC; ++c) lfirst[c] = flat.size(), flat.insert(flat.end(), lists[c].begin(), lists[c].end());
 		MPB_CUDA_OK(cudaMemcpyAsync(d_list, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice, st));
 	};
 	classify();
 	auto chain_once = [&](const int32_t *cnt, const uint64_t *in, const chn::Par &par, uint64_t *uo, uint64_t *bo, int32_t *nuo, int32_t *nbo, int resort) {
 		MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
-		for (int c = 0; c < 5; ++c) {
+		for (int c = NC; c >= 0; --c) { // largest problems first
 			if (lists[c].empty()) continue;
 			cudaStream_t ss = ctx->side[c];
 			const int32_t *lst = d_list + lfirst[c];
@@ -111,7 +115,7 @@ static void chain_problems(mpb_ctx_s *ctx, int n_prob, const std::vector<int64_t
 				ctx->stats.kernel_launches += 1;
 			} else {
 				chain_launch_fill(ss, lst, d_off, cnt, in, nl, par, f, p, t);
-				if (c < 4) chain_launch_bt_smem(ss, lst, nl, caps[c], d_off, cnt, in, par, f, p, v, stack, uo, bo, nuo, nbo, resort);
+				if (c < NC) chain_launch_bt_smem(ss, lst, nl, caps[c], d_off, cnt, in, par, f, p, v, stack, uo, bo, nuo, nbo, resort);
 				else chain_launch_bt(ss, lst, nl, d_off, cnt, in, par, f, p, t, v, z, stack, uo, bo, nuo, nbo, resort);
 				ctx->stats.kernel_launches += 2;
 			}
