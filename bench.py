@@ -266,12 +266,23 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    # dominant kernel by time: the score-only nasw extension kernel.  Its algorithmic HBM traffic is ~0, so the
-    # HBM roofline is reported for the traceback kernel (2 B/cell written once), and the integer rate for both.
+    # Dominant kernel by time: the score-only nasw extension kernel (nasw_v3_kernel<NW,false>).  Its algorithmic HBM traffic is
+    # ~0, so the HBM roofline is reported for the traceback kernels (nasw_v3_kernel<NW,true>: 2 B per DP cell written
+    # once), and the integer rate for both.  achieved = algorithmic bytes of one step / sum of the traceback launches' CUDA-event
+    # durations of that step (events on the launching side streams; each bracket also holds the CIGAR backtrack kernel that
+    # follows); traffic = DRAM bytes of the same launches from the committed ncu capture, both divided by the launches per step.
     tb_gbs = (st.dp_cells_tb * 2 / 1e9) / (st.ms_dp_tb / 1e3) if st.ms_dp_tb > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "nasw_tb_kernel", "achieved": tb_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": tb_gbs / hbm_peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-                "note": "nasw is integer-issue bound, not HBM bound; see int_rate and DESIGN.md"}
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_v6.json")))
+        if args.workload == "C2":
+            traffic = tr["tb_traffic_bytes_per_step"] / tr["tb_launches_per_step"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "nasw_v3_kernel<NW,true> (traceback; 8 launches per step)", "achieved": tb_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": tb_gbs / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": st.dp_cells_tb * 2 / args.steps / 8,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                "note": "nasw is integer-issue / latency bound, not HBM bound (SURVEY 8d tension): see int_rate, DESIGN.md 4 and profiles/README.md"}
     int_rate = {
         "ext_gcell_per_s": st.dp_cells_ext / st.ms_dp_ext / 1e6 if st.ms_dp_ext > 0 else None,
         "tb_gcell_per_s": st.dp_cells_tb / st.ms_dp_tb / 1e6 if st.ms_dp_tb > 0 else None,
