@@ -115,6 +115,7 @@ mpb_ctx_t *mpb_ctx_create(int device)
 	MPB_CUDA_OK(cudaEventCreate(&c->ev0));
 	MPB_CUDA_OK(cudaEventCreate(&c->ev1));
 	MPB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+	MPB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming));
 	int prio_lo = 0, prio_hi = 0;
 	MPB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
 	for (int i = 0; i < mpb_ctx_s::N_SIDE; ++i) {
@@ -151,7 +152,7 @@ void mpb_ctx_destroy(mpb_ctx_t *c)
 	for (DevBuf &b : c->b_c) b.release();
 	c->h_out.release(), c->h_cigar.release();
 	for (PinBuf &b : c->h_c) b.release();
-	cudaEventDestroy(c->ev0), cudaEventDestroy(c->ev1), cudaEventDestroy(c->ev_fork);
+	cudaEventDestroy(c->ev0), cudaEventDestroy(c->ev1), cudaEventDestroy(c->ev_fork), cudaEventDestroy(c->ev_fork2);
 	for (int i = 0; i < mpb_ctx_s::N_SIDE; ++i) cudaStreamDestroy(c->side[i]), cudaEventDestroy(c->ev_join[i]), cudaEventDestroy(c->ev_k0[i]), cudaEventDestroy(c->ev_k1[i]);
 	cudaStreamDestroy(c->stream);
 	delete c->stages;

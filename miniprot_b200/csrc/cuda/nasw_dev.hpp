@@ -54,6 +54,8 @@ void nasw_launch_v3(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, cons
 // packs the CIGARs of a wave (each written at the end of its own worst-case slot) back to back in job order, so that the
 // device-to-host copy moves what was produced instead of the slots; offs[] (n + 1 entries) is scratch
 void nasw_launch_pack(cudaStream_t st, const DpDev *jobs, int n, const int4 *out, const uint32_t *cigar, int64_t *offs, uint32_t *packed);
+// keeps `st` busy for about `us` microseconds (a head start for whatever does not wait behind it)
+void nasw_launch_spacer(cudaStream_t st, int us);
 void nasw_launch_bt(cudaStream_t st, const DpDev *jobs, const int *order, int n, const uint16_t *tb, uint32_t *cigar, int4 *out);
 
 } // namespace cuda

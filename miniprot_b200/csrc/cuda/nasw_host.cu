@@ -63,6 +63,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	const int n = (int)(hi - lo);
 	if (n == 0) return;
 	cudaStream_t st = ctx->stream;
+	const double t_in = mp_realtime();
 	int64_t rw_tot = 0, tb_tot = 0, cig_tot = 0, carry_tot = 0;
 	std::vector<PrepChunk> chunks;
 	std::vector<int> order[2][9]; // [is_tb][class]: 0..3 block-wide wavefront with 1/2/4/8 warps; 4..7 column passes C = 1/2/4/8; 8 multi-pass
@@ -133,11 +134,18 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		for (int c = 8; c >= 0; --c)
 			if (count[b][c]) groups.push_back(Group{ b * 9 + c, b, c, first[b][c], count[b][c] });
 	MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
+	// the widest extension class needs EMPTY SMs (one block fills an SM's shared memory): it forks at once, everybody else
+	// a few microseconds later, behind a spacer on the main stream
+	const bool head_start = big_wave && wsm_env < 0 && count[0][3] > 0 && count[0][3] <= 148;
+	if (head_start) {
+		nasw_launch_spacer(st, 40);
+		MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork2, st));
+	}
 	for (const Group &g : groups) {
 		cudaStream_t ss = ctx->side[g.sid];
 		const int b = g.b, c = g.c, cnt = (int)g.count;
 		const int *ord = dord + g.first;
-		MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
+		MPB_CUDA_OK(cudaStreamWaitEvent(ss, (head_start && !(b == 0 && c == 3)) ? ctx->ev_fork2 : ctx->ev_fork, 0));
 		MPB_CUDA_OK(cudaEventRecord(ctx->ev_k0[g.sid], ss));
 		if (c < 4) {
 			nasw_launch_v3(ss, Cs[c], b == 1, dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>(),
@@ -166,8 +174,10 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		nasw_launch_pack(st, dj, n, ctx->b_out.as<int4>(), ctx->b_cigar.as<uint32_t>(), ctx->b_cigoff.as<int64_t>(), ctx->b_cigpack.as<uint32_t>());
 		ctx->stats.kernel_launches += 2;
 	}
+	const double t_launched = mp_realtime();
 	MPB_CUDA_OK(cudaMemcpyAsync(ctx->h_out.p, ctx->b_out.p, sizeof(int4) * n, cudaMemcpyDeviceToHost, st));
 	MPB_CUDA_OK(cudaStreamSynchronize(st));
+	const double t_synced = mp_realtime();
 	MPB_CUDA_OK(cudaGetLastError());
 	const int4 *ho = ctx->h_out.as<int4>();
 	int64_t cig_used = 0;
@@ -207,6 +217,9 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		}
 		out.cig_off[lo + k + 1] = (int64_t)out.cig.size();
 	}
+	if (trace)
+		fprintf(stderr, "[mpb-trace] nasw wave: %d problems, host prepare+launch %.2f ms, wait %.2f ms, results %.2f ms\n", n, (t_launched - t_in) * 1e3,
+		        (t_synced - t_launched) * 1e3, (mp_realtime() - t_synced) * 1e3);
 }
 
 void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_opt_t *base, std::vector<DpDev> &jobs, DpSet &out)

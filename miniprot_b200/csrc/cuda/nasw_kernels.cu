@@ -27,6 +27,13 @@ namespace cuda {
 
 using namespace nsw;
 
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
 // nucleotide code of row k of a job: nibble (g_start + dir*k) of the packed genome, complemented on the - strand
 __device__ __forceinline__ int job_code(const uint8_t *packed, const DpDev &j, int k)
 {
@@ -633,6 +640,14 @@ void nasw_launch_pack(cudaStream_t st, const DpDev *jobs, int n, const int4 *out
 	nasw_cigoff_kernel<<<1, 1024, 0, st>>>(jobs, n, out, offs);
 	nasw_cigpack_kernel<<<(n + 7) / 8, 256, 0, st>>>(jobs, n, out, cigar, offs, packed);
 }
+
+__global__ void nasw_spacer_kernel(long long ns)
+{
+	const long long t0 = (long long)globaltimer_ns();
+	while ((long long)globaltimer_ns() - t0 < ns) __nanosleep(1000);
+}
+
+void nasw_launch_spacer(cudaStream_t st, int us) { nasw_spacer_kernel<<<1, 1, 0, st>>>((long long)us * 1000); }
 
 void nasw_launch_bt(cudaStream_t st, const DpDev *jobs, const int *order, int n, const uint16_t *tb, uint32_t *cigar, int4 *out)
 {

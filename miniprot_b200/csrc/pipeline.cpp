@@ -131,11 +131,21 @@ void map_batch(Stages *st, const mp_idx_t *mi, const mp_mapopt_t *opt, const Bat
 			}
 		}
 		lap(3);
+		static const bool trace = getenv("MPB_TRACE") != 0;
+		double tt[6] = { mp_realtime() };
 		st->nasw(mi, &nso, b, w1, o1);
+		tt[1] = mp_realtime();
 		for (RegionPlan &p : plans) p.after_wave1(opt, o1, w1r);
+		tt[2] = mp_realtime();
 		st->nasw(mi, &nso, b, w1r, o1r);
+		tt[3] = mp_realtime();
 		for (RegionPlan &p : plans) p.after_retry(mi, opt, b.seq[p.qid], o1r, w2);
+		tt[4] = mp_realtime();
 		st->nasw(mi, &nso, b, w2, o2);
+		tt[5] = mp_realtime();
+		if (trace)
+			fprintf(stderr, "[mpb-trace] S3: wave1 %.2f ms, host %.2f, retries %.2f, host %.2f, wave2 %.2f\n", (tt[1] - tt[0]) * 1e3, (tt[2] - tt[1]) * 1e3, (tt[3] - tt[2]) * 1e3,
+			        (tt[4] - tt[3]) * 1e3, (tt[5] - tt[4]) * 1e3);
 		lap(4);
 		for (RegionPlan &p : plans) p.finish(mi, opt, b.seq[p.qid], o1, o2);
 		// ---- H3 (map.c:228-236)
