@@ -35,6 +35,13 @@ struct RegionPlan {
 	// returns false when the region has no pinned anchor and is dropped
 	bool plan(const mp_idx_t *mi, const mp_mapopt_t *opt, int32_t qid, int32_t qlen, const char *aa, mp_reg1_t *r, int32_t extl0, int32_t extr0,
 	          std::vector<DpJob> &jobs);
+	// wave-1 job indices were taken in a list that is appended to the wave's list at position d
+	void rebase_wave1(int32_t d)
+	{
+		if (jobL >= 0) jobL += d;
+		if (jobR >= 0) jobR += d;
+		for (Fill &f : fills) if (f.job >= 0) f.job += d;
+	}
 	void after_wave1(const mp_mapopt_t *opt, const DpSet &w1, std::vector<DpJob> &retry);
 	void after_retry(const mp_idx_t *mi, const mp_mapopt_t *opt, const char *aa, const DpSet &w1r, std::vector<DpJob> &jobs2);
 	void finish(const mp_idx_t *mi, const mp_mapopt_t *opt, const char *aa, const DpSet &w1, const DpSet &w2);

@@ -42,8 +42,14 @@ struct CudaStages : Stages {
 		}
 	}
 	// residues of the whole batch, concatenated, resident for the duration of the call
+	const Batch *cur_batch = 0; // residues of this batch are already resident (between batch_begin and batch_end)
+	std::vector<int32_t> cur_off;
 	const char *upload_residues(const Batch &b, std::vector<int32_t> &off)
 	{
+		if (&b == cur_batch) {
+			off = cur_off;
+			return ctx->b_aa.as<char>();
+		}
 		off.assign((size_t)b.n + 1, 0);
 		for (int32_t i = 0; i < b.n; ++i) off[(size_t)i + 1] = off[(size_t)i] + b.len[i];
 		const size_t tot = (size_t)off[(size_t)b.n];
@@ -56,6 +62,13 @@ struct CudaStages : Stages {
 		ctx->stats.h2d_bytes += (int64_t)tot;
 		return ctx->b_aa.as<char>();
 	}
+	void batch_begin(const Batch &b) override
+	{
+		cur_batch = 0;
+		upload_residues(b, cur_off);
+		cur_batch = &b;
+	}
+	void batch_end() override { cur_batch = 0; }
 
 	void note_wall(int phase, double ms) override { if (phase >= 0 && phase < 6) ctx->stats.ms_wall[phase] += ms; }
 	void seed_chain(const mp_idx_t *mi, const mp_mapopt_t *opt, const Batch &b, ChainSet &out) override

@@ -32,11 +32,10 @@ static inline int pick_C(int al)
 // per lane amortise the per-step overhead).  A mini-batch of the benchmark's size is latency bound (its waves last as long
 // as their longest problem), and there the block-wide kernel wins on every class; MPB_NASW_KERNEL=cols selects the
 // throughput-oriented family.
+static int g_forced_family = 0; // MPB_NASW_KERNEL=cols|v3 (A/B switch for tests and measurements), read once per nasw_run
 static inline bool use_v3(int al, int nl)
 {
-	const char *e = getenv("MPB_NASW_KERNEL"); // A/B switch for tests and measurements: "cols" or "v3" forces one family
-	const int forced = !e ? 0 : strcmp(e, "cols") == 0 ? 1 : strcmp(e, "v3") == 0 ? 2 : 0;
-	if (forced) return forced == 2 && (al + 7) / 8 * 8 <= 256;
+	if (g_forced_family) return g_forced_family == 2 && (al + 7) / 8 * 8 <= 256;
 	(void)nl;
 	return (al + 7) / 8 * 8 <= 256; // default: latency first (a mini-batch wave is bounded by its longest problems)
 }
@@ -228,6 +227,10 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_
 	out.score.assign(n, 0), out.nt_len.assign(n, 0), out.aa_len.assign(n, 0);
 	out.cig.clear(), out.cig_off.assign(n + 1, 0);
 	if (n == 0) return;
+	{
+		const char *e = getenv("MPB_NASW_KERNEL");
+		g_forced_family = !e ? 0 : strcmp(e, "cols") == 0 ? 1 : strcmp(e, "v3") == 0 ? 2 : 0;
+	}
 	NaswConst cst;
 	fill_const(base, cst);
 	size_t lo = 0;

@@ -94,6 +94,9 @@ struct Stages {
 	virtual void refine(const mp_idx_t *mi, const mp_mapopt_t *opt, const Batch &b, const std::vector<RefineJob> &jobs, RefineSet &out) = 0;
 	// nasw DP over genome slices
 	virtual void nasw(const mp_idx_t *mi, const ns_opt_t *base, const Batch &b, const std::vector<DpJob> &jobs, DpSet &out) = 0;
+	// brackets of one map_batch() call (a backend may keep per-batch state resident between the stages); optional
+	virtual void batch_begin(const Batch & /*b*/) {}
+	virtual void batch_end() {}
 	// wall-clock accounting of the dispatcher's phases (0 S1, 1 H1, 2 S2, 3 H2, 4 S3 waves, 5 H3); optional
 	virtual void note_wall(int /*phase*/, double /*ms*/) {}
 };

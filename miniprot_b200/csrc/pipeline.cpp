@@ -18,6 +18,7 @@
 #include "internal.hpp"
 #include "align.hpp"
 #include "fastx.hpp"
+#include "parfor.hpp"
 
 namespace mpb {
 
@@ -44,35 +45,44 @@ void map_batch(Stages *st, const mp_idx_t *mi, const mp_mapopt_t *opt, const Bat
 	};
 
 	// ---- S1
+	st->batch_begin(b);
 	ChainSet cs;
 	st->seed_chain(mi, opt, b, cs);
 	lap(0);
 
 	// ---- H1 + S2 work list
+	// (the host phases are independent per protein: contiguous ranges of proteins on the worker pool, per-range results
+	// concatenated in order)
 	std::vector<RefineJob> rjobs;
 	std::vector<int32_t> rjob_first((size_t)n + 1, 0);
-	for (int32_t q = 0; q < n; ++q) {
-		QueryState &Q = qs[(size_t)q];
-		const int32_t n_u = (int32_t)(cs.u_off[(size_t)q + 1] - cs.u_off[(size_t)q]);
-		const uint64_t *u = cs.u.data() + cs.u_off[(size_t)q], *a = cs.a.data() + cs.a_off[(size_t)q];
-		Q.reg = regs_from_chains(mi, n_u, u, a, &Q.n_reg);
-		regs_sort(&Q.n_reg, Q.reg);
-		regs_set_parent(opt->mask_level, opt->mask_len, Q.n_reg, Q.reg, kmer, 0);
-		regs_select_sub(opt->pri_ratio * opt->pri_ratio, kmer * 2, opt->best_n, &Q.n_reg, Q.reg);
-		regs_max_ext(0, Q.n_reg, Q.reg, a, 100, opt->max_ext, Q.ext);
-		rjob_first[(size_t)q] = (int32_t)rjobs.size();
-		for (int32_t i = 0; i < Q.n_reg; ++i) { // window of map.c:41-42
-			const mp_reg1_t *r = &Q.reg[i];
-			const int64_t ctg_len = mi->nt->ctg[r->vid >> 1].len;
-			const int32_t extl = (int32_t)(Q.ext[(size_t)i] >> 32), extr = (int32_t)Q.ext[(size_t)i];
-			RefineJob j;
-			j.qid = q, j.vid = r->vid;
-			j.as = r->vs > extl ? r->vs - extl : 0;
-			j.ae = r->ve + extr < ctg_len ? r->ve + extr : ctg_len;
-			rjobs.push_back(j);
-		}
+	{
+		std::vector<std::vector<RefineJob>> part(64);
+		const int n_part = par_ranges(n, 64, [&](int lo, int hi, int c) {
+			std::vector<RefineJob> &out = part[(size_t)c];
+			for (int32_t q = lo; q < hi; ++q) {
+				QueryState &Q = qs[(size_t)q];
+				const int32_t n_u = (int32_t)(cs.u_off[(size_t)q + 1] - cs.u_off[(size_t)q]);
+				const uint64_t *u = cs.u.data() + cs.u_off[(size_t)q], *a = cs.a.data() + cs.a_off[(size_t)q];
+				Q.reg = regs_from_chains(mi, n_u, u, a, &Q.n_reg);
+				regs_sort(&Q.n_reg, Q.reg);
+				regs_set_parent(opt->mask_level, opt->mask_len, Q.n_reg, Q.reg, kmer, 0);
+				regs_select_sub(opt->pri_ratio * opt->pri_ratio, kmer * 2, opt->best_n, &Q.n_reg, Q.reg);
+				regs_max_ext(0, Q.n_reg, Q.reg, a, 100, opt->max_ext, Q.ext);
+				for (int32_t i = 0; i < Q.n_reg; ++i) { // window of map.c:41-42
+					const mp_reg1_t *r = &Q.reg[i];
+					const int64_t ctg_len = mi->nt->ctg[r->vid >> 1].len;
+					const int32_t extl = (int32_t)(Q.ext[(size_t)i] >> 32), extr = (int32_t)Q.ext[(size_t)i];
+					RefineJob j;
+					j.qid = q, j.vid = r->vid;
+					j.as = r->vs > extl ? r->vs - extl : 0;
+					j.ae = r->ve + extr < ctg_len ? r->ve + extr : ctg_len;
+					out.push_back(j);
+				}
+			}
+		});
+		for (int c = 0; c < n_part; ++c) rjobs.insert(rjobs.end(), part[(size_t)c].begin(), part[(size_t)c].end());
+		for (int32_t q = 0; q < n; ++q) rjob_first[(size_t)q + 1] = rjob_first[(size_t)q] + qs[(size_t)q].n_reg;
 	}
-	rjob_first[(size_t)n] = (int32_t)rjobs.size();
 	cs = ChainSet(); // first-round anchors are not needed any more
 	lap(1);
 
@@ -83,7 +93,8 @@ void map_batch(Stages *st, const mp_idx_t *mi, const mp_mapopt_t *opt, const Bat
 
 	// ---- H2: adopt refined chains (map.c:83-109), re-rank (map.c:217-221)
 	const int32_t k2 = opt->kmer2;
-	for (int32_t q = 0; q < n; ++q) {
+	par_ranges(n, 64, [&](int q_lo, int q_hi, int) {
+	for (int32_t q = q_lo; q < q_hi; ++q) {
 		QueryState &Q = qs[(size_t)q];
 		int32_t kept = 0;
 		std::vector<int64_t> offs;
@@ -112,6 +123,7 @@ void map_batch(Stages *st, const mp_idx_t *mi, const mp_mapopt_t *opt, const Bat
 		regs_set_parent(opt->mask_level, opt->mask_len, Q.n_reg, Q.reg, kmer, 0);
 		regs_select_sub(opt->pri_ratio * opt->pri_ratio, kmer * 2, opt->best_n, &Q.n_reg, Q.reg);
 	}
+	});
 	rs = RefineSet();
 
 	// ---- S3: alignment in three waves
@@ -121,13 +133,27 @@ void map_batch(Stages *st, const mp_idx_t *mi, const mp_mapopt_t *opt, const Bat
 		std::vector<RegionPlan> plans;
 		std::vector<DpJob> w1, w1r, w2;
 		DpSet o1, o1r, o2;
-		for (int32_t q = 0; q < n; ++q) {
-			QueryState &Q = qs[(size_t)q];
-			regs_max_ext(mi->nt, Q.n_reg, Q.reg, Q.anchors.data(), 100, opt->max_intron / 2, Q.ext);
-			for (int32_t i = 0; i < Q.n_reg; ++i) {
-				RegionPlan p;
-				if (p.plan(mi, opt, q, b.len[q], b.seq[q], &Q.reg[i], (int32_t)(Q.ext[(size_t)i] >> 32), (int32_t)Q.ext[(size_t)i], w1))
+		{
+			std::vector<std::vector<RegionPlan>> pplan(64);
+			std::vector<std::vector<DpJob>> pjobs(64);
+			const int n_part = par_ranges(n, 64, [&](int q_lo, int q_hi, int c) {
+				for (int32_t q = q_lo; q < q_hi; ++q) {
+					QueryState &Q = qs[(size_t)q];
+					regs_max_ext(mi->nt, Q.n_reg, Q.reg, Q.anchors.data(), 100, opt->max_intron / 2, Q.ext);
+					for (int32_t i = 0; i < Q.n_reg; ++i) {
+						RegionPlan p;
+						if (p.plan(mi, opt, q, b.len[q], b.seq[q], &Q.reg[i], (int32_t)(Q.ext[(size_t)i] >> 32), (int32_t)Q.ext[(size_t)i], pjobs[(size_t)c]))
+							pplan[(size_t)c].push_back(std::move(p));
+					}
+				}
+			});
+			for (int c = 0; c < n_part; ++c) {
+				const int32_t base = (int32_t)w1.size();
+				w1.insert(w1.end(), pjobs[(size_t)c].begin(), pjobs[(size_t)c].end());
+				for (RegionPlan &p : pplan[(size_t)c]) {
+					p.rebase_wave1(base);
 					plans.push_back(std::move(p));
+				}
 			}
 		}
 		lap(3);
@@ -147,24 +173,29 @@ void map_batch(Stages *st, const mp_idx_t *mi, const mp_mapopt_t *opt, const Bat
 			fprintf(stderr, "[mpb-trace] S3: wave1 %.2f ms, host %.2f, retries %.2f, host %.2f, wave2 %.2f\n", (tt[1] - tt[0]) * 1e3, (tt[2] - tt[1]) * 1e3, (tt[3] - tt[2]) * 1e3,
 			        (tt[4] - tt[3]) * 1e3, (tt[5] - tt[4]) * 1e3);
 		lap(4);
-		for (RegionPlan &p : plans) p.finish(mi, opt, b.seq[p.qid], o1, o2);
+		par_ranges((int)plans.size(), 256, [&](int lo, int hi, int) {
+			for (int k = lo; k < hi; ++k) plans[(size_t)k].finish(mi, opt, b.seq[plans[(size_t)k].qid], o1, o2);
+		});
 		// ---- H3 (map.c:228-236)
-		for (int32_t q = 0; q < n; ++q) {
-			QueryState &Q = qs[(size_t)q];
-			int32_t k = 0;
-			for (int32_t i = 0; i < Q.n_reg; ++i) if (Q.reg[i].p) Q.reg[k++] = Q.reg[i];
-			Q.n_reg = k;
-			regs_sort(&Q.n_reg, Q.reg);
-			regs_select_multi_exon(Q.n_reg, Q.reg, opt->io);
-			regs_set_parent(opt->mask_level, opt->mask_len, Q.n_reg, Q.reg, kmer, 0);
-			regs_select_sub(opt->pri_ratio, kmer * 2, opt->best_n, &Q.n_reg, Q.reg);
-		}
+		par_ranges(n, 64, [&](int q_lo, int q_hi, int) {
+			for (int32_t q = q_lo; q < q_hi; ++q) {
+				QueryState &Q = qs[(size_t)q];
+				int32_t k = 0;
+				for (int32_t i = 0; i < Q.n_reg; ++i) if (Q.reg[i].p) Q.reg[k++] = Q.reg[i];
+				Q.n_reg = k;
+				regs_sort(&Q.n_reg, Q.reg);
+				regs_select_multi_exon(Q.n_reg, Q.reg, opt->io);
+				regs_set_parent(opt->mask_level, opt->mask_len, Q.n_reg, Q.reg, kmer, 0);
+				regs_select_sub(opt->pri_ratio, kmer * 2, opt->best_n, &Q.n_reg, Q.reg);
+			}
+		});
 	}
 	for (int32_t q = 0; q < n; ++q) {
 		QueryState &Q = qs[(size_t)q];
 		for (int32_t i = 0; i < Q.n_reg; ++i) Q.reg[i].a = 0; // the anchor store dies with this call
 		n_reg_out[q] = Q.n_reg, reg_out[q] = Q.reg;
 	}
+	st->batch_end();
 	lap(5);
 }
 
