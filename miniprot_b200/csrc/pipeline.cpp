@@ -200,22 +200,29 @@ void map_batch(Stages *st, const mp_idx_t *mi, const mp_mapopt_t *opt, const Bat
 }
 
 // map.c:293-326: per protein, hits in rank order subject to --outn / --outs / --outc; unmapped line with -u
-static void write_batch(FILE *out, Str &buf, const mp_idx_t *mi, const mp_mapopt_t *opt, const Batch &b, const int32_t *n_reg, mp_reg1_t *const *reg)
+// formatting is independent per protein: ranges of proteins on the worker pool, each into its own buffer, written in order
+static void write_batch(FILE *out, const mp_idx_t *mi, const mp_mapopt_t *opt, const Batch &b, const int32_t *n_reg, mp_reg1_t *const *reg)
 {
-	for (int32_t q = 0; q < b.n; ++q) {
-		int32_t best = -1, n_out = 0;
-		buf.l = 0;
-		if (n_reg[q] > 0) best = reg[q][0].p ? reg[q][0].p->dp_max : reg[q][0].chn_sc;
-		for (int32_t j = 0; j < n_reg[q] && j < opt->out_n; ++j) {
-			const mp_reg1_t *r = &reg[q][j];
-			const int32_t sc = r->p ? r->p->dp_max : r->chn_sc;
-			if (sc <= 0 || sc < (double)best * opt->out_sim) continue;
-			if (r->qe - r->qs < (double)b.len[q] * opt->out_cov) continue;
-			if (!(opt->flag & MP_F_NO_PAF)) format_hit(buf, mi, opt, b.name[q], b.len[q], b.seq[q], r);
-			++n_out;
+	std::vector<Str> part(64);
+	const int n_part = par_ranges(b.n, 64, [&](int q_lo, int q_hi, int c) {
+		Str &buf = part[(size_t)c];
+		for (int32_t q = q_lo; q < q_hi; ++q) {
+			int32_t best = -1, n_out = 0;
+			if (n_reg[q] > 0) best = reg[q][0].p ? reg[q][0].p->dp_max : reg[q][0].chn_sc;
+			for (int32_t j = 0; j < n_reg[q] && j < opt->out_n; ++j) {
+				const mp_reg1_t *r = &reg[q][j];
+				const int32_t sc = r->p ? r->p->dp_max : r->chn_sc;
+				if (sc <= 0 || sc < (double)best * opt->out_sim) continue;
+				if (r->qe - r->qs < (double)b.len[q] * opt->out_cov) continue;
+				if (!(opt->flag & MP_F_NO_PAF)) format_hit(buf, mi, opt, b.name[q], b.len[q], b.seq[q], r);
+				++n_out;
+			}
+			if (n_out == 0 && (opt->flag & MP_F_SHOW_UNMAP)) format_hit(buf, mi, opt, b.name[q], b.len[q], b.seq[q], 0);
 		}
-		if (n_out == 0 && (opt->flag & MP_F_SHOW_UNMAP)) format_hit(buf, mi, opt, b.name[q], b.len[q], b.seq[q], 0);
-		if (buf.l) fwrite(buf.s, 1, (size_t)buf.l, out);
+	});
+	for (int c = 0; c < n_part; ++c) {
+		if (part[(size_t)c].l) fwrite(part[(size_t)c].s, 1, (size_t)part[(size_t)c].l, out);
+		free(part[(size_t)c].s);
 	}
 }
 
@@ -227,7 +234,6 @@ int32_t map_file(Stages *st, const mp_idx_t *mi, const char *fn, const mp_mapopt
 		fprintf(stderr, "[WARNING] GFF/GTF/--aln/--trans output is not produced by miniprot_b200 in this round; writing PAF only\n");
 	std::vector<std::string> names, seqs;
 	std::string name, seq;
-	Str buf;
 	bool more = true;
 	int64_t n_done = 0;
 	while (more) {
@@ -246,7 +252,7 @@ int32_t map_file(Stages *st, const mp_idx_t *mi, const char *fn, const mp_mapopt
 		Batch b;
 		b.n = n, b.seq = sp.data(), b.len = len.data(), b.name = np.data();
 		map_batch(st, mi, opt, b, n_reg.data(), reg.data());
-		write_batch(out, buf, mi, opt, b, n_reg.data(), reg.data());
+		write_batch(out, mi, opt, b, n_reg.data(), reg.data());
 		for (int32_t i = 0; i < n; ++i) {
 			for (int32_t j = 0; j < n_reg[(size_t)i]; ++j) free(reg[(size_t)i][j].feat), free(reg[(size_t)i][j].p);
 			free(reg[(size_t)i]);
@@ -254,7 +260,6 @@ int32_t map_file(Stages *st, const mp_idx_t *mi, const char *fn, const mp_mapopt
 		n_done += n;
 		if (mp_verbose >= 3) fprintf(stderr, "[M::%s::%.3f*%.2f] mapped %d sequences\n", __func__, mp_realtime(), mp_cputime() / mp_realtime(), n);
 	}
-	free(buf.s);
 	return 0;
 }
 
