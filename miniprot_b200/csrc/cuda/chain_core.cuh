@@ -173,6 +173,11 @@ CHN_HD int32_t peel_chains(const Par &p, int32_t n_z, const FT *f, const PT *pp,
 	if (!PRESORTED) mpb::flag_sort_by(z, z + n_z, [](const uint64_t &e) { return rec_key(e); }, stack);
 	for (int32_t k = n_z - 1; k >= 0; --k) {
 		const int32_t zi = (int32_t)(uint32_t)z[k], zx = (int32_t)(z[k] >> 32);
+		// A score of kmer (the floor of the fill) means "no predecessor": such an end yields a one-anchor chain, which
+		// min_cnt >= 2 rejects, and its mark can matter to nobody -- whoever chains through it scores higher and has been
+		// peeled already.  The records are sorted, so everything from here down is of that kind (the bulk of a pre-chain
+		// problem: anchors with nothing else in their block).
+		if (zx <= p.kmer && p.min_cnt >= 2) break;
 		if (t[zi] != 0) continue;
 		const int32_t n_v0 = n_v;
 		const int64_t end_i = bk_end(max_drop, z[k], f, pp, t);

@@ -19,6 +19,40 @@ using namespace chn;
 
 constexpr int CHAIN_WARPS = 4;
 
+// The fill walks the anchors in order and looks a short way back, so the warp keeps the 32-anchor block it is in, the one
+// before and the one after in registers (lane l holds anchor i0 + l; one coalesced load per 32 anchors, issued a block
+// ahead) and hands values around by shuffle; only look-backs of more than a block go to memory.  Without this every
+// anchor paid one or two dependent L2 round trips (a[i], a[st], a[hi]) even when it had no predecessor to score, which is
+// the common case of the block-level pre-chain.
+struct AnchorBlocks {
+	uint64_t prev, cur, next;
+	int32_t i0; // first anchor of `cur`
+	__device__ __forceinline__ void init(const uint64_t *a, int32_t n, int lane)
+	{
+		i0 = 0, prev = 0;
+		cur = lane < n ? a[lane] : 0;
+		next = 32 + lane < n ? a[32 + lane] : 0;
+	}
+	__device__ __forceinline__ void enter(const uint64_t *a, int32_t n, int32_t i, int lane) // i is a multiple of 32, i > 0
+	{
+		prev = cur, cur = next, i0 = i;
+		next = i + 32 + lane < n ? a[i + 32 + lane] : 0;
+	}
+	// a[idx] for a warp-uniform idx <= i0 + 31
+	__device__ __forceinline__ uint64_t at(const uint64_t *a, int32_t idx) const
+	{
+		if (idx >= i0) return __shfl_sync(0xffffffffu, cur, idx - i0);
+		if (idx >= i0 - 32) return __shfl_sync(0xffffffffu, prev, idx - (i0 - 32));
+		return a[idx];
+	}
+	// a[j] for a per-lane j in [i0 - 32, i0 + 31] (every lane calls; lanes with j out of that range get garbage)
+	__device__ __forceinline__ uint64_t near(int32_t j) const
+	{
+		const uint64_t c = __shfl_sync(0xffffffffu, cur, j & 31), p = __shfl_sync(0xffffffffu, prev, j & 31);
+		return j >= i0 ? c : p;
+	}
+};
+
 __global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_fill_kernel(const int32_t *list, const int64_t *a_off, const int32_t *cnt, const uint64_t *a_all, int n_prob, Par par,
                                                                      int32_t *f_all, int32_t *p_all, int32_t *t_all)
 {
@@ -32,29 +66,71 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_fill_kernel(const int3
 	int32_t *f = f_all + base, *p = p_all + base, *t = t_all + base;
 	for (int32_t i = lane; i < n; i += 32) __stcg(t + i, 0);
 	__syncwarp();
+	AnchorBlocks ab;
+	ab.init(a, n, lane);
+	int32_t fcur = 0, fprev = 0, pcur = -1, pprev = -1; // f and p of the same two blocks (lane l: anchor i0 + l resp. i0 - 32 + l)
 	int32_t st = 0, hi = -1, hf = 0;
+	uint64_t a_hi = 0;
 	for (int32_t i = 0; i < n; ++i) {
-		const uint64_t ai = a[i];
+		if (i && (i & 31) == 0) ab.enter(a, n, i, lane), fprev = fcur, pprev = pcur;
+		{ // Runs of ISOLATED anchors -- farther than the window from their immediate predecessor, hence from everybody before
+		  // them -- need no scan: st = i, the rescue anchor is out of reach, f = kmer, p = -1, and each becomes the rescue
+		  // anchor of the next.  The lanes settle the rest of the block's run at once.
+			const uint64_t mine = ab.cur;
+			uint64_t left = __shfl_up_sync(0xffffffffu, mine, 1);
+			const uint64_t last_prev = __shfl_sync(0xffffffffu, ab.prev, 31);
+			if (lane == 0) left = last_prev;
+			const int32_t idx = ab.i0 + lane;
+			const bool iso = idx < n && (idx == 0 || (((int64_t)(mine >> 32) - (int64_t)(left >> 32)) << par.bbit) > par.max_dist_x);
+			const uint32_t m = __ballot_sync(0xffffffffu, iso) >> (i & 31);
+			const int run = ~m ? __ffs(~m) - 1 : 32; // consecutive isolated anchors from i on (within the block)
+			if (run > 0) {
+				if (lane >= (i & 31) && lane < (i & 31) + run) {
+					__stcg(f + idx, par.kmer), __stcg(p + idx, -1);
+					fcur = par.kmer, pcur = -1;
+				}
+				i += run - 1;
+				st = i, hf = par.kmer, hi = i, a_hi = __shfl_sync(0xffffffffu, mine, i & 31);
+				continue;
+			}
+		}
+		const uint64_t ai = __shfl_sync(0xffffffffu, ab.cur, i & 31);
 		const int64_t xi = (int64_t)(ai >> 32);
-		while (st < i && ((xi - (int64_t)(a[st] >> 32)) << par.bbit) > par.max_dist_x) ++st;
+		while (st < i && ((xi - (int64_t)(ab.at(a, st) >> 32)) << par.bbit) > par.max_dist_x) ++st;
 		int32_t max_f = par.kmer, max_j = -1, n_skip = 0;
 		if (hi >= 0 && hi >= st) { // chain.c:185-189: rescue through the best anchor so far
-			const int32_t sc = hf + pair_score(par, ai, a[hi]);
+			const int32_t sc = hf + pair_score(par, ai, a_hi);
 			if (sc > max_f) max_f = sc, max_j = hi;
 		} else hf = 0, hi = -1;
 		if (i - st > par.max_iter) st = i - par.max_iter;
+		bool any_mark = false; // has any t[] been set to i yet?
 		for (int32_t jb = i - 1; jb >= st; jb -= 32) {
 			const int32_t j = jb - lane;
+			const bool near = jb == i - 1; // first chunk: j in [i - 32, i - 1], all in the register blocks
 			bool ok = j >= st;
 			int32_t sc = INT32_MIN, pj = -1;
+			uint64_t aj = 0;
+			int32_t fj = 0;
+			if (near) {
+				aj = ab.near(j);
+				const int32_t fc = __shfl_sync(0xffffffffu, fcur, j & 31), fp = __shfl_sync(0xffffffffu, fprev, j & 31);
+				const int32_t pc = __shfl_sync(0xffffffffu, pcur, j & 31), pp = __shfl_sync(0xffffffffu, pprev, j & 31);
+				fj = j >= ab.i0 ? fc : fp, pj = j >= ab.i0 ? pc : pp;
+			} else if (ok) aj = a[j];
 			if (ok) {
-				sc = pair_score(par, ai, a[j]);
+				sc = pair_score(par, ai, aj);
 				ok = sc != INT32_MIN;
-				if (ok) sc += __ldcg(f + j), pj = __ldcg(p + j);
+				if (ok) {
+					if (!near) fj = __ldcg(f + j), pj = __ldcg(p + j);
+					sc += fj;
+				}
 			}
-			if (ok && pj >= 0) __stcg(t + pj, i);
+			if (!ok) pj = -1;
+			const bool mark = ok && pj >= 0;
+			if (mark) __stcg(t + pj, i);
+			any_mark = any_mark || __any_sync(0xffffffffu, mark);
 			__syncwarp();
-			const bool marked = ok && __ldcg(t + j) == i;
+			const bool marked = any_mark && ok && __ldcg(t + j) == i;
 			// running maximum in scan order (lane 0 first)
 			int32_t pm = ok ? sc : INT32_MIN;
 #pragma unroll
@@ -76,8 +152,9 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_fill_kernel(const int3
 			if (brk < 32) break;
 		}
 		if (lane == 0) __stcg(f + i, max_f), __stcg(p + i, max_j);
+		if (lane == (i & 31)) fcur = max_f, pcur = max_j;
 		__syncwarp();
-		if (hf < max_f) hf = max_f, hi = i;
+		if (hf < max_f) hf = max_f, hi = i, a_hi = ai;
 	}
 }
 
@@ -187,14 +264,35 @@ __global__ void __launch_bounds__(32) chain_smem_kernel(const int32_t *list, int
 	for (int32_t i = lane; i < n; i += 32) t[i] = 0;
 	__syncwarp();
 	// ---- phase 1: fill (chain.c:181-209), identical logic to chain_fill_kernel
+	AnchorBlocks ab;
+	ab.init(a, n, lane);
 	int32_t st = 0, hi = -1, hf = 0;
+	uint64_t a_hi = 0;
 	for (int32_t i = 0; i < n; ++i) {
-		const uint64_t ai = a[i];
+		if (i && (i & 31) == 0) ab.enter(a, n, i, lane);
+		{ // runs of isolated anchors, see chain_fill_kernel
+			const uint64_t mine = ab.cur;
+			uint64_t left = __shfl_up_sync(0xffffffffu, mine, 1);
+			const uint64_t last_prev = __shfl_sync(0xffffffffu, ab.prev, 31);
+			if (lane == 0) left = last_prev;
+			const int32_t idx = ab.i0 + lane;
+			const bool iso = idx < n && (idx == 0 || (((int64_t)(mine >> 32) - (int64_t)(left >> 32)) << par.bbit) > par.max_dist_x);
+			const uint32_t m = __ballot_sync(0xffffffffu, iso) >> (i & 31);
+			const int run = ~m ? __ffs(~m) - 1 : 32;
+			if (run > 0) {
+				if (lane >= (i & 31) && lane < (i & 31) + run) f[idx] = par.kmer, p[idx] = -1;
+				__syncwarp();
+				i += run - 1;
+				st = i, hf = par.kmer, hi = i, a_hi = __shfl_sync(0xffffffffu, mine, i & 31);
+				continue;
+			}
+		}
+		const uint64_t ai = __shfl_sync(0xffffffffu, ab.cur, i & 31);
 		const int64_t xi = (int64_t)(ai >> 32);
-		while (st < i && ((xi - (int64_t)(a[st] >> 32)) << par.bbit) > par.max_dist_x) ++st;
+		while (st < i && ((xi - (int64_t)(ab.at(a, st) >> 32)) << par.bbit) > par.max_dist_x) ++st;
 		int32_t max_f = par.kmer, max_j = -1, n_skip = 0;
 		if (hi >= 0 && hi >= st) {
-			const int32_t sc = hf + pair_score(par, ai, a[hi]);
+			const int32_t sc = hf + pair_score(par, ai, a_hi);
 			if (sc > max_f) max_f = sc, max_j = hi;
 		} else hf = 0, hi = -1;
 		if (i - st > par.max_iter) st = i - par.max_iter;
@@ -202,8 +300,11 @@ __global__ void __launch_bounds__(32) chain_smem_kernel(const int32_t *list, int
 			const int32_t j = jb - lane;
 			bool ok = j >= st;
 			int32_t sc = INT32_MIN, pj = -1;
+			uint64_t aj = 0;
+			if (jb == i - 1) aj = ab.near(j); // first chunk: the anchors are in the register blocks
+			else if (ok) aj = a[j];
 			if (ok) {
-				sc = pair_score(par, ai, a[j]);
+				sc = pair_score(par, ai, aj);
 				ok = sc != INT32_MIN;
 				if (ok) sc += f[j], pj = p[j];
 			}
@@ -231,7 +332,7 @@ __global__ void __launch_bounds__(32) chain_smem_kernel(const int32_t *list, int
 		}
 		if (lane == 0) f[i] = max_f, p[i] = (int16_t)max_j;
 		__syncwarp();
-		if (hf < max_f) hf = max_f, hi = i;
+		if (hf < max_f) hf = max_f, hi = i, a_hi = ai;
 	}
 	// ---- phase 2: backtrack + compaction (chain.c:26-110)
 	int32_t n_z = 0;

@@ -84,8 +84,9 @@ static void chain_problems(mpb_ctx_s *ctx, int n_prob, const std::vector<int64_t
 	//                flight) followed by the shared-memory backtrack (13 B per anchor of the class capacity: the finer the
 	//                classes, the more problems fit an SM's shared memory together)
 	//           NC: larger   global-memory fill + single-thread global backtrack
-	static const int NC = 10;
-	static const int caps[NC] = { 2048, 3072, 4096, 5120, 6144, 7168, 8192, 10240, 12288, 16384 };
+	static const int NC = 11;
+	static const int caps[NC] = { 2048, 3072, 4096, 5120, 6144, 7168, 8192, 10240, 12288, 14000, 16384 };
+	static const int fused_max = getenv("MPB_CHAIN_FUSED_MAX") ? atoi(getenv("MPB_CHAIN_FUSED_MAX")) : 2048;
 	std::vector<int32_t> lists[NC + 1], flat, sizes((size_t)n_prob);
 	size_t lfirst[NC + 1];
 	for (int i = 0; i < n_prob; ++i) sizes[(size_t)i] = (int32_t)(h_off[(size_t)i + 1] - h_off[(size_t)i]);
@@ -110,8 +111,8 @@ static void chain_problems(mpb_ctx_s *ctx, int n_prob, const std::vector<int64_t
 			const int32_t *lst = d_list + lfirst[c];
 			const int nl = (int)lists[c].size();
 			MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
-			if (c == 0) {
-				chain_launch_smem(ss, lst, nl, caps[0], d_off, cnt, in, par, v, stack, uo, bo, nuo, nbo, resort);
+			if (c < NC && caps[c] <= fused_max) {
+				chain_launch_smem(ss, lst, nl, caps[c], d_off, cnt, in, par, v, stack, uo, bo, nuo, nbo, resort);
 				ctx->stats.kernel_launches += 1;
 			} else {
 				chain_launch_fill(ss, lst, d_off, cnt, in, nl, par, f, p, t);
