@@ -418,43 +418,51 @@ struct Lane3 {
 		env.rec3(-g.x, rec[0], rec[1], rec[2]), env.rec3(1 - g.x, rec[3], rec[4], rec[5]);
 	}
 
-	// Three real rows of a live column, straight-line (no per-row validity checks): the body of every steady-state step.
-	// pH[r] / rH[r]: H of the column to the left for row r of the previous / of this macro-step (the first column gets NEG).
-	NSW_HD void rows3(const Par &par, const RowRec &rc0, const RowRec &rc1, const RowRec &rc2, const int *pH, const int *rH, const int *rI, const int *rX,
-	                  const int *rS, const int *ps, int W, uint32_t *wd)
+	// One real row of a column, straight-line (no validity checks): rows 0, 1, 2 of a steady-state macro-step in this order.
+	// l0 = H(i, j-1); l1..l3 = H(i-1..i-3, j-1); ri / rx / rs = insertion chain, running row maximum (first-pass H in
+	// traceback mode) and segment chain of the column to the left for this row (the first column gets the boundary values).
+	// Dead columns (x >= W8) run the same arithmetic on their all-NEG profile columns -- nothing to their right is real, so
+	// whatever they produce is never used -- and only hand the row maxima on: no divergent branch inside the warp.
+	template <int R>
+	NSW_HD void row(const Par &par, const RowRec &rc, bool live, int l0, int l1, int l2, int l3, int ri, int rx, int rs, const int *ps, int W, uint32_t &wd)
 	{
-#define NSW_ROW(R, RC, H1S, H2S, H3S, L1, L2, L3) \
-		{ \
-			const int s = ps[RC.nas * W]; \
-			int d_new, it = rI[R]; \
-			if (TB) { \
-				int f0 = seg_start ? NEG : rX[R], iseg = seg_start ? NEG : rS[R], hf; \
-				const int h = cell_trace(par, RC, s, H[H1S], H[H2S], H[H3S], D[H3S], d_new, A, B, Cc, rH[R], f0, L1, L2, L3, iseg, it, hf, wd[R]); \
-				H[H3S] = h, D[H3S] = d_new, oH[R] = h, oI[R] = it, oX[R] = hf, oS[R] = iseg; \
-			} else { \
-				const int h = cell_score(par, RC, s, H[H1S], H[H2S], H[H3S], D[H3S], d_new, A, B, Cc, rH[R], L1, L2, L3, it); \
-				H[H3S] = h, D[H3S] = d_new, oH[R] = h, oI[R] = it, oX[R] = imax(rX[R], (h + bonus) * 4096 + code); \
-			} \
+		constexpr int h3 = R, h2 = (R + 1) % 3, h1 = (R + 2) % 3; // R = 0: (2,1,0), 1: (0,2,1), 2: (1,0,2)
+		const int s = ps[rc.nas * W];
+		int d_new, it = ri;
+		if (TB) {
+			int f0 = seg_start ? NEG : rx, iseg = seg_start ? NEG : rs, hf;
+			const int h = cell_trace(par, rc, s, H[h1], H[h2], H[h3], D[h3], d_new, A, B, Cc, l0, f0, l1, l2, l3, iseg, it, hf, wd);
+			H[h3] = h, D[h3] = d_new, oH[R] = h, oI[R] = it, oX[R] = hf, oS[R] = iseg;
+		} else {
+			const int h = cell_score(par, rc, s, H[h1], H[h2], H[h3], D[h3], d_new, A, B, Cc, l0, l1, l2, l3, it);
+			H[h3] = h, D[h3] = d_new, oH[R] = h, oI[R] = it;
+			const int m = imax(rx, (h + bonus) * 4096 + code);
+			oX[R] = live ? m : rx;
 		}
-		NSW_ROW(0, rc0, 2, 1, 0, pH[2], pH[1], pH[0])
-		NSW_ROW(1, rc1, 0, 2, 1, rH[0], pH[2], pH[1])
-		NSW_ROW(2, rc2, 1, 0, 2, rH[1], rH[0], pH[2])
-#undef NSW_ROW
+	}
+	// after the three rows: fetch the records of step T+2 through the environment's running cursor (AFTER the rows that used
+	// the old ones: no register copies)
+	template <int PH, class Env>
+	NSW_HD void steady_tail(const Geo3 &g, Env &env)
+	{
+		env.next3(rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2]);
+		if (g.x < 6) env.prefetch_ahead(g.x);
 	}
 
 	// Steady-state macro-step: EVERY thread of the block has three real rows (the kernel guarantees T is in that range), so
-	// there is nothing to check.  The caller keeps the left column's H of
-	// the previous step (pH) and of this one (rH) in two alternating buffers, which replaces L[]; the records of step T+2 are
-	// fetched through the environment's running cursor AFTER the rows that used the old ones (no register copies).
+	// there is nothing to check.  pH[r] / rH[r]: H of the column to the left for row r of the previous / of this macro-step
+	// (two alternating buffers of the caller, which replace L[]).  The kernel calls the three rows itself so that it can
+	// send each row's outputs to the right as soon as they exist; this form is the reference sequence (and what the CPU
+	// emulation steps through).
 	template <int PH, class Env>
 	NSW_HD void macro_steady(const Geo3 &g, const Par &par, const int *pH, const int *rH, const int *rI, const int *rX, const int *rS, Env &env, uint32_t *wd)
 	{
-		// dead columns (x >= W8) run the same arithmetic on their all-NEG profile columns -- nothing to their right is real, so
-		// whatever they produce is never used -- and only hand the row maxima on: no divergent branch inside the warp
-		rows3(par, rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2], pH, rH, rI, rX, rS, env.profile(0), env.profile_stride(), wd);
-		env.next3(rec[3 * PH], rec[3 * PH + 1], rec[3 * PH + 2]);
-		if (g.x < 6) env.prefetch_ahead(g.x);
-		if (!TB && !g.live) oX[0] = rX[0], oX[1] = rX[1], oX[2] = rX[2];
+		const int *ps = env.profile(0);
+		const int W = env.profile_stride();
+		row<0>(par, rec[3 * PH], g.live, rH[0], pH[2], pH[1], pH[0], rI[0], rX[0], rS[0], ps, W, wd[0]);
+		row<1>(par, rec[3 * PH + 1], g.live, rH[1], rH[0], pH[2], pH[1], rI[1], rX[1], rS[1], ps, W, wd[1]);
+		row<2>(par, rec[3 * PH + 2], g.live, rH[2], rH[1], rH[0], pH[2], rI[2], rX[2], rS[2], ps, W, wd[2]);
+		steady_tail<PH>(g, env);
 	}
 	// entering the steady range at macro-step T: hand L[] over as the first "previous" buffer and point the record cursor
 	// at the rows step T will fetch
