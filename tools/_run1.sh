@@ -1,4 +1,5 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for r in 1 2; do python bench.py --steps 5 --warmup 3 2>/dev/null | python -c "
-import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print(round(d['value']),round(d['ms_per_step'],1),round(d['e2e']['value']),{k:round(v,1) for k,v in d['wall_ms_per_step'].items()},d['config']['paf_identical_to_reference'])"; done
-python tools/dp_bench.py 592 30000 24 2>&1| head -1; python tools/dp_bench.py 16 100000 200 2>&1| head -1;  python tools/dp_bench.py 4000 10000 24 2>&1| head -2
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_v8.json 2> gpurun_out/bench_v8.err
+tail -c 300 gpurun_out/bench_v8.json
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:nasw_v3_kernel -c 15 -o gpurun_out/v3_full_v8 python bench.py --steps 1 --warmup 0 > gpurun_out/ncu_c.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 280 --csv --log-file gpurun_out/launches_v8.csv python bench.py --steps 1 --warmup 0 > gpurun_out/ncu_b.log 2>&1
+ls -la gpurun_out/ | tail -5
