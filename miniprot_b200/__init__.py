@@ -230,6 +230,27 @@ def nasw_batch(ctx: Context, opt: NsOpt, problems):
     return out
 
 
+def seed_batch(ctx: Context, mi, max_occ: int, seqs):
+    """mpb_seed_batch: sketch + index lookup + sort for a list of protein byte strings; returns one sorted uint64 anchor
+    array (block<<32 | qpos) per protein."""
+    import numpy as np
+
+    n = len(seqs)
+    arr = (C.c_char_p * n)(*seqs)
+    lens = np.array([len(s) for s in seqs], np.int32)
+    off = np.zeros(n + 1, np.int64)
+    ap = C.c_void_p()
+    L = lib()
+    L.mpb_seed_batch.restype = C.c_int
+    L.mpb_seed_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    rc = L.mpb_seed_batch(ctx.h, C.cast(mi, C.c_void_p), max_occ, n, C.cast(arr, C.c_void_p), lens.ctypes.data, off.ctypes.data, C.byref(ap))
+    if rc != 0:
+        raise RuntimeError("mpb_seed_batch failed")
+    a = np.ctypeslib.as_array(C.cast(ap, C.POINTER(C.c_uint64)), shape=(max(int(off[n]), 1),)).copy()[:int(off[n])]
+    L.mpb_free(ap)
+    return [a[off[i]:off[i + 1]] for i in range(n)]
+
+
 def chain_batch(ctx: Context, par: ChainPar, anchor_lists):
     """anchor_lists: list of sorted uint64 arrays.  Returns list of (u array, b array) per problem."""
     import numpy as np

@@ -340,10 +340,23 @@ int mpb_chain_batch(mpb_ctx_t *c, const mpb_chain_par_t *par, int32_t n, const i
 	return 0;
 }
 
-int mpb_seed_batch(mpb_ctx_t *, const mp_idx_t *, int32_t, int32_t, const char *const *, const int32_t *, int64_t *, uint64_t **)
+int mpb_seed_batch(mpb_ctx_t *c, const mp_idx_t *mi, int32_t max_occ, int32_t n_seq, const char *const *seqs, const int32_t *lens, int64_t *a_off, uint64_t **a)
 {
-	fprintf(stderr, "[miniprot_b200] mpb_seed_batch: stage-level seeding entry is not exposed yet (use mpb_map_batch)\n");
-	return -1;
+	if (c == 0 || mi == 0 || n_seq < 0) return -1;
+	MPB_CUDA_OK(cudaSetDevice(c->device));
+	Batch b;
+	b.n = n_seq, b.seq = seqs, b.len = lens, b.name = 0;
+	CudaStages *cs = static_cast<CudaStages*>(c->stages);
+	cs->need_index(mi);
+	std::vector<int32_t> off;
+	const char *d_aa = cs->upload_residues(b, off);
+	std::vector<int64_t> ao;
+	std::vector<uint64_t> av;
+	seed_batch_run(c, mi, max_occ, b, off, d_aa, ao, av);
+	for (int32_t i = 0; i <= n_seq; ++i) a_off[i] = ao[(size_t)i];
+	*a = (uint64_t*)malloc(sizeof(uint64_t) * (av.size() + 1));
+	if (!av.empty()) memcpy(*a, av.data(), sizeof(uint64_t) * av.size());
+	return 0;
 }
 
 void mpb_free(void *p) { free(p); }

@@ -170,15 +170,20 @@ void chain_batch_run(mpb_ctx_s *ctx, const chn::Par &par, int n_prob, const int6
 	chain_problems(ctx, n_prob, off, ctx->b_c[7].as<int64_t>(), ctx->b_c[1].as<uint64_t>(), 0, chn::normalise(par), n_u, n_b, u, bb);
 }
 
-void seed_chain_run(mpb_ctx_s *ctx, const mp_idx_t *mi, const mp_mapopt_t *opt, const Batch &b, const std::vector<int32_t> &aa_off, const char *d_aa, ChainSet &out)
+// Seeding of a batch (map.c:155-177 per query): sketch, adaptive occupancy cut-off, expansion of the index buckets, sort.
+// On return a_off[n_q + 1] delimits each query's sorted anchors inside the device array *d_a_out (ctx->b_c[1]); *d_off_out is
+// the same table on the device.
+static void seed_run(mpb_ctx_s *ctx, const mp_idx_t *mi, int32_t max_occ, const Batch &b, const std::vector<int32_t> &aa_off, const char *d_aa,
+                     std::vector<int64_t> &a_off, uint64_t **d_a_out, int64_t **d_off_out)
 {
 	cudaStream_t st = ctx->stream;
 	const int n_q = b.n;
 	const size_t R = (size_t)aa_off[(size_t)n_q];
-	out.u_off.assign((size_t)n_q + 1, 0), out.a_off.assign((size_t)n_q + 1, 0), out.u.clear(), out.a.clear();
-	if (n_q == 0) return;
 	SeedConst cst;
-	fill_seed_const(mi, opt, cst);
+	mp_mapopt_t tmp;
+	memset(&tmp, 0, sizeof(tmp));
+	tmp.max_occ = max_occ;
+	fill_seed_const(mi, &tmp, cst);
 	int32_t *d_aa_off, *sd_pos, *d_nsd;
 	uint32_t *sd_hash;
 	int64_t *sd_cnt, *sd_aoff, *d_tot, *d_a_off;
@@ -193,7 +198,8 @@ void seed_chain_run(mpb_ctx_s *ctx, const mp_idx_t *mi, const mp_mapopt_t *opt, 
 	MPB_CUDA_OK(cudaMemcpyAsync(d_aa_off, aa_off.data(), sizeof(int32_t) * ((size_t)n_q + 1), cudaMemcpyHostToDevice, st));
 	ctx->time_begin();
 	seed_launch_sketch(st, d_aa, d_aa_off, n_q, cst, ctx->d_ki, sd_hash, sd_pos, sd_cnt, sd_aoff, d_nsd, d_tot);
-	std::vector<int64_t> tot((size_t)n_q), a_off((size_t)n_q + 1, 0);
+	std::vector<int64_t> tot((size_t)n_q);
+	a_off.assign((size_t)n_q + 1, 0);
 	MPB_CUDA_OK(cudaMemcpyAsync(tot.data(), d_tot, sizeof(int64_t) * (size_t)n_q, cudaMemcpyDeviceToHost, st));
 	MPB_CUDA_OK(cudaStreamSynchronize(st));
 	for (int q = 0; q < n_q; ++q) a_off[(size_t)q + 1] = a_off[(size_t)q] + tot[(size_t)q];
@@ -207,6 +213,33 @@ void seed_chain_run(mpb_ctx_s *ctx, const mp_idx_t *mi, const mp_mapopt_t *opt, 
 	ctx->stats.ms_seed += ctx->time_end();
 	ctx->stats.kernel_launches += 3;
 	ctx->stats.n_anchors += (int64_t)N;
+	*d_a_out = d_a, *d_off_out = d_a_off;
+}
+
+// stage-level entry for tests/benchmarks: seeding only (mpb_seed_batch)
+void seed_batch_run(mpb_ctx_s *ctx, const mp_idx_t *mi, int32_t max_occ, const Batch &b, const std::vector<int32_t> &aa_off, const char *d_aa,
+                    std::vector<int64_t> &a_off, std::vector<uint64_t> &a)
+{
+	uint64_t *d_a = 0;
+	int64_t *d_off = 0;
+	a_off.assign((size_t)b.n + 1, 0), a.clear();
+	if (b.n == 0) return;
+	seed_run(ctx, mi, max_occ, b, aa_off, d_aa, a_off, &d_a, &d_off);
+	a.resize((size_t)a_off[(size_t)b.n]);
+	if (!a.empty()) MPB_CUDA_OK(cudaMemcpyAsync(a.data(), d_a, sizeof(uint64_t) * a.size(), cudaMemcpyDeviceToHost, ctx->stream));
+	MPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	ctx->stats.d2h_bytes += (int64_t)(sizeof(uint64_t) * a.size());
+}
+
+void seed_chain_run(mpb_ctx_s *ctx, const mp_idx_t *mi, const mp_mapopt_t *opt, const Batch &b, const std::vector<int32_t> &aa_off, const char *d_aa, ChainSet &out)
+{
+	const int n_q = b.n;
+	out.u_off.assign((size_t)n_q + 1, 0), out.a_off.assign((size_t)n_q + 1, 0), out.u.clear(), out.a.clear();
+	if (n_q == 0) return;
+	std::vector<int64_t> a_off;
+	uint64_t *d_a = 0;
+	int64_t *d_a_off = 0;
+	seed_run(ctx, mi, opt->max_occ, b, aa_off, d_aa, a_off, &d_a, &d_a_off);
 	const int32_t w = 1 << mi->opt.bbit, spl = !(opt->flag & MP_F_NO_SPLICE);
 	const chn::Par pre = chain_par(w, w, w, opt, 2, 0, mi->opt.kmer, mi->opt.bbit);
 	const chn::Par mainp = chain_par(opt->max_intron, opt->max_gap, opt->bw, opt, opt->min_chn_cnt, opt->min_chn_sc, mi->opt.kmer, mi->opt.bbit);

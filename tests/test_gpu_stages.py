@@ -108,3 +108,40 @@ def test_chain_batch_large_problems(ctx):
         for a, (u, b) in zip(lists, got):
             wu, wb = ol.ora_chain(par, a)
             assert len(wu) == len(u) and (wu == u).all() and len(wb) == len(b) and (wb == b).all(), (mode, len(a))
+
+
+def test_seed_batch_matches_oracle(ctx, tmp_path):
+    """mpb_seed_batch (sketch, adaptive occupancy cut-off, bucket expansion, sort) against the oracle's restatement of
+    map.c:126-177 on the same index, protein by protein."""
+    from miniprot_b200 import synth
+
+    g, p = synth.generate(synth.CONFIGS["small"], str(tmp_path))
+    mi = mp.idx_load(g, 8)
+    idx = mi.contents
+    seqs = []
+    with open(p) as fh:
+        cur = []
+        for line in fh:
+            if line.startswith(">"):
+                if cur:
+                    seqs.append("".join(cur).encode())
+                cur = []
+            else:
+                cur.append(line.strip())
+        if cur:
+            seqs.append("".join(cur).encode())
+    seqs += [b"", b"MKV", b"M" * 40, b"ACDEFGHIKLMNPQRSTVWY" * 3 + b"XX*" + b"WWHHKK" * 5]  # degenerate and low-complexity queries
+    tab = product_tables()
+    ora = ol.ora()
+    for max_occ in (20000, 50):
+        got = mp.seed_batch(ctx, mi, max_occ, seqs)
+        assert len(got) == len(seqs)
+        for s, a in zip(seqs, got):
+            n_a = C.c_int64(0)
+            ptr = ora.ora_seed_anchors(C.byref(tab), C.c_void_p(idx.ki), C.c_int64(idx.n_kb), C.c_void_p(idx.kb), C.c_int32(idx.opt.kmer), C.c_int32(idx.opt.mod_bit),
+                                       C.c_int32(max_occ), C.c_char_p(s), C.c_int32(len(s)), C.byref(n_a))
+            want = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(max(n_a.value, 1),)).copy()[:n_a.value] if ptr else np.zeros(0, np.uint64)
+            if ptr:
+                ol._libc.free(C.c_void_p(ptr))
+            assert np.array_equal(a, want), (len(s), len(a), n_a.value)
+    mp.lib().mp_idx_destroy(mi)
