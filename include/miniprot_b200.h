@@ -248,6 +248,13 @@ int mpb_chain_batch(mpb_ctx_t *ctx, const mpb_chain_par_t *par, int32_t n, const
 int mpb_seed_batch(mpb_ctx_t *ctx, const mp_idx_t *mi, int32_t max_occ, int32_t n_seq, const char *const *seqs,
                    const int32_t *lens, int64_t *a_off, uint64_t **a);
 
+/* Second-round refinement over a batch of windows (replaces map.c:41-97 per region): window k is [as, ae) on strand
+ * vid = contig<<1|rev of query qid.  On return a_off[n_win+1] / *a hold the best chain of each window
+ * (window-relative nt end position<<32 | residue end position; empty = no chain) and sc[n_win] its score; *a is malloc'ed. */
+typedef struct { int32_t qid; uint32_t vid; int64_t as, ae; } mpb_window_t;
+int mpb_refine_batch(mpb_ctx_t *ctx, const mp_idx_t *mi, const mp_mapopt_t *opt, int32_t n_seq, const char *const *seqs, const int32_t *lens,
+                     int32_t n_win, const mpb_window_t *win, int64_t *a_off, uint64_t **a, int32_t *sc);
+
 void mpb_free(void *p);                                   /* free() for buffers this library malloc'ed */
 void mpb_regs_free(int32_t n, const int32_t *n_reg, mp_reg1_t **reg); /* free what mpb_map_batch returned */
 int32_t mpb_map_file_path(mpb_ctx_t *ctx, const mp_idx_t *mi, const char *fn, const mp_mapopt_t *opt, const char *out_path);

@@ -251,6 +251,34 @@ def seed_batch(ctx: Context, mi, max_occ: int, seqs):
     return [a[off[i]:off[i + 1]] for i in range(n)]
 
 
+class Window(C.Structure):  # mpb_window_t
+    _fields_ = [("qid", C.c_int32), ("vid", C.c_uint32), ("as_", C.c_int64), ("ae", C.c_int64)]
+
+
+def refine_batch(ctx: Context, mi, mo, seqs, windows):
+    """mpb_refine_batch: windows = list of (qid, vid, as, ae).  Returns one (anchors uint64 array, score) per window."""
+    import numpy as np
+
+    n, nw = len(seqs), len(windows)
+    arr = (C.c_char_p * n)(*seqs)
+    lens = np.array([len(s) for s in seqs], np.int32)
+    win = (Window * max(nw, 1))(*[Window(*w) for w in windows])
+    off = np.zeros(nw + 1, np.int64)
+    sc = np.zeros(max(nw, 1), np.int32)
+    ap = C.c_void_p()
+    L = lib()
+    L.mpb_refine_batch.restype = C.c_int
+    L.mpb_refine_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                   C.c_void_p]
+    rc = L.mpb_refine_batch(ctx.h, C.cast(mi, C.c_void_p), C.cast(C.pointer(mo), C.c_void_p), n, C.cast(arr, C.c_void_p), lens.ctypes.data, nw,
+                            C.cast(win, C.c_void_p), off.ctypes.data, C.byref(ap), sc.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("mpb_refine_batch failed")
+    a = np.ctypeslib.as_array(C.cast(ap, C.POINTER(C.c_uint64)), shape=(max(int(off[nw]), 1),)).copy()[:int(off[nw])]
+    L.mpb_free(ap)
+    return [(a[off[k]:off[k + 1]], int(sc[k])) for k in range(nw)]
+
+
 def chain_batch(ctx: Context, par: ChainPar, anchor_lists):
     """anchor_lists: list of sorted uint64 arrays.  Returns list of (u array, b array) per problem."""
     import numpy as np

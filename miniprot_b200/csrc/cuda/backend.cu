@@ -359,6 +359,27 @@ int mpb_seed_batch(mpb_ctx_t *c, const mp_idx_t *mi, int32_t max_occ, int32_t n_
 	return 0;
 }
 
+int mpb_refine_batch(mpb_ctx_t *c, const mp_idx_t *mi, const mp_mapopt_t *opt, int32_t n_seq, const char *const *seqs, const int32_t *lens, int32_t n_win,
+                     const mpb_window_t *win, int64_t *a_off, uint64_t **a, int32_t *sc)
+{
+	if (c == 0 || mi == 0 || opt == 0 || n_seq < 0 || n_win < 0) return -1;
+	MPB_CUDA_OK(cudaSetDevice(c->device));
+	Batch b;
+	b.n = n_seq, b.seq = seqs, b.len = lens, b.name = 0;
+	std::vector<RefineJob> jobs((size_t)n_win);
+	for (int32_t k = 0; k < n_win; ++k) {
+		if (win[k].qid < 0 || win[k].qid >= n_seq) return -1;
+		jobs[(size_t)k].qid = win[k].qid, jobs[(size_t)k].vid = win[k].vid, jobs[(size_t)k].as = win[k].as, jobs[(size_t)k].ae = win[k].ae;
+	}
+	RefineSet rs;
+	c->stages->refine(mi, opt, b, jobs, rs);
+	a_off[0] = 0;
+	for (int32_t k = 0; k < n_win; ++k) a_off[k + 1] = rs.off[(size_t)k + 1], sc[k] = rs.sc[(size_t)k];
+	*a = (uint64_t*)malloc(sizeof(uint64_t) * (rs.a.size() + 1));
+	if (!rs.a.empty()) memcpy(*a, rs.a.data(), sizeof(uint64_t) * rs.a.size());
+	return 0;
+}
+
 void mpb_free(void *p) { free(p); }
 
 void mpb_regs_free(int32_t n, const int32_t *n_reg, mp_reg1_t **reg) // what the caller of mp_map does per protein (map.c:314-318)

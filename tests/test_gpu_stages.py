@@ -145,3 +145,65 @@ def test_seed_batch_matches_oracle(ctx, tmp_path):
                 ol._libc.free(C.c_void_p(ptr))
             assert np.array_equal(a, want), (len(s), len(a), n_a.value)
     mp.lib().mp_idx_destroy(mi)
+
+
+def test_refine_batch_matches_oracle(ctx, tmp_path):
+    """mpb_refine_batch (window ORF 5-mers x protein 5-mers -> anchors -> base-level chain, best chain kept) against the
+    oracle's restatement of map.c:41-97, window by window: both strands of every protein's own slot, plus a foreign slot."""
+    from miniprot_b200 import synth
+
+    spec = synth.CONFIGS["small"]
+    g, p = synth.generate(spec, str(tmp_path))
+    mi = mp.idx_load(g, 8)
+    mo = mp.mapopt()
+    seqs, ctgs = [], []
+    for path, out in ((p, seqs), (g, ctgs)):
+        cur = []
+        with open(path) as fh:
+            for line in fh:
+                if line.startswith(">"):
+                    if cur:
+                        out.append("".join(cur).encode())
+                    cur = []
+                else:
+                    cur.append(line.strip())
+        if cur:
+            out.append("".join(cur).encode())
+    seqs = seqs[:80]
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    nt4 = np.full(256, 4, np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        nt4[ch] = i
+    slot = spec.genome_len // spec.n_genes
+    windows, slices = [], []
+    for q in range(len(seqs)):
+        for gslot in (q, (q + 37) % spec.n_genes):
+            lo, hi = gslot * slot, (gslot + 1) * slot
+            c = lo // spec.ctg_len
+            c_len = len(ctgs[c])
+            lo -= c * spec.ctg_len
+            hi = min(hi - c * spec.ctg_len, c_len)
+            for rev in (0, 1):
+                as_, ae = (lo, hi) if not rev else (c_len - hi, c_len - lo)
+                sl = ctgs[c][lo:hi] if not rev else ctgs[c][lo:hi].translate(comp)[::-1]
+                windows.append((q, c << 1 | rev, as_, ae))
+                slices.append(nt4[np.frombuffer(sl, np.uint8)])
+    got = mp.refine_batch(ctx, mi, mo, seqs, windows)
+    tab = product_tables()
+    ora = ol.ora()
+    par = mp.ChainPar(mo.max_intron, mo.max_gap, mo.bw, mo.max_chn_max_skip, mo.max_chn_iter, mo.min_chn_cnt, mo.min_chn_sc, mo.chn_coef_log,
+                      0 if (mo.flag & 0x1) else 1, mo.kmer2, 0)
+    n_hit = 0
+    for (q, vid, as_, ae), nt, (a, sc) in zip(windows, slices, got):
+        nb, sb = C.c_int32(0), C.c_int32(0)
+        ptr = ora.ora_refine(C.byref(tab), C.byref(par), C.c_int32(mi.contents.opt.min_aa_len), C.c_int32(mo.max_ava), C.c_void_p(nt.ctypes.data), C.c_int64(len(nt)),
+                             C.c_char_p(seqs[q]), C.c_int32(len(seqs[q])), C.byref(nb), C.byref(sb))
+        want = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(max(nb.value, 1),)).copy()[:nb.value] if ptr else np.zeros(0, np.uint64)
+        if ptr:
+            ol._libc.free(C.c_void_p(ptr))
+        assert np.array_equal(a, want), (q, vid, len(a), nb.value)
+        if len(want):
+            assert sc == sb.value
+            n_hit += 1
+    assert n_hit >= len(seqs) // 2  # the planted genes are found
+    mp.lib().mp_idx_destroy(mi)
