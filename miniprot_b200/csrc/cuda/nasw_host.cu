@@ -69,6 +69,10 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	for (int k = 0; k < n; ++k) {
 		DpDev &j = jobs[lo + k];
 		const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
+		if (!is_tb && j.al > 4095) { // the row maximum carries its column in 12 bits (nasw_core.cuh ExtTracker)
+			fprintf(stderr, "[miniprot_b200] extension over %d residues: more than 4095 columns are not supported by the extension kernels\n", j.al);
+			abort();
+		}
 		const bool v3 = use_v3(j.al, j.nl);
 		const int nw = v3_warps(j.al);
 		j.C = v3 ? 0 : pick_C(j.al);
