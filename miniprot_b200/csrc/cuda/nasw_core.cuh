@@ -388,7 +388,9 @@ struct TbLane {
 // warp shuffle inside a warp, through a double-buffered shared-memory slot across warps (one __syncthreads per
 // macro-step).  Problems of up to 32*NW (<= 256) padded columns run this way; wider ones keep the column-pass kernels.
 // ------------------------------------------------------------------------------------------------
-struct Geo3 { int x, nl, al, W8; bool live, first; };
+// x = column within the pass (sets the skew of the wavefront), col = column of the problem (pass * Wp + x; problems wider than
+// one block run in passes of Wp columns); live = col < W8; first = col == 0 (the constant boundary is to its left)
+struct Geo3 { int x, col, nl, al, W8; bool live, first; };
 
 // Row records of a block-wide problem are stored per TRIPLE of rows (triple m = rows 3m+2 .. 3m+4, the unit of a macro-step)
 // and field-major: six arrays of M 16-byte fields (record halves a/b of the three rows).  Column x works on triple T - x at
@@ -413,8 +415,8 @@ struct Lane3 {
 		for (int k = 0; k < 3; ++k) H[k] = D[k] = L[k] = NEG, oH[k] = oI[k] = oS[k] = NEG, oX[k] = TB ? NEG : INT32_MIN;
 		A = B = Cc = NEG;
 		if (g.first) L[0] = 0, L[1] = L[2] = -fs; // H(-1,-1), H(0,-1), H(1,-1): seen by row 2 only (nasw-sse.c:253-258)
-		code = g.x < g.al ? 4095 - g.x : 0, bonus = g.x == g.al - 1 ? end_bonus : 0;
-		seg_start = slen > 0 && g.x % slen == 0, end_col = g.x == g.al - 1, score = NEG;
+		code = g.col < g.al ? 4095 - g.col : 0, bonus = g.col == g.al - 1 ? end_bonus : 0;
+		seg_start = slen > 0 && g.col % slen == 0, end_col = g.col == g.al - 1, score = NEG;
 		env.rec3(-g.x, rec[0], rec[1], rec[2]), env.rec3(1 - g.x, rec[3], rec[4], rec[5]);
 	}
 

@@ -35,9 +35,8 @@ static inline int pick_C(int al)
 static int g_forced_family = 0; // MPB_NASW_KERNEL=cols|v3 (A/B switch for tests and measurements), read once per nasw_run
 static inline bool use_v3(int al, int nl)
 {
-	if (g_forced_family) return g_forced_family == 2 && (al + 7) / 8 * 8 <= 256;
-	(void)nl;
-	return (al + 7) / 8 * 8 <= 256; // default: latency first (a mini-batch wave is bounded by its longest problems)
+	(void)al, (void)nl;
+	return g_forced_family != 1; // default: latency first (a wave is bounded by its longest problems); wide problems run in passes
 }
 static inline int v3_warps(int al)
 {
@@ -65,6 +64,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	const double t_in = mp_realtime();
 	int64_t rw_tot = 0, tb_tot = 0, cig_tot = 0, carry_tot = 0;
 	std::vector<PrepChunk> chunks;
+	bool wide3[2] = { false, false }; // does the widest block-wide class hold problems of more than one pass?
 	std::vector<int> order[2][9]; // [is_tb][class]: 0..3 block-wide wavefront with 1/2/4/8 warps; 4..7 column passes C = 1/2/4/8; 8 multi-pass
 	for (int k = 0; k < n; ++k) {
 		DpDev &j = jobs[lo + k];
@@ -77,7 +77,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		const int nw = v3_warps(j.al);
 		j.C = v3 ? 0 : pick_C(j.al);
 		j.pad_ = v3 ? 32 * nw : 0;
-		const int Wp = v3 ? 32 * nw : 32 * j.C, W8 = (j.al + 7) / 8 * 8, n_pass = v3 ? 1 : (W8 + Wp - 1) / Wp;
+		const int Wp = v3 ? 32 * nw : 32 * j.C, W8 = (j.al + 7) / 8 * 8, n_pass = (W8 + Wp - 1) / Wp;
 		const int T = v3 ? (j.nl > 2 ? 3 * ((j.nl - 2 + 2) / 3 + Wp + 2) : 0) : (j.nl > 2 ? j.nl - 2 + 32 + 6 : 0); // rows of the wavefront-major traceback buffer
 		// row records: 32 B per row; block-wide problems store them per triple of rows, field-major (nasw_core.cuh v3_triples)
 		const int rec_rows = v3 ? 2 + 3 * nsw::v3_triples(j.nl) : j.nl + 1;
@@ -89,8 +89,9 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 			j.cig_cap = j.nl + j.al + 4;
 			j.cig_off = cig_tot, cig_tot += j.cig_cap;
 		}
-		if (n_pass > 1) j.carry_off = carry_tot, carry_tot += ((int64_t)j.nl + 1) * 4;
+		if (n_pass > 1) j.carry_off = carry_tot, carry_tot += ((int64_t)j.nl + 2) * 4; // four ints per row
 		for (int r = 0; r < rec_rows; r += PREP_ROWS) chunks.push_back(PrepChunk{ k, r, std::min(PREP_ROWS, rec_rows - r), 0 });
+		if (v3 && n_pass > 1) wide3[is_tb] = true;
 		order[is_tb][v3 ? (nw == 1 ? 0 : nw == 2 ? 1 : nw == 4 ? 2 : 3) : n_pass > 1 ? 8 : j.C == 1 ? 4 : j.C == 2 ? 5 : j.C == 4 ? 6 : 7].push_back(k);
 		(is_tb ? ctx->stats.dp_cells_tb : ctx->stats.dp_cells_ext) += (int64_t)j.nl * j.al;
 		(is_tb ? ctx->stats.n_dp_tb : ctx->stats.n_dp_ext) += 1;
@@ -152,7 +153,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		MPB_CUDA_OK(cudaEventRecord(ctx->ev_k0[g.sid], ss));
 		if (c < 4) {
 			nasw_launch_v3(ss, Cs[c], b == 1, dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>(),
-			               wsm_env >= 0 ? wsm_env : (big_wave && b == 0 && c == 3 && cnt <= 148) ? 8 : 0);
+			               wsm_env >= 0 ? wsm_env : (big_wave && b == 0 && c == 3 && cnt <= 148) ? 8 : 0, ctx->b_carry.as<int>(), c == 3 && wide3[b]);
 			ctx->stats.kernel_launches += 1;
 			if (b == 1) {
 				nasw_launch_bt(ss, dj, ord, cnt, ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
@@ -244,7 +245,7 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_
 			const DpDev &j = jobs[hi];
 			const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
 			const bool v3 = use_v3(j.al, j.nl);
-			const int C = pick_C(j.al), Wp = v3 ? 32 * v3_warps(j.al) : 32 * C, W8 = (j.al + 7) / 8 * 8, n_pass = v3 ? 1 : (W8 + Wp - 1) / Wp;
+			const int C = pick_C(j.al), Wp = v3 ? 32 * v3_warps(j.al) : 32 * C, W8 = (j.al + 7) / 8 * 8, n_pass = (W8 + Wp - 1) / Wp;
 			const size_t tbb = is_tb ? (size_t)n_pass * (size_t)(j.nl + 3 * Wp + 64) * Wp * 2 : 0, rwb = (size_t)(j.nl + 20) * 32;
 			if (hi > lo && (tb_bytes + tbb > kTbBudget || rw_bytes + rwb > kRwBudget)) break;
 			tb_bytes += tbb, rw_bytes += rwb, ++hi;

@@ -345,9 +345,12 @@ struct WarpTracker {
 // ------------------------------------------------------------------ block-wide wavefront (one thread per column, 3 rows per step)
 // CTA = NW warps = 32*NW columns of ONE problem; see nasw_core.cuh::Lane3.  TB = false: score-only extension (result by the
 // last thread's tracker); TB = true: global alignment, one 16-bit word per cell to tb[(3T + r) * 32NW + x].
-template <int NW, bool TB>
+// MP (multi-pass, widest instantiation only): a problem wider than the block's Wp columns runs in passes of Wp columns; the last
+// column of a pass leaves what the column to its right needs (H, insertion chain, running row maximum / first-pass H, segment
+// chain: one int4 per row) in the carry array, the first column of the next pass reads it back two macro-steps ahead.
+template <int NW, bool TB, bool MP>
 __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, const int *order, int n_jobs, const int4 *rec, const char *aa, NaswConst cst,
-                                                          int4 *out, uint16_t *tb)
+                                                          int4 *out, uint16_t *tb, int4 *carry_all)
 {
 	extern __shared__ int smem[];
 	constexpr int Wp = 32 * NW;
@@ -358,14 +361,22 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 	const int jid = order[blockIdx.x];
 	const DpDev job = jobs[jid];
 	const int x = threadIdx.x, lane = x & 31, warp = x >> 5;
-	Geo3 g;
-	g.x = x, g.nl = job.nl, g.al = job.al, g.W8 = (job.al + 7) / 8 * 8, g.live = x < g.W8, g.first = x == 0;
+	const int W8all = (job.al + 7) / 8 * 8, n_pass = MP ? (W8all + Wp - 1) / Wp : 1;
+	int4 *carry = MP ? carry_all + job.carry_off / 4 : 0; // one int4 per row
 	Par par;
 	par.go = cst.go, par.ge = cst.ge, par.io = job.io, par.fs = cst.fs, par.gei_stop = cst.fs;
+	WarpTracker trk; // meaningful in the warp that owns the last column (of the last pass)
+	trk.init();
+	int tb_score = NEG;
+	for (int pass = 0; pass < n_pass; ++pass) {
+	const bool last_pass = pass == n_pass - 1, carry_in = MP && pass > 0 && x == 0, carry_out = MP && !last_pass && x == Wp - 1;
+	Geo3 g;
+	g.x = x, g.col = pass * Wp + x, g.nl = job.nl, g.al = job.al, g.W8 = W8all, g.live = g.col < g.W8, g.first = g.col == 0;
+	if (MP && pass > 0) __syncthreads(); // everybody is done with the previous pass's profile and carry rows
 	// profile: 22 x Wp, column x of row a at smem[a * Wp + x]
 	{
 		int rcode = -1;
-		if (x < job.al) rcode = col_residue(aa, cst, job, x);
+		if (g.col < job.al) rcode = col_residue(aa, cst, job, g.col);
 		for (int a = 0; a < 22; ++a) smem[a * Wp + x] = rcode >= 0 ? cst.mat[a * 22 + rcode] : NEG;
 	}
 	if (x == 0) stop_flag[0] = stop_flag[1] = 0;
@@ -379,10 +390,17 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 	env.rec = rec + job.rw_off * 2, env.M = v3_triples(g.nl), env.prof = smem + x, env.Wp = Wp, env.cur = env.rec;
 	Lane3<TB> L;
 	L.init(g, cst.end_bonus, par.fs, env);
-	WarpTracker trk; // meaningful in the warp that owns the last column
-	trk.init();
+	// carry rows of the first column, fetched two macro-steps ahead: cb[T & 1][r] = row 3 T + 2 + r
+	int4 cb[2][3];
+	auto carry_fetch = [&](int Tm, int4 *dst) {
+		if (carry_in) {
+#pragma unroll
+			for (int r = 0; r < 3; ++r) { const int i = 3 * Tm + 2 + r; dst[r] = __ldcg(carry + (i < g.nl ? i : g.nl)); }
+		}
+	};
+	if (MP) carry_fetch(0, cb[0]), carry_fetch(1, cb[1]);
 	const int n_macro = g.nl > 2 ? (g.nl - 2 + 2) / 3 + Wp : 0; // rows 2..nl-1 in triples, plus the skew of the last column
-	uint16_t *tbp = TB ? tb + job.tb_off + x : 0;
+	uint16_t *tbp = TB ? tb + job.tb_off + (int64_t)pass * (3 * (n_macro + 2)) * Wp + x : 0;
 	// (T is even at every loop head, so the parity of macro-step T + PH is PH: all exchange slots are static)
 #define NSW_V3_RECV(PH, RH) \
 		int rI[3], rX[3], rS[3]; \
@@ -394,6 +412,12 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 			const int4 b0 = lds128(xr[PH ^ 1]), b1 = lds128(xr[PH ^ 1] + 16), b2 = lds128(xr[PH ^ 1] + 32); \
 			RH[0] = b0.x, RH[1] = b0.y, RH[2] = b0.z, rI[0] = b0.w, rI[1] = b1.x, rI[2] = b1.y, rX[0] = b1.z, rX[1] = b1.w, rX[2] = b2.x; \
 			if (TB) rS[0] = b2.y, rS[1] = b2.z, rS[2] = b2.w; \
+		} \
+		if (MP) { /* first column of a later pass: the column to its left was the last column of the previous pass */ \
+			if (carry_in) { \
+				_Pragma("unroll") for (int r = 0; r < 3; ++r) { RH[r] = cb[PH][r].x, rI[r] = cb[PH][r].y, rX[r] = cb[PH][r].z; if (TB) rS[r] = cb[PH][r].w; } \
+			} \
+			carry_fetch(T + PH + 2, cb[PH]); \
 		}
 #define NSW_V3_SEND(PH) \
 		if (NW > 1) { \
@@ -410,7 +434,11 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 		uint32_t wd[3]; \
 		const uint32_t done = L.template macro<PH>(g, par, T + PH, rH, rI, rX, rS, env, wd); \
 		if (TB) { _Pragma("unroll") for (int r = 0; r < 3; ++r) if (done >> r & 1) tbp[(int64_t)(3 * (T + PH) + r) * Wp] = (uint16_t)wd[r]; } \
-		else if (warp == NW - 1) { /* the last column sees the complete row maxima; its rows are real when 2 <= i < nl */ \
+		if (MP && carry_out) { \
+			_Pragma("unroll") for (int r = 0; r < 3; ++r) if (done >> r & 1) \
+				carry[Lane3<TB>::row_of(g, T + PH, r)] = make_int4(L.oH[r], L.oI[r], L.oX[r], TB ? L.oS[r] : 0); \
+		} \
+		if (!TB && warp == NW - 1 && last_pass) { /* the last column sees the complete row maxima; its rows are real when 2 <= i < nl */ \
 			(void)done; \
 			_Pragma("unroll") for (int r = 0; r < 3; ++r) { \
 				const int il = 3 * (T + PH - (Wp - 1)) + 2 + r; \
@@ -423,7 +451,10 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 		uint32_t wd[3]; \
 		L.template macro_steady<PH>(g, par, hb[PH ^ 1], hb[PH], rI, rX, rS, env, wd); \
 		if (TB) { if (g.live) { _Pragma("unroll") for (int r = 0; r < 3; ++r) tbs[r * Wp] = (uint16_t)wd[r]; } tbs += 3 * Wp; } \
-		else if (warp == NW - 1) { \
+		if (MP && carry_out) { \
+			_Pragma("unroll") for (int r = 0; r < 3; ++r) carry[Lane3<TB>::row_of(g, T + PH, r)] = make_int4(L.oH[r], L.oI[r], L.oX[r], TB ? L.oS[r] : 0); \
+		} \
+		if (!TB && warp == NW - 1 && last_pass) { \
 			_Pragma("unroll") for (int r = 0; r < 3; ++r) sts32(ring_w + (trk.n_ring + r) * 128, L.oX[r]); \
 			trk.n_ring += 3; \
 			if (trk.n_ring == 30) trk.flush(ring_r, lane, g.al * 3, cst.pen, cst.xdrop); } \
@@ -453,14 +484,16 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 #undef NSW_V3_STEADY
 #undef NSW_V3_CHECK_STOP
 #undef NSW_V3_MACRO
-	if (!TB && warp == NW - 1 && trk.n_ring > 0) trk.flush(ring_r, lane, g.al * 3, cst.pen, cst.xdrop); // the last, partial batch
+	if (!TB && warp == NW - 1 && last_pass && trk.n_ring > 0) trk.flush(ring_r, lane, g.al * 3, cst.pen, cst.xdrop); // the last, partial batch
+	if (TB && g.col == (job.al > 0 ? job.al - 1 : 0)) tb_score = L.score; // the thread that owns column al-1 holds H(nl-1, al-1)
+	} // passes
 	if (TB) {
-		// the thread that owns column al-1 holds H(nl-1, al-1)
-		if (x == (job.al > 0 ? job.al - 1 : 0)) out[jid] = make_int4(L.score, g.nl, g.al, 0);
+		const int c_end = job.al > 0 ? job.al - 1 : 0;
+		if (x == c_end % Wp) out[jid] = make_int4(tb_score, job.nl, job.al, 0);
 	} else if (x == Wp - 1) {
 		int4 r;
 		r.x = trk.max_sc, r.y = trk.max_i + 1;
-		r.z = (trk.max_i >= 0 && trk.max_code != 0) ? 4095 - trk.max_code + 1 : g.al + 1;
+		r.z = (trk.max_i >= 0 && trk.max_code != 0) ? 4095 - trk.max_code + 1 : job.al + 1;
 		r.w = 0;
 		out[jid] = r;
 	}
@@ -475,7 +508,10 @@ struct DevScan {
 	int C, Wp, T, lane; // C == 0: block-wide wavefront layout, word of cell (i, j) at ((i - 2) + 3 j) * Wp + j
 	__device__ __forceinline__ uint32_t at(int i, int j) const
 	{
-		if (C == 0) return base[(int64_t)(i - 2 + 3 * j) * Wp + j];
+		if (C == 0) { // block-wide layout, passes of Wp columns, T rows of Wp words per pass
+			const int pass = j / Wp, jc = j - pass * Wp;
+			return base[((int64_t)pass * T + (i - 2 + 3 * jc)) * Wp + jc];
+		}
 		const int pass = j / Wp, jc = j - pass * Wp, ln = jc / C;
 		return base[((int64_t)pass * T + (i - 2 + ln)) * Wp + jc];
 	}
@@ -504,7 +540,9 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_bt_kernel(const DpDev *j
 	const int jid = order[slot];
 	const DpDev job = jobs[jid];
 	DevScan sc;
-	sc.base = tb + job.tb_off, sc.C = job.C, sc.Wp = job.C ? 32 * job.C : job.pad_, sc.T = job.nl > 2 ? job.nl - 2 + 32 : 0, sc.lane = lane;
+	sc.base = tb + job.tb_off, sc.C = job.C, sc.Wp = job.C ? 32 * job.C : job.pad_, sc.lane = lane;
+	// rows of traceback words per column pass: column-pass kernels nl - 2 + 32, block-wide kernels 3 (n_macro + 2)
+	sc.T = job.nl <= 2 ? 0 : job.C ? job.nl - 2 + 32 : 3 * ((job.nl - 2 + 2) / 3 + job.pad_ + 2);
 	const int n = backtrack_runs(sc, job.nl, job.al, cigar + job.cig_off, job.cig_cap, lane == 0);
 	if (lane == 0) out[jid].w = n;
 }
@@ -565,39 +603,46 @@ void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order,
 // longest problem first -- as earlier ones retire (list scheduling by decreasing length).  Without the cap every block of a
 // wave is resident from the start and the few 100 k-row problems that set the critical path share their issue slots with
 // thousands of short ones.  (228 KB per SM, 1 KB reserved per block, static arrays included.)
-template <int NW, bool TB>
+template <int NW, bool TB, bool MP>
 static void launch_v3(cudaStream_t st, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, uint16_t *tb,
-                      int warps_per_sm)
+                      int warps_per_sm, int *carry)
 {
 	int smem = 22 * 32 * NW * (int)sizeof(int);
 	if (warps_per_sm > 0) {
 		static int stat = -1;
 		if (stat < 0) {
 			cudaFuncAttributes fa;
-			cudaFuncGetAttributes(&fa, nasw_v3_kernel<NW, TB>);
+			cudaFuncGetAttributes(&fa, nasw_v3_kernel<NW, TB, MP>);
 			stat = ((int)fa.sharedSizeBytes + 15) & ~15;
-			cudaFuncSetAttribute(nasw_v3_kernel<NW, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - stat);
+			cudaFuncSetAttribute(nasw_v3_kernel<NW, TB, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - stat);
 		}
 		const int share = (int)((int64_t)233472 * NW / warps_per_sm) - 1024 - stat;
 		smem = std::max(smem, std::min(share, 232448 - stat)) & ~15;
 	}
-	nasw_v3_kernel<NW, TB><<<n, NW * 32, smem, st>>>(jobs, order, n, rec, aa, cst, out, tb);
+	nasw_v3_kernel<NW, TB, MP><<<n, NW * 32, smem, st>>>(jobs, order, n, rec, aa, cst, out, tb, (int4*)carry);
 }
 
-// block-wide wavefront kernels: nw = warps per problem (1, 2, 4 or 8)
+// block-wide wavefront kernels: nw = warps per problem (1, 2, 4 or 8); multi = some problem of the launch is wider than 256
+// columns (nw == 8 only: column passes with a carry)
 void nasw_launch_v3(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out,
-                    uint16_t *tb, int warps_per_sm)
+                    uint16_t *tb, int warps_per_sm, int *carry, bool multi)
 {
 	if (n <= 0) return;
 	switch (nw * 2 + (is_tb ? 1 : 0)) {
-	case 2: launch_v3<1, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
-	case 3: launch_v3<1, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
-	case 4: launch_v3<2, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
-	case 5: launch_v3<2, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
-	case 8: launch_v3<4, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
-	case 9: launch_v3<4, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
-	case 16: launch_v3<8, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
-	default: launch_v3<8, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm); break;
+	case 2: launch_v3<1, false, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
+	case 3: launch_v3<1, true, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
+	case 4: launch_v3<2, false, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
+	case 5: launch_v3<2, true, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
+	case 8: launch_v3<4, false, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
+	case 9: launch_v3<4, true, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
+	case 16:
+		if (multi) launch_v3<8, false, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
+		else launch_v3<8, false, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
+		break;
+	default:
+		if (multi) launch_v3<8, true, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
+		else launch_v3<8, true, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
+		break;
 	}
 }
 
@@ -640,6 +685,7 @@ void nasw_launch_pack(cudaStream_t st, const DpDev *jobs, int n, const int4 *out
 	nasw_cigoff_kernel<<<1, 1024, 0, st>>>(jobs, n, out, offs);
 	nasw_cigpack_kernel<<<(n + 7) / 8, 256, 0, st>>>(jobs, n, out, cigar, offs, packed);
 }
+
 
 __global__ void nasw_spacer_kernel(long long ns)
 {

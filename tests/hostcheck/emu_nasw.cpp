@@ -172,60 +172,78 @@ void run_v3(const Problem &P, int *score, int *nt_len, int *aa_len, std::vector<
 {
 	int NW = (P.W8 + 31) / 32;
 	NW = NW <= 1 ? 1 : NW <= 2 ? 2 : NW <= 4 ? 4 : 8;
-	const int Wp = 32 * NW, n_macro = P.nl > 2 ? (P.nl - 2 + 2) / 3 + Wp : 0;
+	const int Wp = 32 * NW, n_macro = P.nl > 2 ? (P.nl - 2 + 2) / 3 + Wp : 0, n_pass = (P.W8 + Wp - 1) / Wp, Trows = 3 * (n_macro + 2);
 	std::vector<int> prof(22 * Wp);
-	for (int j = 0; j < Wp; ++j)
-		for (int a = 0; a < 22; ++a) prof[a * Wp + j] = j < P.al ? P.mat[a * 22 + P.aas[j]] : NEG;
 	std::vector<Lane3<TB>> L((size_t)Wp);
 	std::vector<Geo3> g((size_t)Wp);
 	std::vector<EmuEnv> env((size_t)Wp);
-	std::vector<ExtTracker> trk((size_t)Wp);
-	std::vector<uint16_t> tb(TB ? (size_t)(3 * (n_macro + 2)) * Wp : 1, 0xffff);
+	ExtTracker trk; // fed by the last column of the last pass
+	trk.init();
+	std::vector<uint16_t> tb(TB ? (size_t)n_pass * Trows * Wp : 1, 0xffff);
+	struct Carry { int h, i, x, s; };
+	std::vector<Carry> carry((size_t)P.nl + 2, Carry{ NEG, NEG, NEG, NEG }); // what the last column of a pass leaves for the next pass, per row
 	PenTable pt;
 	pen_table_build(P.ie_coef, pt);
-	for (int x = 0; x < Wp; ++x) {
-		g[x].x = x, g[x].nl = P.nl, g[x].al = P.al, g[x].W8 = P.W8, g[x].live = x < P.W8, g[x].first = x == 0;
-		env[x].rec = P.rec.data(), env[x].nl = P.nl, env[x].prof = prof.data() + x, env[x].Wp = Wp, env[x].cy = 0, env[x].M = v3_triples(P.nl), env[x].cur = 0;
-		L[x].init(g[x], P.end_bonus, P.par.fs, env[x]);
-		trk[x].init();
-	}
-	std::vector<int> sH((size_t)Wp * 3), sI((size_t)Wp * 3), sX((size_t)Wp * 3), sS((size_t)Wp * 3);
-	int t_lo, t_hi;
-	Lane3<TB>::steady_range(P.nl, Wp, t_lo, t_hi);
-	for (int T = 0; T < n_macro + (n_macro & 1); ++T) {
-		const bool steady = T >= t_lo && T < t_hi; // the kernel's middle loop
-		for (int x = 0; x < Wp; ++x)
-			for (int r = 0; r < 3; ++r) sH[x * 3 + r] = L[x].oH[r], sI[x * 3 + r] = L[x].oI[r], sX[x * 3 + r] = L[x].oX[r], sS[x * 3 + r] = L[x].oS[r];
+	int tb_score = NEG;
+	bool stop = false;
+	for (int pass = 0; pass < n_pass && !stop; ++pass) {
+		const bool last_pass = pass == n_pass - 1;
+		for (int j = 0; j < Wp; ++j)
+			for (int a = 0; a < 22; ++a) prof[a * Wp + j] = pass * Wp + j < P.al ? P.mat[a * 22 + P.aas[pass * Wp + j]] : NEG;
 		for (int x = 0; x < Wp; ++x) {
-			const int s = x ? x - 1 : 0; // what __shfl_up_sync(..., 1) / the shared-memory slot delivers
-			uint32_t wd[3], done;
-			if (steady) {
-				// the kernel's alternating buffers: "previous" = what L[] would hold, "this" = the values just received;
-				// the first column receives the constant boundary slot
-				int pH[3], rH[3], rI[3], rX[3], rS[3];
-				if (T == t_lo) L[x].steady_enter(g[x], T, pH, env[x]);
-				else for (int r = 0; r < 3; ++r) pH[r] = L[x].L[r];
-				for (int r = 0; r < 3; ++r) {
-					rH[r] = x ? sH[s * 3 + r] : NEG, rI[r] = x ? sI[s * 3 + r] : NEG, rS[r] = x ? sS[s * 3 + r] : NEG;
-					rX[r] = x ? sX[s * 3 + r] : TB ? NEG : INT32_MIN;
-				}
-				if (T & 1) L[x].template macro_steady<1>(g[x], P.par, pH, rH, rI, rX, rS, env[x], wd);
-				else L[x].template macro_steady<0>(g[x], P.par, pH, rH, rI, rX, rS, env[x], wd);
-				L[x].steady_leave(rH);
-				done = TB ? (g[x].live ? 7u : 0u) : 7u;
-			} else if (T & 1) done = L[x].template macro<1>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd);
-			else done = L[x].template macro<0>(g[x], P.par, T, &sH[s * 3], &sI[s * 3], &sX[s * 3], &sS[s * 3], env[x], wd);
-			for (int r = 0; r < 3; ++r) {
-				if (!(done >> r & 1)) continue;
-				if (TB) tb[(size_t)(3 * T + r) * Wp + x] = (uint16_t)wd[r];
-				else trk[x].row(Lane3<TB>::row_of(g[x], T, r), L[x].oX[r], P.al * 3, pt, P.xdrop);
-			}
+			g[x].x = x, g[x].col = pass * Wp + x, g[x].nl = P.nl, g[x].al = P.al, g[x].W8 = P.W8, g[x].live = g[x].col < P.W8, g[x].first = g[x].col == 0;
+			env[x].rec = P.rec.data(), env[x].nl = P.nl, env[x].prof = prof.data() + x, env[x].Wp = Wp, env[x].cy = 0, env[x].M = v3_triples(P.nl), env[x].cur = 0;
+			L[x].init(g[x], P.end_bonus, P.par.fs, env[x]);
 		}
-		if (!TB && (T & 1) && trk[Wp - 1].stopped) break;
+		std::vector<int> sH((size_t)Wp * 3), sI((size_t)Wp * 3), sX((size_t)Wp * 3), sS((size_t)Wp * 3);
+		std::vector<Carry> carry_next = carry; // rows are read (by column 0) long before the last column rewrites them
+		int t_lo, t_hi;
+		Lane3<TB>::steady_range(P.nl, Wp, t_lo, t_hi);
+		for (int T = 0; T < n_macro + (n_macro & 1); ++T) {
+			const bool steady = T >= t_lo && T < t_hi; // the kernel's middle loop
+			for (int x = 0; x < Wp; ++x)
+				for (int r = 0; r < 3; ++r) sH[x * 3 + r] = L[x].oH[r], sI[x * 3 + r] = L[x].oI[r], sX[x * 3 + r] = L[x].oX[r], sS[x * 3 + r] = L[x].oS[r];
+			for (int x = 0; x < Wp; ++x) {
+				const int s = x ? x - 1 : 0; // what __shfl_up_sync(..., 1) / the shared-memory slot delivers
+				uint32_t wd[3], done;
+				// inputs from the left: the column x-1 of this pass, the carry of the previous pass, or the constant boundary
+				int rH[3], rI[3], rX[3], rS[3];
+				for (int r = 0; r < 3; ++r) {
+					if (x) rH[r] = sH[s * 3 + r], rI[r] = sI[s * 3 + r], rX[r] = sX[s * 3 + r], rS[r] = sS[s * 3 + r];
+					else if (pass > 0) {
+						int i = 3 * T + 2 + r;
+						i = i < P.nl ? i : P.nl;
+						rH[r] = carry[(size_t)i].h, rI[r] = carry[(size_t)i].i, rX[r] = carry[(size_t)i].x, rS[r] = carry[(size_t)i].s;
+					} else rH[r] = NEG, rI[r] = NEG, rS[r] = NEG, rX[r] = TB ? NEG : INT32_MIN;
+				}
+				if (steady) {
+					// the kernel's alternating buffers: "previous" = what L[] would hold, "this" = the values just received
+					int pH[3];
+					if (T == t_lo) L[x].steady_enter(g[x], T, pH, env[x]);
+					else for (int r = 0; r < 3; ++r) pH[r] = L[x].L[r];
+					if (T & 1) L[x].template macro_steady<1>(g[x], P.par, pH, rH, rI, rX, rS, env[x], wd);
+					else L[x].template macro_steady<0>(g[x], P.par, pH, rH, rI, rX, rS, env[x], wd);
+					L[x].steady_leave(rH);
+					done = TB ? (g[x].live ? 7u : 0u) : 7u;
+				} else if (T & 1) done = L[x].template macro<1>(g[x], P.par, T, rH, rI, rX, rS, env[x], wd);
+				else done = L[x].template macro<0>(g[x], P.par, T, rH, rI, rX, rS, env[x], wd);
+				for (int r = 0; r < 3; ++r) {
+					if (!(done >> r & 1)) continue;
+					const int i = Lane3<TB>::row_of(g[x], T, r);
+					if (TB) tb[((size_t)pass * Trows + (size_t)(3 * T + r)) * Wp + x] = (uint16_t)wd[r];
+					else if (x == Wp - 1 && last_pass) trk.row(i, L[x].oX[r], P.al * 3, pt, P.xdrop);
+					if (x == Wp - 1 && !last_pass) carry_next[(size_t)i] = Carry{ L[x].oH[r], L[x].oI[r], L[x].oX[r], L[x].oS[r] };
+				}
+			}
+			if (!TB && (T & 1) && trk.stopped) { stop = true; break; }
+		}
+		carry.swap(carry_next);
+		const int c_end = P.al > 0 ? P.al - 1 : 0;
+		if (TB && c_end / Wp == pass) tb_score = L[(size_t)(c_end % Wp)].score;
 	}
 	if (TB) {
-		*score = L[P.al > 0 ? P.al - 1 : 0].score;
-		auto at = [&](int i, int j) -> uint32_t { return tb[(size_t)(i - 2 + 3 * j) * Wp + j]; };
+		*score = tb_score;
+		auto at = [&](int i, int j) -> uint32_t { const int ps = j / Wp, jc = j - ps * Wp; return tb[((size_t)ps * Trows + (size_t)(i - 2 + 3 * jc)) * Wp + jc]; };
 		struct CpuScan {
 			decltype(at) &tbf;
 			uint32_t word(int i, int j) const { return tbf(i, j); }
@@ -251,7 +269,7 @@ void run_v3(const Problem &P, int *score, int *nt_len, int *aa_len, std::vector<
 		const int n = backtrack_runs(scan, P.nl, P.al, buf.data(), cap, true);
 		cigar.assign(buf.begin() + (cap - n), buf.end());
 	} else {
-		const ExtTracker &t = trk[Wp - 1];
+		const ExtTracker &t = trk;
 		*score = t.max_sc, *nt_len = t.max_i + 1;
 		*aa_len = (t.max_i >= 0 && t.max_code != 0) ? 4095 - t.max_code + 1 : P.al + 1;
 	}

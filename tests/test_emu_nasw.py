@@ -40,8 +40,8 @@ def test_emu_matches_oracle(hc, Ccols):
         if it % 5 == 0:
             par["sp"] = (8, 15, 21, 30, 4, 4)
         al_max = (250, 30, 70, 140, 300)[[0, 1, 2, 4, 8].index(Ccols)]
-        if it % 6 == 0 and Ccols:
-            al_max = 32 * Ccols * 2 + 20  # force several column passes
+        if it % 6 == 0:
+            al_max = 32 * Ccols * 2 + 20 if Ccols else (700 if it % 12 else 560)  # force several column passes (256 columns each when Ccols == 0)
         nt, aa = ol.random_dp_problem(rng, al_max=al_max, flank=60)
         if len(nt) < 3:
             continue
