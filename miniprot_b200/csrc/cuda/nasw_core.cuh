@@ -475,11 +475,11 @@ struct Lane3 {
 		env.seek3(T - g.x + 2);
 	}
 	NSW_HD void steady_leave(const int *pH) { L[0] = pH[0], L[1] = pH[1], L[2] = pH[2]; }
-	// macro-steps [lo, hi) are steady for a block of Wp columns: every column has three rows inside [3, nl) (lo, hi even)
+	// macro-steps [lo, hi) are steady for a block of Wp columns: every column has three rows inside [3, nl - 1) (lo, hi even)
 	NSW_HD static void steady_range(int nl, int Wp, int &lo, int &hi)
 	{
 		lo = Wp;
-		hi = nl >= 5 ? (nl - 5) / 3 + 1 : 0;
+		hi = nl >= 6 ? (nl - 6) / 3 + 1 : 0; // ... and below nl - 1: the last row (where the global score is read) stays in the general step
 		if (hi < lo) hi = lo;
 		hi = lo + ((hi - lo) & ~1);
 	}

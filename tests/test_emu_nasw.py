@@ -79,3 +79,19 @@ def test_pen_table_equals_fp_formula(hc):
     hc.emu_pen_check.argtypes = [C.c_float, C.c_int]
     for coef in (0.5, 0.25, 1.0, 3.0):  # PEN_STEPS covers ie_coef up to ~5
         assert hc.emu_pen_check(coef, 3_000_000) == 0
+
+
+def test_emu_score_when_end_column_is_first_of_a_pass(hc):
+    """Global score is read at (nl-1, al-1).  When al-1 is the FIRST column of a block or pass (al = 1, 257, 513) its last row
+    comes earliest of all columns -- it must not fall into the check-free steady loop (regression: AS:i of one C5 hit)."""
+    rng = np.random.default_rng(4242)
+    tab, mat = ol.ref_tables(), ol.default_mat()
+    par = dict(ol.DEFAULT_NASW)
+    for al, nls in ((1, (104, 107, 110, 113, 116)), (257, (803, 806, 809, 812, 815)), (513, (806, 809, 812, 1211))):
+        for nl in nls:
+            nt0, aa = ol.random_dp_problem(rng, al_max=al, flank=10, intron_max=100)
+            aa = (aa + bytes(b"ARNDCQEGHILKMFPSTWYV"[i] for i in rng.integers(0, 20, size=al)))[:al]
+            nt = np.concatenate([nt0, rng.integers(0, 4, size=nl).astype(np.uint8)])[:nl]
+            a = ol.ora_nasw(tab, nt, aa, 1, mat, par)
+            b = emu(hc, nt, aa, 1, 0, mat, par)
+            assert a[0] == b[0] and a[3] == b[3], (al, nl, a[0], b[0])

@@ -207,3 +207,23 @@ def test_refine_batch_matches_oracle(ctx, tmp_path):
             n_hit += 1
     assert n_hit >= len(seqs) // 2  # the planted genes are found
     mp.lib().mp_idx_destroy(mi)
+
+
+def test_nasw_global_score_end_column_first_of_pass(ctx):
+    """al = 1, 257, 513: the end column is the first column of a block / pass, its last row must not be handled by the
+    check-free steady loop (see tests/test_emu_nasw.py, same name)."""
+    rng = np.random.default_rng(4242)
+    opt = mp.nsopt()
+    mat = opt._mat_keepalive
+    tab = product_tables()
+    probs = []
+    for al, nls in ((1, (104, 107, 110, 113, 116)), (257, (803, 806, 809, 812, 815)), (513, (806, 809, 812, 1211))):
+        for nl in nls:
+            nt0, aa = ol.random_dp_problem(rng, al_max=al, flank=10, intron_max=100)
+            aa = (aa + bytes(b"ARNDCQEGHILKMFPSTWYV"[i] for i in rng.integers(0, 20, size=al)))[:al]
+            nt = np.concatenate([nt0, rng.integers(0, 4, size=nl).astype(np.uint8)])[:nl]
+            probs.append((nt, aa, 1, opt.io))
+    got = mp.nasw_batch(ctx, opt, probs)
+    for (nt, aa, flag, io), g in zip(probs, got):
+        w = ol.ora_nasw(tab, nt, aa, flag, mat, _par(opt))
+        assert w[0] == g[0] and list(w[3]) == list(g[3]), (len(nt), len(aa), w[0], g[0])
