@@ -3,7 +3,8 @@
 //
 // HBM layout of one wave (all grow-only arenas of the context):
 //   jobs[]    DpDev descriptors                              order[]  job ids grouped by (kind, C), longest first
-//   rw[]      one 32-bit row word per nucleotide row (+1)    carry[]  per-row spill for problems wider than a pass
+//   rw[]      32-byte row records (triple-major for the      carry[]  one int4 per row for problems wider than a pass
+//             block-wide kernels, nasw_core.cuh v3_triples)
 //   tb[]      16-bit traceback words, wavefront-major        cigar[]  per-problem CIGAR slots (filled from the end)
 //   out[]     int4 {score, nt_len, aa_len, n_cigar}
 // A wave whose traceback or row-word footprint exceeds the budget is cut into sub-waves.
@@ -16,7 +17,7 @@ namespace mpb {
 namespace cuda {
 
 static const size_t kTbBudget = (size_t)24 << 30;   // bytes of traceback words per sub-wave
-static const size_t kRwBudget = (size_t)8 << 30;    // bytes of row words per sub-wave
+static const size_t kRwBudget = (size_t)8 << 30;    // bytes of row records per sub-wave
 
 static inline int pick_C(int al)
 {
@@ -24,14 +25,11 @@ static inline int pick_C(int al)
 	return W8 <= 32 ? 1 : W8 <= 64 ? 2 : W8 <= 128 ? 4 : 8;
 }
 
-// Kernel family: the block-wide wavefront (one thread per column, nasw_v3_kernel) serves every problem of up to 256 padded
-// columns; wider ones use the column-pass kernels (8 columns per lane, several passes).  MPB_NASW_KERNEL=cols forces the
-// column-pass family for everything (A/B measurements only).
-// Measured on B200 (profiles/README.md): per nucleotide row the block-wide kernel is ~2x faster (it sets the critical path
-// of a wave: 100 k-row extensions), per cell the column-pass kernels are up to 3x more efficient on wide problems (8 columns
-// per lane amortise the per-step overhead).  A mini-batch of the benchmark's size is latency bound (its waves last as long
-// as their longest problem), and there the block-wide kernel wins on every class; MPB_NASW_KERNEL=cols selects the
-// throughput-oriented family.
+// Kernel family: the block-wide wavefront (one thread per column, nasw_v3_kernel) serves every problem; those wider than 256
+// padded columns run in column passes inside the same kernel.  MPB_NASW_KERNEL=cols forces the warp-per-problem column-pass
+// family for everything (A/B measurements and tests only).
+// Measured on B200 (profiles/README.md): per nucleotide row the block-wide kernel is several times faster, and a mini-batch
+// is latency bound -- its waves last as long as their longest problem (100 k-row extensions).
 static int g_forced_family = 0; // MPB_NASW_KERNEL=cols|v3 (A/B switch for tests and measurements), read once per nasw_run
 static inline bool use_v3(int al, int nl)
 {

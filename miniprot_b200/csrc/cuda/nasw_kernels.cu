@@ -2,20 +2,20 @@
 //
 // Replaces reference nasw-sse.c:340 ns_global_gs16b (striped SSE2, one problem per CPU thread) by:
 //
-//   nasw_prep_kernel   one thread per nucleotide row: unpack the 4-bit genome slice (strand / reversal aware),
-//                      translate the codon ending at the row, evaluate the donor / acceptor rules, and emit one
-//                      32-bit "row word" (nasw-sse.c:91-210).  HBM-bound: 0.5 B/row read, 4 B/row written.
-//   nasw_ext_kernel    score-only extension DP (80 % of all DP cells).  One warp per problem, lane l owns C
-//                      protein columns, anti-diagonal wavefront over nucleotide rows; the left-neighbour
-//                      dependency travels by warp shuffle; the substitution profile sits in shared memory;
-//                      row words are prefetched one step ahead with coalesced loads.  Integer-issue bound.
-//   nasw_tb_kernel     global alignment with traceback: same wavefront, additionally tracks the reference's
-//                      first-pass / lazy-F distinction and streams one 16-bit traceback word per cell to HBM in
-//                      wavefront-major order (fully coalesced 64*C-byte stores per warp step).
-//   nasw_bt_kernel     one thread per problem walks the traceback words and writes the CIGAR.
-//
-// Problems wider than 32*C columns are processed in column passes of 32*C; the last lane spills its per-row
-// outputs to a carry array that lane 0 of the next pass reads back (rows stay in wavefront order).
+//   nasw_prep_kernel   one thread per nucleotide row: unpack the 4-bit genome slice (strand / reversal aware), translate the
+//                      codon ending at the row, evaluate the donor / acceptor rules (nasw-sse.c:91-210) and emit the 32-byte
+//                      row record with every per-row constant of the recurrences precombined.  HBM-bound.
+//   nasw_v3_kernel     the production DP kernel ("block-wide wavefront"): one CTA of 1/2/4/8 warps per problem, one thread
+//                      per protein column, three rows per macro-step, skewed so that a column's left neighbour finished
+//                      the same rows one macro-step earlier (warp shuffles inside a warp, 48 bytes of shared memory and a
+//                      barrier between warps).  TB = false: score-only extension (80 % of all DP cells) with the
+//                      warp-parallel x-drop bookkeeping; TB = true: global alignment that also streams one 16-bit
+//                      traceback word per cell in wavefront-major order.  MP: problems wider than 256 columns in column
+//                      passes with a per-row carry.  Latency bound (row-to-row dependency), see DESIGN.md section 4.
+//   nasw_ext_kernel /  the first design, kept as the A/B family (MPB_NASW_KERNEL=cols): one warp per problem, lane l owns
+//   nasw_tb_kernel     C protein columns, one row per step, column passes of 32*C with a carry array.
+//   nasw_bt_kernel     one warp per problem walks the traceback words a run at a time and writes the CIGAR.
+//   nasw_cigoff/cigpack_kernel   pack the CIGARs of a wave back to back before the device-to-host copy.
 #include <algorithm>
 #include <cuda_runtime.h>
 #include <stdint.h>
