@@ -27,6 +27,7 @@ public:
 			for (int c = 0; c < n_chunks; ++c) f(c);
 			return;
 		}
+		std::lock_guard<std::mutex> one_at_a_time(run_mu_); // callers on different host threads (several contexts) take turns
 		{
 			std::lock_guard<std::mutex> lk(mu_);
 			job_ = &f, n_chunks_ = n_chunks, next_.store(0), busy_ = (int)th_.size(), ++gen_;
@@ -77,7 +78,7 @@ private:
 		}
 	}
 	std::vector<std::thread> th_;
-	std::mutex mu_;
+	std::mutex mu_, run_mu_;
 	std::condition_variable cv_, cv_done_;
 	const std::function<void(int)> *job_ = 0;
 	int n_chunks_ = 0, busy_ = 0;
