@@ -118,7 +118,9 @@ bool RegionPlan::plan(const mp_idx_t *mi, const mp_mapopt_t *opt, int32_t qid_, 
 		ne0 = ne1, ae0 = ae1;
 	}
 	ve_pin = ne0 + vs0, qe_pin = ae0;
-	has_right = qe_pin < qlen && ve_pin < ae; // align.c:316
+	// align.c:316.  With fewer than 3 bases left the reference's extension loop never runs and it stops at an assertion
+	// (nasw-sse.c:443); such a hit simply ends at the last pinned anchor here.
+	has_right = qe_pin < qlen && ve_pin < ae && ae - ve_pin >= 3;
 	if (has_right) {
 		DpJob j;
 		j.qid = qid, j.vid = r->vid, j.nt_st = ve_pin, j.nl = (int32_t)(ae - ve_pin), j.aa_st = qe_pin, j.al = qlen - qe_pin, j.flag = NS_F_EXT_RIGHT, j.io = opt->io;
@@ -131,6 +133,12 @@ bool RegionPlan::plan(const mp_idx_t *mi, const mp_mapopt_t *opt, int32_t qid_, 
 void RegionPlan::after_wave1(const mp_mapopt_t *opt, const DpSet &w1, std::vector<DpJob> &retry)
 {
 	l_nt = w1.nt_len[(size_t)jobL], l_aa = w1.aa_len[(size_t)jobL];
+	if (l_nt < 0 || (has_right && w1.nt_len[(size_t)jobR] < 0)) { // the stage refused the problem
+		static bool warned = false;
+		if (!warned) fprintf(stderr, "[WARNING] an extension over more than 32767 residues is not supported; such hits are dropped\n"), warned = true;
+		failed = true;
+		return;
+	}
 	if (l_aa != as1 && l_nt < opt->max_ext && opt->io > opt->io_end) { // align.c:290-296: 5'-end exon
 		const int64_t as_alt = vs1 - as > opt->max_ext ? vs1 - opt->max_ext : as;
 		DpJob j;
@@ -152,6 +160,7 @@ void RegionPlan::after_wave1(const mp_mapopt_t *opt, const DpSet &w1, std::vecto
 
 void RegionPlan::after_retry(const mp_idx_t *mi, const mp_mapopt_t *opt, const char *aa, const DpSet &w1r, std::vector<DpJob> &jobs2)
 {
+	if (failed) return;
 	if (jobL2 >= 0 && w1r.aa_len[(size_t)jobL2] == as1) l_nt = w1r.nt_len[(size_t)jobL2], l_aa = w1r.aa_len[(size_t)jobL2];
 	if (jobR2 >= 0 && w1r.aa_len[(size_t)jobR2] == qlen - qe_pin) r_nt = w1r.nt_len[(size_t)jobR2], r_aa = w1r.aa_len[(size_t)jobR2];
 	r->vs = vs1 - l_nt;
@@ -266,6 +275,7 @@ static void fill_statistics(const mp_idx_t *mi, mp_reg1_t *r, const mp_mapopt_t 
 
 void RegionPlan::finish(const mp_idx_t *mi, const mp_mapopt_t *opt, const char *aa, const DpSet &w1, const DpSet &w2)
 {
+	if (failed) { r->p = 0; return; }
 	std::vector<uint32_t> cg;
 	int32_t score = 0;
 	auto take = [&](const Fill &f, const DpSet &src) {

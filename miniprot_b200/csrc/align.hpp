@@ -25,6 +25,7 @@ struct RegionPlan {
 	int64_t ve_pin = 0;       // end of the last pinned anchor
 	int32_t qe_pin = 0;
 	bool has_right = false;
+	bool failed = false;      // a DP problem of this region could not be run (extension over more than 32767 residues): the region is dropped
 	int32_t jobL = -1, jobL2 = -1, jobR = -1, jobR2 = -1;
 	int32_t l_nt = 0, l_aa = 0, r_nt = 0, r_aa = 0; // accepted extension results
 	Fill left_fill, right_fill; // wave 2

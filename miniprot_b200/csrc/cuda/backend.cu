@@ -96,6 +96,14 @@ struct CudaStages : Stages {
 	}
 };
 
+// nasw-sse.c:426 is served from a step table; refuse (loudly) a coefficient whose steps do not fit it
+bool bad_ie_coef(float ie_coef)
+{
+	if (nasw_check_ie_coef(ie_coef) == 0) return false;
+	fprintf(stderr, "[miniprot_b200] ie_coef = %g: the extension length penalty has more than %d steps and is not supported\n", (double)ie_coef, nsw::PEN_STEPS);
+	return true;
+}
+
 std::mutex g_default_mu;
 mpb_ctx_t *g_default_ctx = 0;
 std::vector<mpb_ctx_s*> g_all_ctx;
@@ -229,6 +237,7 @@ int mpb_map_batch(mpb_ctx_t *c, const mp_idx_t *mi, const mp_mapopt_t *opt, int3
                   const char *const *names, int32_t *n_reg_out, mp_reg1_t **reg_out)
 {
 	if (!c) return -1;
+	if (bad_ie_coef(opt->ie_coef)) return -3;
 	MPB_CUDA_OK(cudaSetDevice(c->device));
 	Batch b;
 	b.n = n_seq, b.seq = seqs, b.len = lens, b.name = names;
@@ -239,6 +248,7 @@ int mpb_map_batch(mpb_ctx_t *c, const mp_idx_t *mi, const mp_mapopt_t *opt, int3
 int32_t mpb_map_file(mpb_ctx_t *c, const mp_idx_t *mi, const char *fn, const mp_mapopt_t *opt, FILE *out)
 {
 	if (!c) return -1;
+	if (bad_ie_coef(opt->ie_coef)) return -3;
 	MPB_CUDA_OK(cudaSetDevice(c->device));
 	return map_file(c->stages, mi, fn, opt, out);
 }
@@ -279,6 +289,7 @@ int64_t mpb_format_paf(const mp_idx_t *mi, const mp_mapopt_t *opt, const char *q
 int mpb_nasw_batch(mpb_ctx_t *c, const ns_opt_t *opt, int32_t n, const mpb_dp_problem_t *prob, mpb_dp_result_t *rst)
 {
 	if (!c) return -1;
+	if (bad_ie_coef(opt->ie_coef)) return -3;
 	MPB_CUDA_OK(cudaSetDevice(c->device));
 	// pack the host sequences the way the genome is stored, so that the same kernels serve both paths
 	int64_t nt_tot = 0, aa_tot = 0;

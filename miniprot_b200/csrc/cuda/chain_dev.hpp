@@ -7,7 +7,9 @@
 namespace mpb {
 namespace cuda {
 
-constexpr int CHAIN_STACK = 1100; // pending ranges of the flag sort per problem (<= 4 significant key bytes)
+// pending ranges of the flag sort per problem: the sort works depth first, every pass pops one range and pushes at most 255
+// (its buckets of more than 64 items), and a 64-bit key has 8 digits: 8 * 255 + 1 is the worst case for any input size
+constexpr int CHAIN_STACK = 2048;
 
 // score fill of the problems list[0..n_prob) (list == NULL: problems 0..n_prob-1), per-anchor state in global memory
 void chain_launch_fill(cudaStream_t st, const int32_t *list, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, int n_prob, const chn::Par &par, int32_t *f,

@@ -46,6 +46,8 @@ namespace cuda {
 // `d_aa` the residue buffer their aa_off refer to.  jobs[].{g_start,dir,comp,nl,al,aa_off,flag,io} must be set.
 void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_opt_t *base, std::vector<DpDev> &jobs, DpSet &out);
 
+int nasw_check_ie_coef(float ie_coef); // 0 if the extension length penalty fits the kernels' step table
+
 // chaining stage over many independent problems (chain_kernels.cu)
 struct ChainPar { int32_t max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc; float chn_coef_log; int32_t is_spliced, kmer, bbit; };
 

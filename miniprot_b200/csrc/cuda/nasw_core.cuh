@@ -181,7 +181,7 @@ NSW_HD int ext_len_penalty(float ie_coef, int x)
 // The length penalty pen(x) = (int)(ie_coef*log2(x) + .5) (x = i - 3*al) is a non-decreasing step function of x with a
 // few dozen steps below 2^31, so the host tabulates where it steps (with the reference's exact FP32 arithmetic) and the
 // device only advances an index: thr[k] = smallest x with pen(x) > pen(thr[k-1]), val[k] = pen(thr[k]).
-constexpr int PEN_STEPS = 160;
+constexpr int PEN_STEPS = 256;
 struct PenTable { int32_t n; int32_t thr[PEN_STEPS]; int32_t val[PEN_STEPS]; };
 
 inline void pen_table_build(float ie_coef, PenTable &t) // host only
@@ -203,12 +203,20 @@ inline void pen_table_build(float ie_coef, PenTable &t) // host only
 }
 
 // extension bookkeeping of one problem (nasw-sse.c:423-433): fed one finished row at a time
+// The row maximum travels through the columns together with the column it was first seen in: best = H_adjusted * 2^cb +
+// (2^cb - 1 - column), cb = code_bits(al): 12 bits as long as the columns fit (the int16 score then has 19 bits of room),
+// 15 bits for extensions over up to 32767 residues (32767 * 2^15 still fits an int32).
+NSW_HD int code_bits(int al) { return al <= 4095 ? 12 : 15; }
+constexpr int CODE_MAX_AL = 32767;
+
 struct ExtTracker {
 	int max_sc, max_log, max_i, max_code;
 	int pen, pk, next_thr; // current penalty, index of the next table step, and the x at which it applies
+	int cb;                // width of the column code (code_bits)
 	bool stopped;
-	NSW_HD void init() { max_sc = INT32_MIN, max_log = INT32_MIN, max_i = -1, max_code = 0, pen = 0, pk = 0, next_thr = 2, stopped = false; }
-	// best = max over columns of (H_adjusted << 12 | (4095 - column)), padding columns carry code 0
+	NSW_HD void init(int code_bits_ = 12) { max_sc = INT32_MIN, max_log = INT32_MIN, max_i = -1, max_code = 0, pen = 0, pk = 0, next_thr = 2, stopped = false, cb = code_bits_; }
+	NSW_HD int aa_len(int al) const { return (max_i >= 0 && max_code != 0) ? ((1 << cb) - 1) - max_code + 1 : al + 1; }
+	// best = max over columns of (H_adjusted << cb | (2^cb - 1 - column)), padding columns carry code 0
 	NSW_HD void row(int i, int best, int pen_base /* 3*al */, const PenTable &pt, int xdrop)
 	{
 		const int x = i - pen_base;
@@ -216,9 +224,9 @@ struct ExtTracker {
 			while (pk < pt.n && x >= pt.thr[pk]) pen = pt.val[pk], ++pk;
 			next_thr = pk < pt.n ? pt.thr[pk] : INT32_MAX;
 		}
-		const int tsc = best >> 12, tlog = tsc - pen;
+		const int tsc = best >> cb, tlog = tsc - pen;
 		const bool better = !stopped && tlog > max_log;
-		max_sc = better ? tsc : max_sc, max_i = better ? i : max_i, max_code = better ? (best & 4095) : max_code;
+		max_sc = better ? tsc : max_sc, max_i = better ? i : max_i, max_code = better ? (best & ((1 << cb) - 1)) : max_code;
 		max_log = better ? tlog : max_log;
 		stopped = stopped || max_log - tlog > xdrop;
 	}
@@ -246,7 +254,7 @@ struct LaneGeom {            // where this lane sits in the problem
 template <int C, bool MULTI>
 struct ExtLane {
 	int Hr[3][C], Dr[3][C], A[C], B[C], Cc[C];
-	int code[C], bonus[C];
+	int code[C], bonus[C], cmul;
 	int Lr[3];
 	int outH, outI, outB;    // what the lane to the right receives next step
 	RowRec rec[2];           // records of the rows of this step (phase parity) and the next
@@ -258,9 +266,10 @@ struct ExtLane {
 		for (int k = 0; k < C; ++k) {
 			const int jg = g.col0 + k;
 			Hr[0][k] = Hr[1][k] = Hr[2][k] = Dr[0][k] = Dr[1][k] = Dr[2][k] = A[k] = B[k] = Cc[k] = NEG;
-			code[k] = jg < g.al ? 4095 - jg : 0;
+			code[k] = jg < g.al ? ((1 << code_bits(g.al)) - 1) - jg : 0;
 			bonus[k] = jg == g.al - 1 ? end_bonus : 0;
 		}
+		cmul = 1 << code_bits(g.al);
 		Lr[0] = Lr[1] = Lr[2] = NEG;
 		if (g.lane == 0 && g.pass == 0) Lr[0] = 0, Lr[1] = Lr[2] = -fs; // H(-1,-1) = 0, H(0,-1) = H(1,-1) = -fs, seen by row 2 only
 		outH = outI = NEG, outB = INT32_MIN;
@@ -293,7 +302,7 @@ struct ExtLane {
 #pragma unroll
 			for (int k = 0; k < C; ++k) {
 				hn[k] = cell_score(par, rc, ps[k], Hr[h1][k], Hr[h2][k], Hr[h3][k], Dr[h3][k], dn[k], A[k], B[k], Cc[k], l0, l1, l2, l3, it);
-				best = imax(best, (hn[k] + bonus[k]) * 4096 + code[k]);
+				best = imax(best, (hn[k] + bonus[k]) * cmul + code[k]);
 				l0 = hn[k], l1 = Hr[h1][k], l2 = Hr[h2][k], l3 = Hr[h3][k];
 			}
 #pragma unroll
@@ -403,7 +412,7 @@ struct Lane3 {
 	int H[3], D[3], A, B, Cc, L[3];
 	RowRec rec[6];
 	int oH[3], oI[3], oX[3], oS[3]; // per row of the macro-step: final H, insertion chain, (ext) running best / (tb) first-pass H, (tb) segment chain
-	int code, bonus, score;
+	int code, cmul, score; // code = bonus * cmul + column code: row maximum candidate = H * cmul + code
 	bool seg_start, end_col;
 
 	NSW_HD static int row_of(const Geo3 &g, int T, int r) { return 3 * (T - g.x) + 2 + r; }
@@ -415,7 +424,8 @@ struct Lane3 {
 		for (int k = 0; k < 3; ++k) H[k] = D[k] = L[k] = NEG, oH[k] = oI[k] = oS[k] = NEG, oX[k] = TB ? NEG : INT32_MIN;
 		A = B = Cc = NEG;
 		if (g.first) L[0] = 0, L[1] = L[2] = -fs; // H(-1,-1), H(0,-1), H(1,-1): seen by row 2 only (nasw-sse.c:253-258)
-		code = g.col < g.al ? 4095 - g.col : 0, bonus = g.col == g.al - 1 ? end_bonus : 0;
+		cmul = 1 << code_bits(g.al);
+		code = (g.col < g.al ? (cmul - 1) - g.col : 0) + (g.col == g.al - 1 ? end_bonus : 0) * cmul;
 		seg_start = slen > 0 && g.col % slen == 0, end_col = g.col == g.al - 1, score = NEG;
 		env.rec3(-g.x, rec[0], rec[1], rec[2]), env.rec3(1 - g.x, rec[3], rec[4], rec[5]);
 	}
@@ -438,7 +448,7 @@ struct Lane3 {
 		} else {
 			const int h = cell_score(par, rc, s, H[h1], H[h2], H[h3], D[h3], d_new, A, B, Cc, l0, l1, l2, l3, it);
 			H[h3] = h, D[h3] = d_new, oH[R] = h, oI[R] = it;
-			const int m = imax(rx, (h + bonus) * 4096 + code);
+			const int m = imax(rx, h * cmul + code);
 			oX[R] = live ? m : rx;
 		}
 	}
@@ -516,7 +526,7 @@ struct Lane3 {
 				} else {
 					const int h = cell_score(par, rc, s, H[h1], H[h2], H[h3], D[h3], d_new, A, B, Cc, l0, L[h1], L[h2], L[h3], it);
 					H[h3] = h, D[h3] = d_new;
-					oH[r] = h, oI[r] = it, oX[r] = imax(lx, (h + bonus) * 4096 + code);
+					oH[r] = h, oI[r] = it, oX[r] = imax(lx, h * cmul + code);
 				}
 				done |= 1u << r;
 			} else if (!TB) oX[r] = lx, done |= 1u << r; // dead columns only hand the row maximum on

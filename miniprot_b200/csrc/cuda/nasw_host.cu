@@ -53,6 +53,16 @@ static void fill_const(const ns_opt_t *o, NaswConst &c)
 	nsw::pen_table_build(o->ie_coef, c.pen);
 }
 
+// The extension length penalty reaches the kernels as a step table (nasw_core.cuh PenTable).  A coefficient so large that the
+// table cannot hold all its steps below 2^31 is refused up front (0 = fine).
+int nasw_check_ie_coef(float ie_coef)
+{
+	nsw::PenTable t;
+	nsw::pen_table_build(ie_coef, t);
+	if (t.n < nsw::PEN_STEPS) return 0;
+	return nsw::ext_len_penalty(ie_coef, 2147483646) == t.val[t.n - 1] ? 0 : -1;
+}
+
 // run jobs[lo, hi) as one sub-wave
 static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const NaswConst &cst, std::vector<DpDev> &jobs, size_t lo, size_t hi, DpSet &out)
 {
@@ -63,13 +73,16 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	int64_t rw_tot = 0, tb_tot = 0, cig_tot = 0, carry_tot = 0;
 	std::vector<PrepChunk> chunks;
 	bool wide3[2] = { false, false }; // does the widest block-wide class hold problems of more than one pass?
+	std::vector<int> unsupported;
 	std::vector<int> order[2][9]; // [is_tb][class]: 0..3 block-wide wavefront with 1/2/4/8 warps; 4..7 column passes C = 1/2/4/8; 8 multi-pass
 	for (int k = 0; k < n; ++k) {
 		DpDev &j = jobs[lo + k];
 		const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
-		if (!is_tb && j.al > 4095) { // the row maximum carries its column in 12 bits (nasw_core.cuh ExtTracker)
-			fprintf(stderr, "[miniprot_b200] extension over %d residues: more than 4095 columns are not supported by the extension kernels\n", j.al);
-			abort();
+		if (!is_tb && j.al > nsw::CODE_MAX_AL) { // the row maximum carries its column in at most 15 bits (nasw_core.cuh code_bits): the problem is not
+			// run and reports nt_len = -1, which the caller treats as "this alignment failed" (the region is dropped with a warning)
+			unsupported.push_back(k);
+			j.C = 0, j.pad_ = 32, j.rw_off = 0, j.tb_off = j.cig_off = 0, j.cig_cap = 0, j.carry_off = 0;
+			continue;
 		}
 		const bool v3 = use_v3(j.al, j.nl);
 		const int nw = v3_warps(j.al);
@@ -213,6 +226,11 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	for (int k = 0; k < n; ++k) {
 		const DpDev &j = jobs[lo + k];
 		out.score[lo + k] = ho[k].x, out.nt_len[lo + k] = ho[k].y, out.aa_len[lo + k] = ho[k].z;
+		if (!unsupported.empty() && std::find(unsupported.begin(), unsupported.end(), k) != unsupported.end()) {
+			out.score[lo + k] = INT32_MIN, out.nt_len[lo + k] = -1, out.aa_len[lo + k] = 0;
+			out.cig_off[lo + k + 1] = (int64_t)out.cig.size();
+			continue;
+		}
 		if (j.cig_cap > 0 && ho[k].w > 0) {
 			out.cig.insert(out.cig.end(), hc + off, hc + off + ho[k].w);
 			off += ho[k].w;

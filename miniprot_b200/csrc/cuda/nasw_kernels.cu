@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_ext_kernel(const DpDev *
 	Par par;
 	par.go = cst.go, par.ge = cst.ge, par.io = job.io, par.fs = cst.fs, par.gei_stop = cst.fs;
 	ExtTracker trk;
-	trk.init();
+	trk.init(code_bits(g.al));
 	DevEnv env;
 	env.rec = rec + job.rw_off * 2, env.nl = g.nl, env.prof = prof + lane * C, env.Wp = Wp, env.cy = carry + job.carry_off;
 
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_ext_kernel(const DpDev *
 	if (lane == 31) {
 		int4 r;
 		r.x = trk.max_sc, r.y = trk.max_i + 1;
-		r.z = (trk.max_i >= 0 && trk.max_code != 0) ? 4095 - trk.max_code + 1 : g.al + 1;
+		r.z = trk.aa_len(g.al);
 		r.w = 0;
 		out[jid] = r;
 	}
@@ -305,7 +305,9 @@ struct WarpTracker {
 	bool stopped;
 	int n_ring, i_base;                   // rows [i_base, i_base + n_ring) wait in the ring
 	int pen, pk, next_thr;                // per lane: lane r follows the rows i_base + r of successive batches
-	__device__ __forceinline__ void init() { max_sc = INT32_MIN, max_log = INT32_MIN, max_i = -1, max_code = 0, stopped = false, n_ring = 0, i_base = 2, pen = 0, pk = 0, next_thr = 2; }
+	int cb;                               // width of the column code in a row maximum (nasw_core.cuh code_bits)
+	__device__ __forceinline__ void init(int code_bits_) { max_sc = INT32_MIN, max_log = INT32_MIN, max_i = -1, max_code = 0, stopped = false, n_ring = 0, i_base = 2, pen = 0, pk = 0, next_thr = 2, cb = code_bits_; }
+	__device__ __forceinline__ int aa_len(int al) const { return (max_i >= 0 && max_code != 0) ? ((1 << cb) - 1) - max_code + 1 : al + 1; }
 	// the ring is [slot][lane]: every lane of the warp stores its own value (no divergent branch on the critical path) and
 	// only lane 31's column -- the last column of the problem -- is read back.  ring_w = address of (slot 0, this lane),
 	// ring_r = address of (slot = this lane, lane 31)
@@ -320,7 +322,7 @@ struct WarpTracker {
 				while (pk < pt.n && x >= pt.thr[pk]) pen = pt.val[pk], ++pk;
 				next_thr = pk < pt.n ? pt.thr[pk] : INT32_MAX;
 			}
-			const int tsc = best >> 12, tlog = valid ? tsc - pen : INT32_MIN;
+			const int tsc = best >> cb, tlog = valid ? tsc - pen : INT32_MIN;
 			int pm = tlog; // inclusive prefix maximum over the batch
 #pragma unroll
 			for (int d = 1; d < 32; d <<= 1) {
@@ -333,7 +335,7 @@ struct WarpTracker {
 			const int bm = __shfl_sync(0xffffffffu, pm, last);
 			if (bm > max_log) {
 				const int w = __ffs(__ballot_sync(0xffffffffu, lane <= last && tlog == bm)) - 1;
-				max_log = bm, max_sc = __shfl_sync(0xffffffffu, tsc, w), max_code = __shfl_sync(0xffffffffu, best & 4095, w), max_i = i_base + w;
+				max_log = bm, max_sc = __shfl_sync(0xffffffffu, tsc, w), max_code = __shfl_sync(0xffffffffu, best & ((1 << cb) - 1), w), max_i = i_base + w;
 			}
 			stopped = sm != 0;
 		}
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 	Par par;
 	par.go = cst.go, par.ge = cst.ge, par.io = job.io, par.fs = cst.fs, par.gei_stop = cst.fs;
 	WarpTracker trk; // meaningful in the warp that owns the last column (of the last pass)
-	trk.init();
+	trk.init(code_bits(job.al));
 	int tb_score = NEG;
 	for (int pass = 0; pass < n_pass; ++pass) {
 	const bool last_pass = pass == n_pass - 1, carry_in = MP && pass > 0 && x == 0, carry_out = MP && !last_pass && x == Wp - 1;
@@ -493,7 +495,7 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 	} else if (x == Wp - 1) {
 		int4 r;
 		r.x = trk.max_sc, r.y = trk.max_i + 1;
-		r.z = (trk.max_i >= 0 && trk.max_code != 0) ? 4095 - trk.max_code + 1 : job.al + 1;
+		r.z = trk.aa_len(job.al);
 		r.w = 0;
 		out[jid] = r;
 	}

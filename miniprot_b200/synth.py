@@ -202,6 +202,11 @@ CONFIGS = {
     "C3": SynthSpec(3_000_000_000, 20000, 0.8, 50000, 13),
     "C4": SynthSpec(2_000_000_000, 5000, 0.8, 20000, 14, min_exons=4, max_exons=8, long_intron=(50_000, 150_000)),
     "C5": SynthSpec(100_000_000, 1000, 0.6, 5000, 15, fs_per_base=0.0067),
+    # cut-down shapes of C3 / C4 for the parity tests (same generator, same options as the full configs):
+    #   C3s: 1 Gbp, so that every protein has >= 16384 anchors (the large chaining class) and -I gives bw ~ 1.2e5
+    #   C4s: 400 kbp slots, one 50-150 kbp intron per gene, for the -G x -e sweep
+    "C3s": SynthSpec(1_000_000_000, 2000, 0.8, 50000, 13),
+    "C4s": SynthSpec(120_000_000, 300, 0.8, 20000, 14, ctg_len=40_000_000, min_exons=4, max_exons=8, long_intron=(50_000, 150_000)),
     "tiny": SynthSpec(2_000_000, 40, 0.8, 2000, 7, ctg_len=700_000),
     "tiny5": SynthSpec(2_000_000, 40, 0.6, 2000, 8, ctg_len=700_000, fs_per_base=0.0067),
     "small": SynthSpec(20_000_000, 300, 0.8, 5000, 9, ctg_len=7_000_000),

@@ -54,7 +54,7 @@ void run_ext(const Problem &P, int *score, int *nt_len, int *aa_len)
 	const int Wp = 32 * C, n_pass = (P.W8 + Wp - 1) / Wp, T = P.nl > 2 ? P.nl - 2 + 32 : 0;
 	std::vector<int> prof(22 * Wp), cy((size_t)(P.nl + 1) * 3);
 	ExtTracker trk;
-	trk.init();
+	trk.init(code_bits(P.al));
 	PenTable pt;
 	pen_table_build(P.ie_coef, pt);
 	for (int pass = 0; pass < n_pass; ++pass) {
@@ -91,7 +91,7 @@ void run_ext(const Problem &P, int *score, int *nt_len, int *aa_len)
 		trk = trks[31];
 	}
 	*score = trk.max_sc, *nt_len = trk.max_i + 1;
-	*aa_len = (trk.max_i >= 0 && trk.max_code != 0) ? 4095 - trk.max_code + 1 : P.al + 1;
+	*aa_len = trk.aa_len(P.al);
 }
 
 template <int C, bool MULTI>
@@ -178,7 +178,7 @@ void run_v3(const Problem &P, int *score, int *nt_len, int *aa_len, std::vector<
 	std::vector<Geo3> g((size_t)Wp);
 	std::vector<EmuEnv> env((size_t)Wp);
 	ExtTracker trk; // fed by the last column of the last pass
-	trk.init();
+	trk.init(code_bits(P.al));
 	std::vector<uint16_t> tb(TB ? (size_t)n_pass * Trows * Wp : 1, 0xffff);
 	struct Carry { int h, i, x, s; };
 	std::vector<Carry> carry((size_t)P.nl + 2, Carry{ NEG, NEG, NEG, NEG }); // what the last column of a pass leaves for the next pass, per row
@@ -271,7 +271,7 @@ void run_v3(const Problem &P, int *score, int *nt_len, int *aa_len, std::vector<
 	} else {
 		const ExtTracker &t = trk;
 		*score = t.max_sc, *nt_len = t.max_i + 1;
-		*aa_len = (t.max_i >= 0 && t.max_code != 0) ? 4095 - t.max_code + 1 : P.al + 1;
+		*aa_len = t.aa_len(P.al);
 	}
 }
 
