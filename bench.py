@@ -1,17 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- the protein-to-genome mapping hot path on N B200s (BASELINE.json metric: proteins/s, DP Gcell/s).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|small|tiny]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C5|C4s|C3s|small|tiny]
 
 One "step" = one pass of the hot path (seed + chain + refine + nasw DP waves + host bookkeeping) over one batch of
-synthetic proteins of the named workload.  N>1 is launched by torchrun, one rank per GPU: rank 0 builds the index,
-ONE NCCL broadcast puts ki / kb / packed genome into every GPU's HBM, every rank then maps its own shard of
-queries (weak scaling: fixed proteins per GPU) with no further communication.
+synthetic proteins of the named workload (C2 = BASELINE.json configs[1]: 100 Mbp genome, 1000 proteins of ~400 aa per GPU).
+N>1 is launched by torchrun, one rank per GPU: rank 0 loads the index, ONE NCCL broadcast puts ki / kb / packed genome
+into every GPU's HBM, every rank then maps its own shard of queries (weak scaling) with no further communication.
 
-JSON line (rank 0): metric proteins/s; `value` = mapping with the index resident in HBM and the parsed proteins in
-host memory (mpb_map_batch); `e2e` = the reference-facing call on files (mpb_map_file: FASTA in, PAF out, every
-host<->device copy inside); `roofline` for the dominant kernel; `cpu_baseline` = the reference CLI on this box.
-`--impl reference` times the unmodified reference (oracle/_ref/miniprot -t<all cores>) on the same workload.
+Both arms time MAPPING with the index already loaded (ours: resident in HBM; reference: resident in host memory), on the same
+proteins: the N shards of 1000 proteins each.
+
+  ours       `value`  = mpb_map_batch: parsed proteins in host memory -> regions (index resident in HBM)
+             `e2e`    = mpb_map_file: FASTA file in -> PAF file out, every host<->device copy inside the timed region
+  reference  `value` = `e2e` = the unmodified reference's own mp_map_file (oracle/_ref/libref.so, compiled from /root/reference by
+             oracle/Makefile, all host threads) on the concatenation of the same N shards, FASTA in -> PAF out, called in-process
+             with its index loaded once before the timed region.
+
+What a process pays once (context creation, index load, upload / broadcast) is reported separately under `process`.
+The PAF of EVERY rank is compared with the reference's output for that rank's shard; a mismatch fails the run.
 """
 from __future__ import annotations
 
@@ -29,7 +36,10 @@ sys.path.insert(0, ROOT)
 from miniprot_b200 import synth  # noqa: E402
 
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "miniprot")
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libref.so")
 CACHE = os.environ.get("MPB_BENCH_DIR", "/tmp/mpb_bench")
+PHASES = ["S1_seed_chain", "H1_regions", "S2_refine", "H2_plan", "S3_dp_waves", "H3_finish"]
+WORKLOAD_OPTS = {"C3": "-I", "C3s": "-I"}  # reference CLI options that belong to a workload (BASELINE.json configs[2])
 
 
 def read_fasta(path):
@@ -62,7 +72,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         if not self.rows:
@@ -75,7 +85,7 @@ class ClockSampler(threading.Thread):
 
 
 def prepare(workload, rank, world):
-    """Synthetic inputs + prebuilt .mpi index (rank 0 writes, others wait at the barrier outside)."""
+    """Synthetic inputs (rank 0 writes genome, planted proteins and every rank's query shard; the others wait outside)."""
     spec = synth.CONFIGS[workload]
     d = os.path.join(CACHE, workload)
     if rank == 0:
@@ -85,27 +95,118 @@ def prepare(workload, rank, world):
     return spec, d
 
 
-def run_reference(args, spec, d, mpi):
-    """--impl reference: the unmodified reference CLI on this box's host cores, same workload, same metric."""
-    prot = synth.shard_queries(spec, d, 0)
-    n_prot = len(read_fasta(prot)[0])
+def workload_text(name, spec, n_per_gpu, world):
+    return (f"{name}: {spec.genome_len} bp genome, {world} x {n_per_gpu} proteins ~400 aa (one shard per GPU), identity {spec.identity}, "
+            f"options '{WORKLOAD_OPTS.get(name, '')}'")
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the reference, in-process (oracle/_ref/libref.so: every symbol of the unmodified reference renamed ref_*)
+class RefLib:
+    def __init__(self):
+        import miniprot_b200 as mp  # only for the ctypes mirrors of the option structs (same layout: miniprot.h:36-77)
+
+        self.mp = mp
+        self.L = C.CDLL(REF_LIB)
+        self.L.ref_mp_start()
+        C.c_int32.in_dll(self.L, "ref_mp_verbose").value = 1
+        self.L.ref_mp_idx_load.restype = C.c_void_p
+        self.L.ref_mp_idx_load.argtypes = [C.c_char_p, C.c_void_p, C.c_int32]
+        self.L.ref_mp_map_file.restype = C.c_int32
+        self.L.ref_mp_map_file.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int]
+        self.L.ref_mp_idx_destroy.argtypes = [C.c_void_p]
+        self.L.ref_mp_mapopt_set_max_intron.argtypes = [C.c_void_p, C.c_int64]
+        self.libc = C.CDLL(None)
+        self.mi = None
+
+    def load(self, path, threads):
+        io = self.mp.IdxOpt()
+        self.L.ref_mp_idxopt_init(C.byref(io))
+        t0 = time.perf_counter()
+        self.mi = self.L.ref_mp_idx_load(path.encode(), C.byref(io), threads)
+        if not self.mi:
+            raise RuntimeError(f"reference cannot load {path}")
+        return time.perf_counter() - t0
+
+    def mapopt(self, workload, l_seq):
+        mo = self.mp.MapOpt()
+        self.L.ref_mp_mapopt_init(C.byref(mo))
+        if WORKLOAD_OPTS.get(workload) == "-I":
+            self.L.ref_mp_mapopt_set_max_intron(C.byref(mo), l_seq)
+        return mo
+
+    def map_file(self, prot, out_path, mo, threads):
+        """ref mp_map_file writes to stdout: point fd 1 at out_path for the duration of the call.  Returns seconds."""
+        sys.stdout.flush()
+        self.libc.fflush(None)
+        saved = os.dup(1)
+        fd = os.open(out_path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        os.dup2(fd, 1)
+        os.close(fd)
+        try:
+            t0 = time.perf_counter()
+            rc = self.L.ref_mp_map_file(self.mi, prot.encode(), C.byref(mo), threads)
+            self.libc.fflush(None)
+            dt = time.perf_counter() - t0
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        if rc != 0:
+            raise RuntimeError("reference mp_map_file failed")
+        return dt
+
+    def close(self):
+        if self.mi:
+            self.L.ref_mp_idx_destroy(self.mi)
+            self.mi = None
+
+
+def ensure_ref_index(spec, d, cores):
+    g = os.path.join(d, spec.tag() + ".fa")
+    mpi = os.path.join(d, spec.tag() + ".ref.mpi")
+    if not os.path.exists(mpi):
+        subprocess.run([REF_BIN, f"-t{cores}", "-d", mpi + ".tmp", g], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        os.replace(mpi + ".tmp", mpi)
+    return mpi
+
+
+def run_reference(args):
+    """--impl reference: the unmodified reference's mp_map_file on this box's host cores, same proteins, index preloaded."""
+    world = max(args.gpus, 1)
     cores = os.cpu_count() or 1
-    cmd = [REF_BIN, f"-t{cores}", mpi, prot]
+    if not os.path.exists(REF_LIB):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref.so is not built (run __graft_entry__.build() where /root/reference exists)"}))
+        return
+    spec, d = prepare(args.workload, 0, world)
+    mpi = ensure_ref_index(spec, d, cores)
+    shards = [synth.shard_queries(spec, d, r) for r in range(world)]
+    allp = os.path.join(d, f"{spec.tag()}.all{world}.faa")
+    with open(allp, "w") as o:
+        for s in shards:
+            o.write(open(s).read())
+    n_prot = len(read_fasta(allp)[0])
+    ref = RefLib()
+    t_load = ref.load(mpi, cores)
+    l_seq = os.path.getsize(os.path.join(d, spec.tag() + ".fa"))  # only used by -I workloads (set from the genome size, options.c:31)
+    mo = ref.mapopt(args.workload, l_seq)
+    out = os.path.join(d, "ref.all.paf")
     for _ in range(args.warmup):
-        subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
-    dt = (time.perf_counter() - t0) / args.steps
+        ref.map_file(allp, out, mo, cores)
+    dts = [ref.map_file(allp, out, mo, cores) for _ in range(args.steps)]
+    ref.close()
+    dt = sum(dts) / len(dts)
     v = n_prot / dt
     print(json.dumps({
         "impl": "reference", "metric": "proteins/s", "value": v, "unit": "proteins/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {spec.genome_len} bp genome, {n_prot} proteins, defaults", "index": "prebuilt .mpi (load time inside the step)"},
-        "cpu_baseline": {"value": v, "unit": "proteins/s", "cores": cores, "kind": "reference", "sample": f"all {n_prot} proteins, {args.steps} runs of miniprot -t{cores}"},
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16 (SSE2, 8 lanes)", "data": "synthetic",
+        "config": {"workload": workload_text(args.workload, spec, n_prot // world, world), "timed": "mp_map_file in-process (FASTA in, PAF out), index resident in host memory"},
+        "process": {"index_load_s": round(t_load, 3), "note": "mp_idx_load of the prebuilt .mpi, once, outside the timed region"},
+        "cpu_baseline": {"value": v, "unit": "proteins/s", "cores": cores, "kind": "reference",
+                         "sample": f"all {n_prot} proteins ({world} shards), mp_map_file with {cores} threads, {args.steps} timed passes of {dt:.2f} s"},
         "e2e": {"value": v, "unit": "proteins/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -118,16 +219,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", 0))
 
     if args.impl == "reference":
-        if rank != 0:
-            return
-        spec, d = prepare(args.workload, 0, 1)
-        g = os.path.join(d, spec.tag() + ".fa")
-        mpi = os.path.join(d, spec.tag() + ".ref.mpi")
-        if not os.path.exists(mpi):
-            subprocess.run([REF_BIN, f"-t{os.cpu_count()}", "-d", mpi, g], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        run_reference(args, spec, d, mpi)
+        if rank == 0:
+            run_reference(args)
         return
 
+    t_proc = time.perf_counter()
     import numpy as np
     import torch
     import miniprot_b200 as mp
@@ -144,24 +240,31 @@ def main():
     L.mpb_event_end_ms.argtypes = [C.c_void_p]
     L.mpb_map_batch.argtypes = [C.c_void_p, C.POINTER(mp.Idx), C.POINTER(mp.MapOpt), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mpb_regs_free.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
+    cores = os.cpu_count() or 1
 
     spec, d = prepare(args.workload, rank, world)
     g = os.path.join(d, spec.tag() + ".fa")
     mpi = os.path.join(d, spec.tag() + ".mpi")
-    t_idx = time.perf_counter()
+    t_build = 0.0
     if rank == 0 and not os.path.exists(mpi):
-        mi0 = mp.idx_load(g, os.cpu_count() or 8)
+        t0 = time.perf_counter()
+        mi0 = mp.idx_load(g, cores)
         L.mp_idx_dump((mpi + ".tmp").encode(), mi0)
         os.replace(mpi + ".tmp", mpi)
         L.mp_idx_destroy(mi0)
+        t_build = time.perf_counter() - t0
     if dist:
         dist.barrier()
+    t0 = time.perf_counter()
+    ctx = mp.Context(local)  # pins this rank's host threads to the GPU's NUMA node (MPB_AFFINITY=0 disables)
+    t_ctx = time.perf_counter() - t0
+    t0 = time.perf_counter()
     mi = mp.idx_load(mpi)  # host copy: contig table, block offsets, packed genome for the host-side statistics
-    t_idx = time.perf_counter() - t_idx
-    ctx = mp.Context(local)
+    t_load = time.perf_counter() - t0
     nb = mp.n_bucket(mi.contents.opt)
     n_kb, l_seq = mi.contents.n_kb, mi.contents.nt.contents.l_seq
     bcast_ms = None
+    t0 = time.perf_counter()
     if dist:
         # the ONE collective of the path: NCCL broadcast of the read-only index from rank 0 over NVLink
         ki = torch.empty(nb + 1, dtype=torch.int64, device=dev)
@@ -184,11 +287,14 @@ def main():
         assert L.mpb_idx_attach_device(ctx.h, mi, ki.data_ptr(), kb.data_ptr(), sq.data_ptr()) == 0
     else:
         assert L.mpb_idx_upload(ctx.h, mi) == 0
+    t_up = time.perf_counter() - t0
 
     prot = synth.shard_queries(spec, d, rank)
     names, seqs = read_fasta(prot)
     n = len(seqs)
     mo = mp.mapopt()
+    if WORKLOAD_OPTS.get(args.workload) == "-I":
+        L.mp_mapopt_set_max_intron(mo, l_seq)
     c_seqs = (C.c_char_p * n)(*[s.encode() for s in seqs])
     c_names = (C.c_char_p * n)(*[s.encode() for s in names])
     c_lens = (C.c_int32 * n)(*[len(s) for s in seqs])
@@ -204,6 +310,8 @@ def main():
         mp.map_file(ctx, mi, prot, out_paf, mo)
 
     def timed(fn, steps):
+        """K steps between barriers + device synchronisation; CUDA events on the context's stream and the host clock around
+        them (a step ends with host bookkeeping after the last kernel, so the larger of the two closes the bracket)."""
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
@@ -214,26 +322,62 @@ def main():
         ms = L.mpb_event_end_ms(ctx.h)
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
-        ms = max(ms, wall)  # a step ends with host bookkeeping after the last kernel: the wall clock closes the bracket
+        mine = max(ms, wall)
+        ms = mine
         if dist:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            t = torch.tensor([mine], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms
+        return ms, mine
 
+    t0 = time.perf_counter()
+    step_e2e()  # first pass of this process: grows the arenas (cudaMalloc), loads the kernels
+    t_first = time.perf_counter() - t0
     for _ in range(max(args.warmup, 3)):
         step_resident()
     ctx.reset_stats()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = timed(step_resident, args.steps)
+    ms, ms_mine = timed(step_resident, args.steps)
     st = ctx.stats()
     step_e2e()
     ctx.reset_stats()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e, ms_e2e_mine = timed(step_e2e, args.steps)
     st2 = ctx.stats()
     sampler.stop_flag = True
+    int_peak = None
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import int_peak as ip
+        int_peak = ip.measure(ctx)
+
+    # ---- parity, EVERY rank: this rank's PAF against the reference's mp_map_file on the same shard (the checker only)
+    parity, cpu = None, None
+    if os.path.exists(REF_LIB) and os.path.exists(REF_BIN):
+        if rank == 0:
+            ensure_ref_index(spec, d, cores)
+        if dist:
+            dist.barrier()
+        try:
+            os.sched_setaffinity(0, range(cores))  # the context pinned this process to the GPU's NUMA node; the checker may use every core
+        except Exception:
+            pass
+        ref = RefLib()
+        thr = max(cores // world, 1)
+        ref.load(os.path.join(d, spec.tag() + ".ref.mpi"), thr)
+        ref_out = os.path.join(d, f"ref.rank{rank}.paf")
+        ref_dt = ref.map_file(prot, ref_out, ref.mapopt(args.workload, l_seq), thr)
+        ref.close()
+        parity = open(out_paf, "rb").read() == open(ref_out, "rb").read()
+        cpu = {"value": n / ref_dt, "unit": "proteins/s", "cores": thr, "kind": "reference",
+               "sample": f"the {n} proteins of rank 0's shard, reference mp_map_file in-process with {thr} threads, index resident, {ref_dt:.2f} s"}
+    per_rank = [[ms_mine / args.steps, ms_e2e_mine / args.steps, 1.0 if parity else 0.0 if parity is not None else -1.0] + [w / args.steps for w in st.ms_wall]]
+    if dist:
+        t = torch.tensor(per_rank[0], dtype=torch.float64, device=dev)
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [[float(x) for x in a.tolist()] for a in allt]
 
     tot_prot = n * world
     value = tot_prot / (ms / args.steps / 1e3)
@@ -245,65 +389,80 @@ def main():
             dist.destroy_process_group()
         return
 
-    # parity gate + CPU baseline (reference CLI on this box, bounded sample)
-    cores = os.cpu_count() or 1
-    cpu = {"value": None, "unit": "proteins/s", "cores": cores, "kind": "reference", "sample": "reference binary not present"}
-    parity = None
-    if os.path.exists(REF_BIN):
-        ref_mpi = os.path.join(d, spec.tag() + ".ref.mpi")
-        if not os.path.exists(ref_mpi):
-            subprocess.run([REF_BIN, f"-t{cores}", "-d", ref_mpi, g], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        t0 = time.perf_counter()
-        ref = subprocess.run([REF_BIN, f"-t{cores}", ref_mpi, prot], check=True, capture_output=True).stdout
-        dt = time.perf_counter() - t0
-        cpu = {"value": n / dt, "unit": "proteins/s", "cores": cores, "kind": "reference",
-               "sample": f"all {n} proteins of rank 0's shard, miniprot -t{cores}, prebuilt .mpi, {dt:.2f} s wall (index load included)"}
-        parity = open(out_paf, "rb").read() == ref
-
+    parity_all = None if any(r[2] < 0 for r in per_rank) else all(r[2] > 0.5 for r in per_rank)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    # Dominant kernel by time: the score-only nasw extension kernel (nasw_v3_kernel<NW,false>).  Its algorithmic HBM traffic is
-    # ~0, so the HBM roofline is reported for the traceback kernels (nasw_v3_kernel<NW,true>: 2 B per DP cell written
-    # once), and the integer rate for both.  achieved = algorithmic bytes of one step / sum of the traceback launches' CUDA-event
-    # durations of that step (events on the launching side streams; each bracket also holds the CIGAR backtrack kernel that
-    # follows); traffic = DRAM bytes of the same launches from the committed ncu capture, both divided by the launches per step.
-    tb_gbs = (st.dp_cells_tb * 2 / 1e9) / (st.ms_dp_tb / 1e3) if st.ms_dp_tb > 0 else 0.0
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_v6.json")))
-        if args.workload == "C2":
-            traffic = tr["tb_traffic_bytes_per_step"] / tr["tb_launches_per_step"]
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": "nasw_v3_kernel<NW,true> (traceback; 8 launches per step)", "achieved": tb_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": tb_gbs / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": st.dp_cells_tb * 2 / args.steps / 8,
-                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-                "note": "nasw is integer-issue / latency bound, not HBM bound (SURVEY 8d tension): see int_rate, DESIGN.md 4 and profiles/README.md"}
-    int_rate = {
-        "ext_gcell_per_s": st.dp_cells_ext / st.ms_dp_ext / 1e6 if st.ms_dp_ext > 0 else None,
-        "tb_gcell_per_s": st.dp_cells_tb / st.ms_dp_tb / 1e6 if st.ms_dp_tb > 0 else None,
-        "ext_int_ops_per_cell": 32, "tb_int_ops_per_cell": 46}
+
+    # ---- rooflines.  Kernel times are CUDA events on the stream each class is launched on.
+    CLS = ["v3<1>", "v3<2>", "v3<4>", "v3<8>", "cols<1>", "cols<2>", "cols<4>", "cols<8>", "cols<8,multi>"]
+
+    def cls_rows(b):
+        rows = []
+        for c in range(9):
+            if st.n_class[b][c]:
+                rows.append({"kernel": ("nasw_tb " if b else "nasw_ext ") + CLS[c], "launches_per_step": st.n_class[b][c] / args.steps,
+                             "ms_per_launch": st.ms_class[b][c] / st.n_class[b][c], "gcell_per_launch": st.cells_class[b][c] / st.n_class[b][c] / 1e9})
+        return rows
+    ext_rows, tb_rows = cls_rows(0), cls_rows(1)
+    # HBM roofline: the traceback kernels write 2 B per DP cell once; the class with the most cells is quoted
+    roofline = {"bound": "hbm", "kernel": None, "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None}
+    if tb_rows:
+        top = max(tb_rows, key=lambda r: r["gcell_per_launch"] * r["launches_per_step"])
+        gbs = top["gcell_per_launch"] * 2 / (top["ms_per_launch"] / 1e3)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            if args.workload == "C2":
+                traffic = tr.get(top["kernel"], {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roofline.update({"kernel": top["kernel"] + " (global alignment with traceback; 2 B per DP cell written once)", "achieved": gbs, "frac": gbs / hbm_peak,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": top["gcell_per_launch"] * 2e9, "ms_per_launch": top["ms_per_launch"],
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)"})
+    # integer roofline of the dominant kernel by time (score-only extension): 32 int16 operations per cell against
+    # the measured fused add-max rate of this device (tools/int_peak.py, run above)
+    roofline_int = None
+    if ext_rows and int_peak:
+        top = max(ext_rows, key=lambda r: r["ms_per_launch"] * r["launches_per_step"])
+        ach = top["gcell_per_launch"] * 32e9 / (top["ms_per_launch"] / 1e3)
+        pk32, pk16 = int_peak["viaddmnmx_s32"]["int_ops_per_s"], int_peak["viaddmnmx_s16x2"]["int_ops_per_s"]
+        roofline_int = {"bound": "int", "kernel": top["kernel"] + " (score-only extension)", "achieved": ach / 1e12, "peak": pk16 / 1e12, "unit": "Tint16-op/s",
+                        "frac": ach / pk16, "peak_32bit_lanes": pk32 / 1e12, "frac_of_32bit_peak": ach / pk32, "ops_per_cell": 32, "ms_per_launch": top["ms_per_launch"],
+                        "note": "peak = measured VIADDMNMX.S16x2 issue rate x 4 ops (tools/int_peak.py); the wave is bounded by the row-to-row latency of its longest problems"}
+    walls = sorted(r[0] for r in per_rank)
+    slow = max(range(world), key=lambda r: per_rank[r][0])
     print(json.dumps({
         "metric": "proteins/s", "value": value, "unit": "proteins/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16 scores (int32 lanes)",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16 scores",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {spec.genome_len} bp genome, {n} proteins per GPU ~400 aa, identity {spec.identity}, defaults",
-                   "l2": "index (ki+kb+genome) and DP working set exceed the 126 MB L2", "index_build_or_load_s": round(t_idx, 2),
-                   "nccl_index_broadcast_ms": bcast_ms, "paf_identical_to_reference": parity},
+        "config": {"workload": workload_text(args.workload, spec, n, world), "timed": "mapping with the index resident in HBM (value: mpb_map_batch; e2e: mpb_map_file, FASTA in, PAF out)",
+                   "l2": "index (ki+kb+genome, 315 MB at C2) and DP working set exceed the 126 MB L2; no flush needed",
+                   "paf_identical_to_reference": parity_all, "paf_identical_per_rank": [r[2] > 0.5 for r in per_rank]},
+        "process": {"ctx_create_s": round(t_ctx, 3), "index_load_s": round(t_load, 3), "index_upload_or_broadcast_s": round(t_up, 3), "index_build_s": round(t_build, 2),
+                    "nccl_index_broadcast_ms": bcast_ms, "first_pass_s": round(t_first, 3), "since_start_s": round(time.perf_counter() - t_proc, 1),
+                    "note": "paid once per process, outside the timed region (the reference arm reports its own index_load_s)"},
         "dp_gcell_per_s": cells / (ms / args.steps / 1e3) / 1e9 * world,
         "stage_ms_per_step": {"seed": st.ms_seed / args.steps, "chain": st.ms_chain / args.steps, "refine": st.ms_refine / args.steps,
-                              "dp_ext": st.ms_dp_ext / args.steps, "dp_tb": st.ms_dp_tb / args.steps},
-        "wall_ms_per_step": dict(zip(["S1_seed_chain", "H1_regions", "S2_refine", "H2_plan", "S3_dp_waves", "H3_finish"], [w / args.steps for w in st.ms_wall])),
+                              "dp_prep": st.ms_prep / args.steps, "dp_waves_wall": st.ms_dp_wave / args.steps, "dp_backtrack": st.ms_bt / args.steps},
+        "nasw_kernels": ext_rows + tb_rows,
+        "wall_ms_per_step": dict(zip(PHASES, [w / args.steps for w in st.ms_wall])),
+        "ranks": {"ms_per_step": {"min": walls[0], "median": walls[len(walls) // 2], "max": walls[-1]}, "per_rank_ms_per_step": [round(r[0], 3) for r in per_rank],
+                  "per_rank_e2e_ms_per_step": [round(r[1], 3) for r in per_rank], "slowest_rank": slow,
+                  "slowest_rank_wall_ms_per_step": dict(zip(PHASES, [round(x, 3) for x in per_rank[slow][3:]]))},
         "e2e": {"value": e2e, "unit": "proteins/s", "h2d_bytes_per_step": st2.h2d_bytes // args.steps, "d2h_bytes_per_step": st2.d2h_bytes // args.steps,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(st.kernel_launches), "roofline": roofline, "int_rate": int_rate, "cpu_baseline": cpu, "clocks": sampler.summary()}))
+        "gpu_launches": int(st.kernel_launches), "roofline": roofline, "roofline_int": roofline_int, "int_peak": int_peak, "cpu_baseline": cpu,
+        "clocks": sampler.summary()}))
     ctx.close()
     if dist:
         dist.destroy_process_group()
+    if parity_all is False:
+        sys.stderr.write("bench.py: PAF differs from the reference on at least one rank\n")
+        sys.exit(1)
 
 
 if __name__ == "__main__":

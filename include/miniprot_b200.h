@@ -261,6 +261,11 @@ int32_t mpb_map_file_path(mpb_ctx_t *ctx, const mp_idx_t *mi, const char *fn, co
 void mpb_event_begin(mpb_ctx_t *ctx);                     /* CUDA-event bracket on the context's stream */
 double mpb_event_end_ms(mpb_ctx_t *ctx);
 
+/* Measured integer-issue peak of the device: variant 0 = 32-bit fused add-max, 1 = 32-bit three-way max, 2 = packed
+ * int16x2 add-max, 3 = packed int16x2 three-way max, 4 = packed add-max with the zero floor.  Outputs: thread-level instructions
+ * per second and elementary integer operations per second (an add-max or three-way max = 2, packed forms = 4). */
+int mpb_int_peak(mpb_ctx_t *ctx, int variant, double *thread_instr_per_s, double *int_ops_per_s);
+
 /* counters since context creation (for bench.py): */
 typedef struct {
 	int64_t dp_cells_ext, dp_cells_tb; /* sum nl*al over executed DP problems */
@@ -270,6 +275,14 @@ typedef struct {
 	int64_t h2d_bytes, d2h_bytes;
 	double ms_seed, ms_chain, ms_refine, ms_dp_ext, ms_dp_tb; /* CUDA-event time per stage (kernels of one stage may overlap) */
 	double ms_wall[6]; /* host wall clock per dispatcher phase: S1, H1, S2, H2, S3 (three DP waves incl. their host steps), H3 */
+	/* nasw kernels by class: [0] score-only extension, [1] global alignment with traceback; classes 0..3 = block-wide
+	 * wavefront kernels with 1 / 2 / 4 / 8 warps per problem, 4..8 = the column-pass family.  ms = CUDA-event time of the
+	 * DP kernel alone on its own stream (classes of one wave overlap in time), cells = sum nl*al, n = launches. */
+	double ms_class[2][9];
+	int64_t cells_class[2][9], n_class[2][9];
+	double ms_bt;      /* CIGAR backtrack kernels */
+	double ms_dp_wave; /* device wall time of the DP waves: fork of the class streams -> last join */
+	double ms_prep;    /* row preparation kernels */
 } mpb_stats_t;
 void mpb_get_stats(const mpb_ctx_t *ctx, mpb_stats_t *st);
 void mpb_reset_stats(mpb_ctx_t *ctx);

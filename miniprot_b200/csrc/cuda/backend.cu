@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <stdio.h>
 #include <mutex>
+#include <sched.h>
 #include "ctx.hpp"
 #include "stages_dev.hpp"
 #include "../align.hpp"
@@ -104,6 +105,46 @@ bool bad_ie_coef(float ie_coef)
 	return true;
 }
 
+// Host threads of a rank stay on the NUMA node its GPU hangs off (pinned staging buffers, the worker pool of the host phases
+// and the driver's own threads then never cross the socket interconnect; with one rank per GPU on a two-socket box the ranks
+// of the far socket otherwise straggle).  MPB_AFFINITY=0 leaves the affinity of the calling thread alone.
+void pin_to_device_node(int device)
+{
+	if (const char *e = getenv("MPB_AFFINITY")) if (atoi(e) == 0) return;
+	char bus[64];
+	if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return;
+	for (char *q = bus; *q; ++q) if (*q >= 'A' && *q <= 'F') *q = (char)(*q - 'A' + 'a');
+	char path[256];
+	snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+	FILE *fp = fopen(path, "r");
+	if (!fp) return;
+	int node = -1;
+	if (fscanf(fp, "%d", &node) != 1) node = -1;
+	fclose(fp);
+	if (node < 0) return;
+	snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+	fp = fopen(path, "r");
+	if (!fp) return;
+	char list[4096];
+	const size_t got = fread(list, 1, sizeof(list) - 1, fp);
+	fclose(fp);
+	list[got] = 0;
+	cpu_set_t cur, want;
+	CPU_ZERO(&want);
+	if (sched_getaffinity(0, sizeof(cur), &cur) != 0) return;
+	int n_set = 0;
+	for (char *q = list; *q;) { // "0-31,64-95"
+		char *end;
+		long a = strtol(q, &end, 10), b = a;
+		if (end == q) break;
+		if (*end == '-') b = strtol(end + 1, &end, 10);
+		for (long c = a; c <= b && c < CPU_SETSIZE; ++c) if (CPU_ISSET((int)c, &cur)) CPU_SET((int)c, &want), ++n_set;
+		q = *end == ',' ? end + 1 : end;
+		if (*end != ',') break;
+	}
+	if (n_set > 0) sched_setaffinity(0, sizeof(want), &want);
+}
+
 std::mutex g_default_mu;
 mpb_ctx_t *g_default_ctx = 0;
 std::vector<mpb_ctx_s*> g_all_ctx;
@@ -130,6 +171,7 @@ mpb_ctx_t *mpb_ctx_create(int device)
 	}
 	if (device < 0 || device >= n_dev) { fprintf(stderr, "[miniprot_b200] bad device %d (have %d)\n", device, n_dev); return 0; }
 	MPB_CUDA_OK(cudaSetDevice(device));
+	pin_to_device_node(device);
 	mpb_ctx_s *c = new mpb_ctx_s();
 	c->device = device;
 	MPB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -146,7 +188,11 @@ mpb_ctx_t *mpb_ctx_create(int device)
 		MPB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
 		MPB_CUDA_OK(cudaEventCreate(&c->ev_k0[i]));
 		MPB_CUDA_OK(cudaEventCreate(&c->ev_k1[i]));
+		MPB_CUDA_OK(cudaEventCreate(&c->ev_km[i]));
 	}
+	MPB_CUDA_OK(cudaEventCreate(&c->ev_w0));
+	MPB_CUDA_OK(cudaEventCreate(&c->ev_w1));
+	MPB_CUDA_OK(cudaEventCreate(&c->ev_p0));
 	memset(&c->stats, 0, sizeof(c->stats));
 	c->stages = new CudaStages(c);
 	{
@@ -174,7 +220,8 @@ void mpb_ctx_destroy(mpb_ctx_t *c)
 	c->h_out.release(), c->h_cigar.release();
 	for (PinBuf &b : c->h_c) b.release();
 	cudaEventDestroy(c->ev0), cudaEventDestroy(c->ev1), cudaEventDestroy(c->ev_fork), cudaEventDestroy(c->ev_fork2);
-	for (int i = 0; i < mpb_ctx_s::N_SIDE; ++i) cudaStreamDestroy(c->side[i]), cudaEventDestroy(c->ev_join[i]), cudaEventDestroy(c->ev_k0[i]), cudaEventDestroy(c->ev_k1[i]);
+	for (int i = 0; i < mpb_ctx_s::N_SIDE; ++i) cudaStreamDestroy(c->side[i]), cudaEventDestroy(c->ev_join[i]), cudaEventDestroy(c->ev_k0[i]), cudaEventDestroy(c->ev_k1[i]), cudaEventDestroy(c->ev_km[i]);
+	cudaEventDestroy(c->ev_w0), cudaEventDestroy(c->ev_w1), cudaEventDestroy(c->ev_p0);
 	cudaStreamDestroy(c->stream);
 	delete c->stages;
 	delete c;

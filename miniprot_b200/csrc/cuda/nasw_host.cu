@@ -132,6 +132,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	ctx->stats.h2d_bytes += sizeof(DpDev) * n + sizeof(int) * flat.size() + sizeof(PrepChunk) * chunks.size();
 	const DpDev *dj = ctx->b_jobs.as<DpDev>();
 	const int *dord = ctx->b_order.as<int>();
+	MPB_CUDA_OK(cudaEventRecord(ctx->ev_p0, st));
 	nasw_launch_prep(st, dj, ctx->b_chunks.as<PrepChunk>(), (int)chunks.size(), packed, cst, ctx->b_rw.as<int4>());
 	ctx->stats.kernel_launches += 1;
 	static const int Cs[9] = { 1, 2, 4, 8, 1, 2, 4, 8, 16 }; // warps per problem (classes 0..3) or columns per lane (4..8)
@@ -148,6 +149,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	for (int b = 0; b < 2; ++b)
 		for (int c = 8; c >= 0; --c)
 			if (count[b][c]) groups.push_back(Group{ b * 9 + c, b, c, first[b][c], count[b][c] });
+	MPB_CUDA_OK(cudaEventRecord(ctx->ev_w0, st));
 	MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
 	// the widest extension class needs EMPTY SMs (one block fills an SM's shared memory): it forks at once, everybody else
 	// a few microseconds later, behind a spacer on the main stream
@@ -172,9 +174,11 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 			}
 		} else if (b == 0) {
 			nasw_launch_ext(ss, Cs[c], dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>());
+			MPB_CUDA_OK(cudaEventRecord(ctx->ev_km[g.sid], ss));
 			ctx->stats.kernel_launches += 1;
 		} else {
 			nasw_launch_tb(ss, Cs[c], dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_carry.as<int>(), ctx->b_tb.as<uint16_t>());
+			MPB_CUDA_OK(cudaEventRecord(ctx->ev_km[g.sid], ss));
 			nasw_launch_bt(ss, dj, ord, cnt, ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
 			ctx->stats.kernel_launches += 2;
 		}
@@ -182,6 +186,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		MPB_CUDA_OK(cudaEventRecord(ctx->ev_join[g.sid], ss));
 		MPB_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_join[g.sid], 0));
 	}
+	MPB_CUDA_OK(cudaEventRecord(ctx->ev_w1, st));
 	// results: scores first; the CIGARs are packed back to back on the device and only what was produced is copied
 	if (cig_tot) {
 		ctx->b_cigpack.reserve(sizeof(uint32_t) * (size_t)(cig_tot + 4));
@@ -202,11 +207,24 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		MPB_CUDA_OK(cudaMemcpyAsync(ctx->h_cigar.p, ctx->b_cigpack.p, sizeof(uint32_t) * (size_t)cig_used, cudaMemcpyDeviceToHost, st));
 		MPB_CUDA_OK(cudaStreamSynchronize(st));
 	}
+	{
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ctx->ev_w0, ctx->ev_w1);
+		ctx->stats.ms_dp_wave += ms;
+		cudaEventElapsedTime(&ms, ctx->ev_p0, ctx->ev_w0);
+		ctx->stats.ms_prep += ms;
+	}
 	static const bool trace = getenv("MPB_TRACE") != 0; // per-class durations of every wave on stderr (diagnostics only)
 	for (const Group &g : groups) { // sum of the classes' own durations (they overlap in time; the wave's wall time is what the step pays)
-		float ms = 0;
+		float ms = 0, ms_dp = 0;
 		cudaEventElapsedTime(&ms, ctx->ev_k0[g.sid], ctx->ev_k1[g.sid]);
+		cudaEventElapsedTime(&ms_dp, ctx->ev_k0[g.sid], ctx->ev_km[g.sid]);
 		(g.b == 0 ? ctx->stats.ms_dp_ext : ctx->stats.ms_dp_tb) += ms;
+		ctx->stats.ms_class[g.b][g.c] += ms_dp, ctx->stats.n_class[g.b][g.c] += 1, ctx->stats.ms_bt += ms - ms_dp;
+		for (size_t k = 0; k < g.count; ++k) {
+			const DpDev &jj = jobs[lo + flat[g.first + k]];
+			ctx->stats.cells_class[g.b][g.c] += (int64_t)jj.nl * jj.al;
+		}
 		if (trace) {
 			int hist[5] = { 0 };
 			double hc[5] = { 0 }, cells = 0;

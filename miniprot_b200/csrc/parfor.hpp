@@ -8,6 +8,8 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <sched.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace mpb {
@@ -42,8 +44,20 @@ public:
 private:
 	HostPool()
 	{
-		int t = (int)std::thread::hardware_concurrency();
-		t = t < 2 ? 1 : t > 16 ? 16 : t;
+		// MPB_HOST_THREADS, else the cores this process may run on (the affinity mask set when the GPU context was created)
+		// shared among the ranks of the node, two hardware threads per core, at most 16
+		int t = 0;
+		if (const char *e = getenv("MPB_HOST_THREADS")) t = atoi(e);
+		if (t <= 0) {
+			cpu_set_t cur;
+			t = (int)std::thread::hardware_concurrency();
+			if (sched_getaffinity(0, sizeof(cur), &cur) == 0 && CPU_COUNT(&cur) > 0) t = CPU_COUNT(&cur);
+			int ranks = 1;
+			if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
+			if (ranks > 1) t = t * 2 / ranks / 2; // the mask covers one of two sockets when there are several ranks
+			t = t > 16 ? 16 : t;
+		}
+		t = t < 2 ? 1 : t > 64 ? 64 : t;
 		for (int i = 1; i < t; ++i) th_.emplace_back([this] { loop(); });
 	}
 	~HostPool()

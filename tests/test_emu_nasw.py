@@ -56,6 +56,18 @@ def test_emu_matches_oracle(hc, Ccols):
                 assert a[:3] == b[:3], (it, flag, len(nt), len(aa), a[:3], b[:3])
 
 
+def test_emu_extension_wider_than_4095_columns(hc):
+    """The row maximum carries its column in 15 bits once the extension has more than 4095 columns (nasw_core.cuh code_bits)."""
+    rng = np.random.default_rng(77)
+    tab, mat = ol.ref_tables(), ol.default_mat()
+    par = dict(ol.DEFAULT_NASW)
+    nt, aa = ol.random_dp_problem(rng, al_max=4400, flank=30, intron_max=200, p_sub=0.25)
+    while len(aa) < 4200:
+        nt, aa = ol.random_dp_problem(rng, al_max=4400, flank=30, intron_max=200, p_sub=0.25)
+    for flag, Ccols in ((4, 0), (2, 8)):
+        assert ol.ora_nasw(tab, nt, aa, flag, mat, par)[:3] == emu(hc, nt, aa, flag, Ccols, mat, par)[:3]
+
+
 def test_emu_xdrop_and_tiny(hc):
     rng = np.random.default_rng(4)
     tab, mat = ol.ref_tables(), ol.default_mat()

@@ -1,0 +1,82 @@
+"""Drop-in boundary on the GPU: the reference's UNMODIFIED callers linked against libminiprot_b200.so.
+
+  oracle/_ref/miniprot_b200_cli = /root/reference/main.c   + libminiprot_b200.so   (oracle/Makefile)
+  oracle/_ref/example_b200      = /root/reference/example.c + libminiprot_b200.so  (mp_map one query at a time, reads r->p->cigar)
+Their stdout must equal that of the same two programs built from the reference's own objects (oracle/_ref/miniprot,
+oracle/_ref/example_ref).  Plus the reference-named single-problem entry points called directly: ns_global_gs16[b], mp_map."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import miniprot_b200 as mp
+import oracle_lib as ol
+from miniprot_b200 import synth
+
+pytestmark = pytest.mark.gpu
+REFD = os.path.join(ol.ORA_DIR, "_ref")
+CLI, EX, EX_REF = (os.path.join(REFD, x) for x in ("miniprot_b200_cli", "example_b200", "example_ref"))
+DATA = os.path.join(REFD, "data")
+need_bins = pytest.mark.skipif(not all(os.path.exists(x) for x in (CLI, EX, EX_REF, ol.REF_BIN)), reason="drop-in binaries not built (oracle/Makefile)")
+
+
+def out(cmd):
+    return subprocess.run(cmd, check=True, capture_output=True).stdout
+
+
+@need_bins
+def test_reference_cli_on_our_library(tmp_path):
+    g, p = os.path.join(DATA, "DPP3-hs.gen.fa.gz"), os.path.join(DATA, "DPP3-mm.pep.fa.gz")
+    for args in ((), ("-j2",), ("-G", "2k"), ("-u", "--outn=3")):
+        assert out([CLI, "-t4", *args, g, p]) == out([ol.REF_BIN, "-t4", *args, g, p]), args
+    g, p = synth.generate(synth.CONFIGS["small"], str(tmp_path))
+    mpi = str(tmp_path / "ours.mpi")
+    subprocess.run([CLI, "-t8", "-d", mpi, g], check=True, capture_output=True)  # index built and dumped by our library ...
+    assert out([ol.REF_BIN, "-t8", mpi, p]) == out([CLI, "-t8", mpi, p])        # ... restored by the reference, and by us
+    assert out([CLI, "-t8", "-I", g, p]) == out([ol.REF_BIN, "-t8", "-I", g, p])
+
+
+@need_bins
+def test_reference_example_on_our_library(tmp_path):
+    g, p = synth.generate(synth.CONFIGS["tiny"], str(tmp_path))
+    assert out([EX, g, p]) == out([EX_REF, g, p])
+    g, p = os.path.join(DATA, "DPP3-hs.gen.fa.gz"), os.path.join(DATA, "DPP3-mm.pep.fa.gz")
+    assert out([EX, g, p]) == out([EX_REF, g, p])
+
+
+class NsRst(C.Structure):  # ns_rst_t (nasw.h:73-78)
+    _fields_ = [("n_cigar", C.c_int32), ("m_cigar", C.c_int32), ("nt_len", C.c_int32), ("aa_len", C.c_int32), ("score", C.c_int32), ("cigar", C.POINTER(C.c_uint32))]
+
+
+def test_ns_global_gs16b_single_calls():
+    """The reference-named DP entry points, one problem per call (a GPU batch of one), against the oracle."""
+    L = mp.lib()
+    rng = np.random.default_rng(11)
+    opt = mp.nsopt()
+    tab_syms = (("nt4", "ns_tab_nt4"), ("aa20", "ns_tab_aa20"), ("aa13", "ns_tab_aa13"), ("codon", "ns_tab_codon"), ("codon13", "ns_tab_codon13"))
+    tab = ol.OraTab()
+    for f, sym in tab_syms:
+        setattr(tab, f, C.addressof(C.c_uint8.in_dll(L, sym)))
+    par = dict(go=opt.go, ge=opt.ge, io=opt.io, fs=opt.fs, xdrop=opt.xdrop, end_bonus=opt.end_bonus, sp=tuple(opt.sp), sp_null_bonus=opt.sp_null_bonus, ie_coef=opt.ie_coef)
+    for fn in ("ns_global_gs16b", "ns_global_gs16"):
+        f = getattr(L, fn)
+        f.restype = None
+        for flag in (1, 2, 4):
+            nt, aa = ol.random_dp_problem(rng, al_max=70, flank=50)
+            while len(nt) < 3:
+                nt, aa = ol.random_dp_problem(rng, al_max=70, flank=50)
+            opt.flag = flag
+            r = NsRst()
+            args = [None, nt.ctypes.data_as(C.c_char_p), C.c_int32(len(nt)), aa, C.c_int32(len(aa)), C.byref(opt)]
+            if fn.endswith("b"):
+                args.append(None)
+            f(*args, C.byref(r))
+            w = ol.ora_nasw(tab, nt, aa, flag, opt._mat_keepalive, par)
+            if flag == 1:
+                assert w[0] == r.score and w[3] == [r.cigar[k] for k in range(r.n_cigar)] and (r.nt_len, r.aa_len) == (len(nt), len(aa)), fn
+                L.mpb_free(r.cigar)
+            else:
+                assert w[:3] == (r.score, r.nt_len, r.aa_len), (fn, flag)
+    opt.flag = 0

@@ -84,6 +84,23 @@ def test_nasw_xdrop_long_tail(ctx):
         assert ol.ora_nasw(tab, nt, aa, flag, mat, _par(opt))[:3] == g[:3]
 
 
+def test_nasw_extension_wider_than_4095_columns(ctx):
+    """Extensions over more than 4095 residues (a protein whose first pinned anchor lies deep inside): the row maximum
+    carries a 15-bit column code there (nasw_core.cuh code_bits).  Reference behaviour: nasw-sse.c:435-443 has no limit."""
+    rng = np.random.default_rng(4242)
+    opt = mp.nsopt()
+    tab, mat = product_tables(), opt._mat_keepalive
+    probs = []
+    for flag, al in ((4, 4300), (2, 4500), (4, 4096), (2, 4095)):
+        nt, aa = ol.random_dp_problem(rng, al_max=al, flank=40, intron_max=300, p_sub=0.25)
+        while len(aa) < al - 200:  # random_dp_problem draws the length from [1, al_max]
+            nt, aa = ol.random_dp_problem(rng, al_max=al, flank=40, intron_max=300, p_sub=0.25)
+        probs.append((nt, aa, flag, opt.io))
+    got = mp.nasw_batch(ctx, opt, probs)
+    for (nt, aa, flag, io), g in zip(probs, got):
+        assert ol.ora_nasw(tab, nt, aa, flag, mat, _par(opt))[:3] == g[:3], (flag, len(nt), len(aa))
+
+
 @pytest.mark.parametrize("mode", ["pre", "main", "refine"])
 def test_chain_batch_matches_oracle(ctx, mode):
     rng = np.random.default_rng({"pre": 31, "main": 32, "refine": 33}[mode])
