@@ -398,11 +398,11 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
 
     # ---- rooflines.  Kernel times are CUDA events on the stream each class is launched on.
-    CLS = ["v3<1>", "v3<2>", "v3<4>", "v3<8>", "cols<1>", "cols<2>", "cols<4>", "cols<8>", "cols<8,multi>"]
+    CLS = ["v3<1>", "v3<2>", "v3<4>", "v3<8>", "cols<1>", "cols<2>", "cols<4>", "cols<8>", "cols<8,multi>", "pair<1>", "pair<2>", "pair<4>", "pair<8>", "", "", ""]
 
     def cls_rows(b):
         rows = []
-        for c in range(9):
+        for c in range(16):
             if st.n_class[b][c]:
                 rows.append({"kernel": ("nasw_tb " if b else "nasw_ext ") + CLS[c], "launches_per_step": st.n_class[b][c] / args.steps,
                              "ms_per_launch": st.ms_class[b][c] / st.n_class[b][c], "gcell_per_launch": st.cells_class[b][c] / st.n_class[b][c] / 1e9})

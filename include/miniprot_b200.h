@@ -276,10 +276,11 @@ typedef struct {
 	double ms_seed, ms_chain, ms_refine, ms_dp_ext, ms_dp_tb; /* CUDA-event time per stage (kernels of one stage may overlap) */
 	double ms_wall[6]; /* host wall clock per dispatcher phase: S1, H1, S2, H2, S3 (three DP waves incl. their host steps), H3 */
 	/* nasw kernels by class: [0] score-only extension, [1] global alignment with traceback; classes 0..3 = block-wide
-	 * wavefront kernels with 1 / 2 / 4 / 8 warps per problem, 4..8 = the column-pass family.  ms = CUDA-event time of the
+	 * wavefront kernels with 1 / 2 / 4 / 8 warps per problem, 4..8 = the column-pass family, 9..12 = pair-lane kernels with
+	 * 1 / 2 / 4 / 8 warps per problem.  ms = CUDA-event time of the
 	 * DP kernel alone on its own stream (classes of one wave overlap in time), cells = sum nl*al, n = launches. */
-	double ms_class[2][9];
-	int64_t cells_class[2][9], n_class[2][9];
+	double ms_class[2][16];
+	int64_t cells_class[2][16], n_class[2][16];
 	double ms_bt;      /* CIGAR backtrack kernels */
 	double ms_dp_wave; /* device wall time of the DP waves: fork of the class streams -> last join */
 	double ms_prep;    /* row preparation kernels */

@@ -72,7 +72,7 @@ class Stats(C.Structure):  # mpb_stats_t
                 ("n_anchors", C.c_int64), ("n_chain_problems", C.c_int64), ("n_refine_regions", C.c_int64),
                 ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("ms_seed", C.c_double),
                 ("ms_chain", C.c_double), ("ms_refine", C.c_double), ("ms_dp_ext", C.c_double), ("ms_dp_tb", C.c_double), ("ms_wall", C.c_double * 6),
-                ("ms_class", (C.c_double * 9) * 2), ("cells_class", (C.c_int64 * 9) * 2), ("n_class", (C.c_int64 * 9) * 2),
+                ("ms_class", (C.c_double * 16) * 2), ("cells_class", (C.c_int64 * 16) * 2), ("n_class", (C.c_int64 * 16) * 2),
                 ("ms_bt", C.c_double), ("ms_dp_wave", C.c_double), ("ms_prep", C.c_double)]
 
 

@@ -183,7 +183,7 @@ mpb_ctx_t *mpb_ctx_create(int device)
 	MPB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
 	for (int i = 0; i < mpb_ctx_s::N_SIDE; ++i) {
 		// (numerically lower = more urgent) widest extension class first, then the other extension classes, then the rest
-		const int prio = i == 3 ? prio_hi : i < 9 ? std::min(prio_hi + 1, prio_lo) : prio_lo;
+		const int prio = i < 13 ? prio_hi : prio_lo; // extension classes of a DP wave (stream ids 0..12) before everything else
 		MPB_CUDA_OK(cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, prio));
 		MPB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
 		MPB_CUDA_OK(cudaEventCreate(&c->ev_k0[i]));
@@ -229,7 +229,8 @@ void mpb_ctx_destroy(mpb_ctx_t *c)
 
 mpb_ctx_t *mpb_ctx_default(void)
 {
-	std::lock_guard<std::mutex> lk(g_default_mu);
+	static std::mutex once_mu; // not g_default_mu: mpb_ctx_create takes that one itself
+	std::lock_guard<std::mutex> lk(once_mu);
 	if (!g_default_ctx) {
 		int dev = 0;
 		if (const char *e = getenv("LOCAL_RANK")) dev = atoi(e);

@@ -6,8 +6,8 @@
 //                      ballots + chain_core.cuh::resolve_chunk() reproduce the order-dependent max_skip logic,
 //                      t[] marks go through memory exactly as in the reference.  Latency / integer bound; the
 //                      byte volume is tiny (20 B of scratch per anchor, chain.c:175-178).
-//   chain_bt_kernel    one thread per problem: backtrack with the reference's unstable sort order, compaction,
-//                      optional re-sort of the kept anchors (the pre-chain of map.c:186-192).
+//   chain_bt_*_kernel  one warp per problem: backtrack with the reference's unstable sort order (cycle chases and peeling on
+//                      lane 0, everything parallel shared by the lanes), compaction; the pre-chain's result by stream compaction.
 #include <cuda_runtime.h>
 #include "chain_core.cuh"
 #include "chain_dev.hpp"
@@ -195,19 +195,42 @@ __device__ void flag_sort_warp(uint64_t *rec, int n, KeyFn key, FlagRange<uint64
 		if (lane == 0) {
 			uint32_t acc = 0;
 			for (int k = 0; k < 256; ++k) ws->head[k] = acc, acc += ws->cnt[k], ws->tail[k] = acc;
+		}
+		__syncwarp();
+		{
+			// The cycle-leader permutation (ksort.h:133-146).  Its order defines the reference's tie order, so the chase of a
+			// cycle stays sequential (lane 0).  What the lanes share is the part that moves nothing: the run of items at the
+			// head of bucket k that already carry digit k is skipped 32 at a time (in a chaining problem most scores are equal --
+			// the floor score of isolated anchors -- and sit in one huge bucket that is almost entirely in place).
 			uint64_t *b = r.beg;
-			for (int k = 0; k < 256;) { // the cycle-leader permutation (ksort.h:133-146), sequential by definition
-				if (ws->head[k] == ws->tail[k]) { ++k; continue; }
-				int d = (int)((key(b[ws->head[k]]) >> shift) & 255);
-				if (d == k) { ++ws->head[k]; continue; }
-				uint64_t hand = b[ws->head[k]];
-				do {
-					const uint64_t next = b[ws->head[d]];
-					b[ws->head[d]++] = hand;
-					hand = next;
-					d = (int)((key(hand) >> shift) & 255);
-				} while (d != k);
-				b[ws->head[k]++] = hand;
+			for (int k = 0; k < 256; ++k) {
+				for (;;) {
+					const uint32_t h = ws->head[k], e = ws->tail[k];
+					if (h >= e) break;
+					const uint32_t idx = h + (uint32_t)lane;
+					const bool misplaced = idx < e && (int)((key(b[idx]) >> shift) & 255) != k;
+					const uint32_t mm = __ballot_sync(0xffffffffu, misplaced);
+					__syncwarp();
+					if (mm == 0) { // all of the next 32 (or all that are left) are in place
+						if (lane == 0) ws->head[k] = h + 32 < e ? h + 32 : e;
+						__syncwarp();
+						continue;
+					}
+					if (lane == 0) {
+						const uint32_t at = h + (uint32_t)(__ffs(mm) - 1); // items before it are in place: skipped
+						uint64_t hand = b[at];
+						int d = (int)((key(hand) >> shift) & 255);
+						ws->head[k] = at;
+						do {
+							const uint64_t next = b[ws->head[d]];
+							b[ws->head[d]++] = hand;
+							hand = next;
+							d = (int)((key(hand) >> shift) & 255);
+						} while (d != k);
+						b[ws->head[k]++] = hand;
+					}
+					__syncwarp();
+				}
 			}
 		}
 		__syncwarp();
@@ -420,24 +443,48 @@ __global__ void __launch_bounds__(32) chain_bt_smem_kernel(const int32_t *list, 
 	if (lane == 0) n_u_out[prob] = n_u, n_b_out[prob] = n_b;
 }
 
-// same for problems that do not fit in shared memory: one thread, everything in global memory
-__global__ void __launch_bounds__(32) chain_bt_kernel(const int32_t *list, int n_list, const int64_t *a_off, const int32_t *cnt, const uint64_t *a_all, Par par,
-                                                     int32_t *f_all, const int32_t *p_all, int32_t *t_all, int32_t *v_all, uint64_t *z_all,
-                                                     FlagRange<uint64_t> *stack_all, uint64_t *u_all, uint64_t *b_all, int32_t *n_u_out, int32_t *n_b_out, int resort)
+// Same for problems too large for shared memory (more than 16384 anchors: every pre-chain problem of a gigabase genome): one
+// WARP per problem, everything in global memory (L2).  The lanes share what is parallel -- gathering the (score, index)
+// records, the flag sort's histograms / range scans / skipping of items already in place, the compaction -- and lane 0 does what
+// is sequential by definition: the cycle chases of the sort and the best-first peeling, which only visits anchors of chains
+// above the floor score (a small fraction of a pre-chain problem).
+__global__ void __launch_bounds__(32) chain_bt_global_kernel(const int32_t *list, int n_list, const int64_t *a_off, const int32_t *cnt, const uint64_t *a_all, Par par,
+                                                            int32_t *f_all, const int32_t *p_all, int32_t *t_all, int32_t *v_all, uint64_t *z_all,
+                                                            FlagRange<uint64_t> *stack_all, uint64_t *u_all, uint64_t *b_all, int32_t *n_u_out, int32_t *n_b_out, int resort)
 {
-	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-	if (slot >= n_list) return;
-	const int prob = list[slot];
+	__shared__ WarpSortScratch ws;
+	if ((int)blockIdx.x >= n_list) return;
+	const int prob = list[blockIdx.x], lane = threadIdx.x;
 	const int64_t base = a_off[prob];
 	const int32_t n = cnt ? cnt[prob] : (int32_t)(a_off[prob + 1] - base);
-	int32_t n_b = 0, n_u = 0;
-	if (n > 0) {
-		n_u = backtrack_compact(par, n, a_all + base, f_all + base, p_all + base, t_all + base, v_all + base, z_all + base,
-		                        stack_all + (int64_t)prob * CHAIN_STACK, u_all + base, b_all + base, &n_b);
-		if (resort && n_b > 1)
-			flag_sort_by(b_all + base, b_all + base + n_b, [](const uint64_t &x) { return x; }, stack_all + (int64_t)prob * CHAIN_STACK);
+	int32_t *f = f_all + base, *t = t_all + base, *v = v_all + base;
+	const int32_t *pp = p_all + base;
+	uint64_t *z = z_all + base, *u = u_all + base, *b = b_all + base;
+	const uint64_t *a = a_all + base;
+	int32_t n_z = 0;
+	for (int32_t i0 = 0; i0 < n; i0 += 32) {
+		const int32_t i = i0 + lane;
+		const int32_t fi = i < n ? __ldcg(f + i) : 0;
+		const bool keep = i < n && fi >= par.min_sc;
+		if (i < n) t[i] = 0;
+		const uint32_t m = __ballot_sync(0xffffffffu, keep);
+		if (keep) z[n_z + __popc(m & ((1u << lane) - 1u))] = (uint64_t)(uint32_t)fi << 32 | (uint32_t)i;
+		n_z += __popc(m);
 	}
-	n_u_out[prob] = n_u, n_b_out[prob] = n_b;
+	__syncwarp();
+	int32_t n_u = 0, n_b = 0, n_v = 0;
+	FlagRange<uint64_t> *stack = stack_all + (int64_t)prob * CHAIN_STACK;
+	flag_sort_warp(z, n_z, [](const uint64_t &e) { return rec_key(e); }, stack, &ws, lane);
+	if (lane == 0 && n > 0) n_u = peel_chains<int32_t, true, int32_t, int32_t>(par, n_z, f, pp, t, v, z, stack, u, &n_v);
+	n_u = __shfl_sync(0xffffffffu, n_u, 0), n_v = __shfl_sync(0xffffffffu, n_v, 0);
+	__syncwarp();
+	if (resort) n_b = keep_filter_warp(n, n_v, v, t, a, b, lane); // pre-chain: accepted anchors in sorted order
+	else {
+		if (n > 0) compact_chains(n_u, a, f, v, z, stack, u, b, &n_b, lane, 32, [] { __syncwarp(); });
+		__syncwarp();
+		n_b = __shfl_sync(0xffffffffu, n_b, 0);
+	}
+	if (lane == 0) n_u_out[prob] = n_u, n_b_out[prob] = n_b;
 }
 
 void chain_launch_fill(cudaStream_t st, const int32_t *list, const int64_t *a_off, const int32_t *cnt, const uint64_t *a, int n_prob, const Par &par, int32_t *f, int32_t *p,
@@ -470,7 +517,7 @@ void chain_launch_bt(cudaStream_t st, const int32_t *list, int n_list, const int
                      const int32_t *p, int32_t *t, int32_t *v, void *z, void *stack, uint64_t *u, uint64_t *b, int32_t *n_u, int32_t *n_b, int resort)
 {
 	if (n_list > 0)
-		chain_bt_kernel<<<(n_list + 31) / 32, 32, 0, st>>>(list, n_list, a_off, cnt, a, par, f, p, t, v, (uint64_t*)z, (FlagRange<uint64_t>*)stack, u, b, n_u, n_b, resort);
+		chain_bt_global_kernel<<<n_list, 32, 0, st>>>(list, n_list, a_off, cnt, a, par, f, p, t, v, (uint64_t*)z, (FlagRange<uint64_t>*)stack, u, b, n_u, n_b, resort);
 }
 
 } // namespace cuda

@@ -11,7 +11,7 @@ struct mpb_ctx_s {
 	cudaEvent_t ev0 = 0, ev1 = 0;
 	// side streams: size classes of one DP wave (and independent stage pieces) run concurrently; each class is bounded
 	// by its longest problem, so serialising them on one stream would add the critical paths up
-	static const int N_SIDE = 18; // 0..8 are high-priority streams (extension classes of a DP wave: their long problems must be dispatched first; 3, the widest class, highest), 9..17 normal
+	static const int N_SIDE = 32; // 0..8 are high-priority streams (extension classes of a DP wave: their long problems must be dispatched first; 3, the widest class, highest), 9..17 normal
 	cudaStream_t side[N_SIDE] = {0};
 	cudaEvent_t ev_fork = 0, ev_fork2 = 0, ev_join[N_SIDE] = {0}, ev_k0[N_SIDE] = {0}, ev_k1[N_SIDE] = {0}, ev_km[N_SIDE] = {0};
 	cudaEvent_t ev_w0 = 0, ev_w1 = 0, ev_p0 = 0; // timing of a DP wave on the main stream: before the prep kernel, at the fork, after the last join

@@ -12,6 +12,7 @@
 #include <numeric>
 #include "ctx.hpp"
 #include "nasw_core.cuh"
+#include "nasw_pair.cuh"
 
 namespace mpb {
 namespace cuda {
@@ -42,6 +43,29 @@ static inline int v3_warps(int al)
 	return nw <= 1 ? 1 : nw <= 2 ? 2 : nw <= 4 ? 4 : 8;
 }
 
+// Pair-lane kernels (nasw_pair.cuh: two columns per thread as packed int16x2) serve every problem whose scores provably stay
+// inside their value domain and whose padded width fits 8 warps; MPB_NASW_KERNEL=v3|cols keeps them out (A/B measurements).
+struct PairLimits { int smin, smax, dmax, amax; };
+static PairLimits pair_limits(const ns_opt_t *o)
+{
+	PairLimits l;
+	l.smin = 127, l.smax = -128;
+	for (int a = 0; a < 22; ++a)
+		for (int b = 0; b < 22; ++b) { const int v = o->sc[a * 22 + b]; l.smin = std::min(l.smin, v), l.smax = std::max(l.smax, v); }
+	l.dmax = std::max({ o->sp[0], o->sp[1], o->sp[2], o->sp[3], o->sp[4], 0 });            // nasw-sse.c:120-127
+	l.amax = std::max({ o->sp[0] + 3 * std::max(o->sp[5], 0), o->sp[2], o->sp[3], 0 });   // nasw-sse.c:128-137
+	int dmin = std::min({ o->sp[0], o->sp[1], o->sp[2], o->sp[3], o->sp[4], o->sp[5] });
+	if (dmin < 0) l.dmax = 1 << 20; // negative splice penalties: not a case the value-domain argument covers
+	return l;
+}
+static inline bool use_pair(const DpDev &j, const ns_opt_t *o, const PairLimits &l)
+{
+	if (g_forced_family == 1 || g_forced_family == 2) return false;
+	const int W8 = (j.al + 7) / 8 * 8;
+	if (nsw::pair_warps_for(W8) == 0 || j.nl < 3) return false;
+	return nsw::pair_eligible(j.al, o->go, o->ge, j.io, o->fs, o->end_bonus, l.smin, l.smax, l.dmax, l.amax);
+}
+
 static void fill_const(const ns_opt_t *o, NaswConst &c)
 {
 	memcpy(c.mat, o->sc, 484);
@@ -64,17 +88,19 @@ int nasw_check_ie_coef(float ie_coef)
 }
 
 // run jobs[lo, hi) as one sub-wave
-static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const NaswConst &cst, std::vector<DpDev> &jobs, size_t lo, size_t hi, DpSet &out)
+static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const NaswConst &cst, const ns_opt_t *nso, std::vector<DpDev> &jobs, size_t lo, size_t hi, DpSet &out)
 {
 	const int n = (int)(hi - lo);
 	if (n == 0) return;
 	cudaStream_t st = ctx->stream;
 	const double t_in = mp_realtime();
 	int64_t rw_tot = 0, tb_tot = 0, cig_tot = 0, carry_tot = 0;
-	std::vector<PrepChunk> chunks;
+	std::vector<PrepChunk> chunks, pchunks; // row-record chunks of the 32-bit families, pair-record chunks of the pair-lane family
 	bool wide3[2] = { false, false }; // does the widest block-wide class hold problems of more than one pass?
 	std::vector<int> unsupported;
-	std::vector<int> order[2][9]; // [is_tb][class]: 0..3 block-wide wavefront with 1/2/4/8 warps; 4..7 column passes C = 1/2/4/8; 8 multi-pass
+	const PairLimits plim = pair_limits(nso);
+	constexpr int NCLS = 13;
+	std::vector<int> order[2][NCLS]; // [is_tb][class]: 0..3 block-wide wavefront with 1/2/4/8 warps; 4..7 column passes C = 1/2/4/8; 8 multi-pass; 9..12 pair-lane kernels with 1/2/4/8 warps
 	for (int k = 0; k < n; ++k) {
 		DpDev &j = jobs[lo + k];
 		const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
@@ -82,6 +108,23 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 			// run and reports nt_len = -1, which the caller treats as "this alignment failed" (the region is dropped with a warning)
 			unsupported.push_back(k);
 			j.C = 0, j.pad_ = 32, j.rw_off = 0, j.tb_off = j.cig_off = 0, j.cig_cap = 0, j.carry_off = 0;
+			continue;
+		}
+		if (use_pair(j, nso, plim)) { // pair-lane kernels: pair records (96 B per triple of rows), wavefront-major traceback of 64 columns per warp
+			const int W8 = (j.al + 7) / 8 * 8, pw = nsw::pair_warps_for(W8), K = nsw::pair_rec_slots(j.nl), n_macro = nsw::pair_n_macro(j.nl, W8);
+			j.C = 0, j.pad_ = 64 * pw;
+			j.rw_off = rw_tot, rw_tot += (int64_t)192 * nsw::pair_rec_blocks(j.nl); // two parities x blocks x 192 sixteen-byte fields, in units of 32 bytes
+			j.tb_off = j.cig_off = 0, j.cig_cap = 0, j.carry_off = 0;
+			if (is_tb) {
+				j.tb_off = tb_tot, tb_tot += (int64_t)3 * (n_macro + 2) * j.pad_;
+				j.cig_cap = j.nl + j.al + 4;
+				j.cig_off = cig_tot, cig_tot += j.cig_cap;
+			}
+			const int n_tri = 2 * K; // record indices 0 .. 2K-1 (the tail past the last real triple is never read unmasked)
+			for (int m = 0; m < n_tri; m += 1024) pchunks.push_back(PrepChunk{ k, m, std::min(1024, n_tri - m), 0 });
+			order[is_tb][9 + (pw == 1 ? 0 : pw == 2 ? 1 : pw == 4 ? 2 : 3)].push_back(k);
+			(is_tb ? ctx->stats.dp_cells_tb : ctx->stats.dp_cells_ext) += (int64_t)j.nl * j.al;
+			(is_tb ? ctx->stats.n_dp_tb : ctx->stats.n_dp_ext) += 1;
 			continue;
 		}
 		const bool v3 = use_v3(j.al, j.nl);
@@ -108,9 +151,9 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		(is_tb ? ctx->stats.n_dp_tb : ctx->stats.n_dp_ext) += 1;
 	}
 	std::vector<int> flat;
-	size_t first[2][9], count[2][9];
+	size_t first[2][NCLS], count[2][NCLS];
 	for (int b = 0; b < 2; ++b)
-		for (int c = 0; c < 9; ++c) {
+		for (int c = 0; c < NCLS; ++c) {
 			std::vector<int> &v = order[b][c];
 			std::stable_sort(v.begin(), v.end(), [&](int x, int y) { return jobs[lo + x].nl > jobs[lo + y].nl; });
 			first[b][c] = flat.size(), count[b][c] = v.size();
@@ -118,7 +161,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		}
 	ctx->b_jobs.reserve(sizeof(DpDev) * n);
 	ctx->b_order.reserve(sizeof(int) * (flat.size() + 1));
-	ctx->b_chunks.reserve(sizeof(PrepChunk) * (chunks.size() + 1));
+	ctx->b_chunks.reserve(sizeof(PrepChunk) * (chunks.size() + pchunks.size() + 1));
 	ctx->b_rw.reserve(32 * (size_t)(rw_tot + 4));
 	ctx->b_out.reserve(sizeof(int4) * n);
 	ctx->b_carry.reserve(sizeof(int) * (size_t)(carry_tot + 4));
@@ -128,46 +171,48 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	ctx->h_cigar.reserve(sizeof(uint32_t) * (size_t)(cig_tot + 4));
 	MPB_CUDA_OK(cudaMemcpyAsync(ctx->b_jobs.p, jobs.data() + lo, sizeof(DpDev) * n, cudaMemcpyHostToDevice, st));
 	MPB_CUDA_OK(cudaMemcpyAsync(ctx->b_order.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, st));
-	MPB_CUDA_OK(cudaMemcpyAsync(ctx->b_chunks.p, chunks.data(), sizeof(PrepChunk) * chunks.size(), cudaMemcpyHostToDevice, st));
-	ctx->stats.h2d_bytes += sizeof(DpDev) * n + sizeof(int) * flat.size() + sizeof(PrepChunk) * chunks.size();
+	if (!chunks.empty()) MPB_CUDA_OK(cudaMemcpyAsync(ctx->b_chunks.p, chunks.data(), sizeof(PrepChunk) * chunks.size(), cudaMemcpyHostToDevice, st));
+	if (!pchunks.empty())
+		MPB_CUDA_OK(cudaMemcpyAsync(ctx->b_chunks.as<PrepChunk>() + chunks.size(), pchunks.data(), sizeof(PrepChunk) * pchunks.size(), cudaMemcpyHostToDevice, st));
+	ctx->stats.h2d_bytes += sizeof(DpDev) * n + sizeof(int) * flat.size() + sizeof(PrepChunk) * (chunks.size() + pchunks.size());
 	const DpDev *dj = ctx->b_jobs.as<DpDev>();
 	const int *dord = ctx->b_order.as<int>();
 	MPB_CUDA_OK(cudaEventRecord(ctx->ev_p0, st));
 	nasw_launch_prep(st, dj, ctx->b_chunks.as<PrepChunk>(), (int)chunks.size(), packed, cst, ctx->b_rw.as<int4>());
-	ctx->stats.kernel_launches += 1;
-	static const int Cs[9] = { 1, 2, 4, 8, 1, 2, 4, 8, 16 }; // warps per problem (classes 0..3) or columns per lane (4..8)
+	nasw_launch_prep_pair(st, dj, ctx->b_chunks.as<PrepChunk>() + chunks.size(), (int)pchunks.size(), packed, cst, ctx->b_rw.as<int4>());
+	ctx->stats.kernel_launches += (chunks.empty() ? 0 : 1) + (pchunks.empty() ? 0 : 1);
+	static const int Cs[NCLS] = { 1, 2, 4, 8, 1, 2, 4, 8, 16, 1, 2, 4, 8 }; // warps per problem (classes 0..3, 9..12) or columns per lane (4..8)
 	// Scheduling of a big wave.  It is bounded by its longest extensions (100 k rows next to thousands of short problems):
-	//  * the extension classes run on high-priority streams and are ordered longest first, so those problems start at once;
-	//  * the widest class (8 warps that meet at a barrier every macro-step) loses half its speed when foreign warps share
-	//    its issue slots, and it holds only a handful of problems: its blocks get an SM each (residency cap, nasw_launch_v3).
-	// MPB_NASW_WSM=<warps per SM> caps every block-wide launch instead (measurements only).
+	//  * the extension classes run on high-priority streams and are ordered longest first, so those problems start at once.
+	// MPB_NASW_WSM=<warps per SM> caps the residency of the block-wide launches (measurements only).
 	static const int wsm_env = getenv("MPB_NASW_WSM") ? atoi(getenv("MPB_NASW_WSM")) : -1;
-	const bool big_wave = n >= 296;
 	// fork: every (kind, size class) runs on its own stream -- each is bounded by its longest problem
 	struct Group { int sid, b, c; size_t first, count; };
 	std::vector<Group> groups;
 	for (int b = 0; b < 2; ++b)
-		for (int c = 8; c >= 0; --c)
-			if (count[b][c]) groups.push_back(Group{ b * 9 + c, b, c, first[b][c], count[b][c] });
+		for (int c = NCLS - 1; c >= 0; --c)
+			if (count[b][c]) groups.push_back(Group{ b * NCLS + c, b, c, first[b][c], count[b][c] });
 	MPB_CUDA_OK(cudaEventRecord(ctx->ev_w0, st));
 	MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
-	// the widest extension class needs EMPTY SMs (one block fills an SM's shared memory): it forks at once, everybody else
-	// a few microseconds later, behind a spacer on the main stream
-	const bool head_start = big_wave && wsm_env < 0 && count[0][3] > 0 && count[0][3] <= 148;
-	if (head_start) {
-		nasw_launch_spacer(st, 40);
-		MPB_CUDA_OK(cudaEventRecord(ctx->ev_fork2, st));
-	}
 	for (const Group &g : groups) {
 		cudaStream_t ss = ctx->side[g.sid];
 		const int b = g.b, c = g.c, cnt = (int)g.count;
 		const int *ord = dord + g.first;
-		MPB_CUDA_OK(cudaStreamWaitEvent(ss, (head_start && !(b == 0 && c == 3)) ? ctx->ev_fork2 : ctx->ev_fork, 0));
+		MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
 		MPB_CUDA_OK(cudaEventRecord(ctx->ev_k0[g.sid], ss));
-		if (c < 4) {
-			nasw_launch_v3(ss, Cs[c], b == 1, dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>(),
-			               wsm_env >= 0 ? wsm_env : (big_wave && b == 0 && c == 3 && cnt <= 148) ? 8 : 0, ctx->b_carry.as<int>(), c == 3 && wide3[b]);
+		if (c >= 9) {
+			nasw_launch_pair(ss, Cs[c], b == 1, dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>());
 			ctx->stats.kernel_launches += 1;
+			MPB_CUDA_OK(cudaEventRecord(ctx->ev_km[g.sid], ss));
+			if (b == 1) {
+				nasw_launch_bt(ss, dj, ord, cnt, ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
+				ctx->stats.kernel_launches += 1;
+			}
+		} else if (c < 4) {
+			nasw_launch_v3(ss, Cs[c], b == 1, dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>(),
+			               wsm_env > 0 ? wsm_env : 0, ctx->b_carry.as<int>(), c == 3 && wide3[b]);
+			ctx->stats.kernel_launches += 1;
+			MPB_CUDA_OK(cudaEventRecord(ctx->ev_km[g.sid], ss));
 			if (b == 1) {
 				nasw_launch_bt(ss, dj, ord, cnt, ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
 				ctx->stats.kernel_launches += 1;
@@ -268,7 +313,7 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_
 	if (n == 0) return;
 	{
 		const char *e = getenv("MPB_NASW_KERNEL");
-		g_forced_family = !e ? 0 : strcmp(e, "cols") == 0 ? 1 : strcmp(e, "v3") == 0 ? 2 : 0;
+		g_forced_family = !e ? 0 : strcmp(e, "cols") == 0 ? 1 : strcmp(e, "v3") == 0 ? 2 : 0; // anything else: pair-lane kernels where eligible, block-wide otherwise
 	}
 	NaswConst cst;
 	fill_const(base, cst);
@@ -284,7 +329,7 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_
 			if (hi > lo && (tb_bytes + tbb > kTbBudget || rw_bytes + rwb > kRwBudget)) break;
 			tb_bytes += tbb, rw_bytes += rwb, ++hi;
 		}
-		run_subwave(ctx, packed, d_aa, cst, jobs, lo, hi, out);
+		run_subwave(ctx, packed, d_aa, cst, base, jobs, lo, hi, out);
 		lo = hi;
 	}
 }

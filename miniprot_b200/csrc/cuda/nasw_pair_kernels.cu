@@ -1,0 +1,354 @@
+// nasw_pair_kernels.cu -- the PAIR-LANE nasw kernels ("v4") for sm_100a: two protein columns per thread as packed int16x2
+// (VIADDMNMX.S16x2 / VIMNMX3.S16x2 / VIMNMX.S16x2 with predicates), see nasw_pair.cuh for the per-thread logic, the value
+// domain and the exactness argument.
+//
+//   nasw_prep_pair_kernel   packed genome -> pair records (one 96-byte record per triple of rows, entries paired with the row
+//                           three above: what a thread needs when its low column is on triple m and its high column on m-1)
+//   nasw_pair_kernel<NW,TB> one CTA of NW warps per problem, 64 columns in the first warp and 62 in every further one.
+//                           Inside a warp the wavefront moves by shuffles.  BETWEEN warps there is no block-wide barrier: the
+//                           last lane of a warp drops what its right neighbour needs (3 rows x 3..4 registers + the macro-step
+//                           number as a tag in every 16-byte chunk) into a ring of PAIR_SLOTS slots in shared memory; lane 0 of
+//                           the next warp is a RELAY -- it owns no columns, loads that slot straight into its own output registers
+//                           and so feeds lane 1 through the same shuffle as everybody else.  Warps run as far apart as the ring
+//                           allows, each at the speed of a single warp.
+//                           TB = false: score-only extension with the warp-parallel x-drop tracker (nasw_warp.cuh);
+//                           TB = true : global alignment, two traceback words per thread and row in one 32-bit store, in the
+//                           wavefront-major layout nasw_bt_kernel walks.
+#include <algorithm>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "nasw_pair.cuh"
+#include "nasw_dev.hpp"
+#include "nasw_warp.cuh"
+
+namespace mpb {
+namespace cuda {
+
+using namespace nsw;
+
+constexpr int PAIR_TRI = 1024;  // triples per prep CTA
+constexpr int PAIR_SLOTS = 8;   // depth of the ring between neighbouring warps (macro-steps a warp may run ahead of its right neighbour)
+constexpr int PAIR_PROF_HI = 22 * 128; // byte offset of the high-half profile table of a warp
+
+__device__ __forceinline__ int pair_job_code(const uint8_t *packed, const DpDev &j, int k)
+{
+	const int64_t g = j.g_start + (int64_t)j.dir * k;
+	int b = packed[g >> 1] >> ((g & 1) * 4) & 0xf;
+	if (j.comp) b = b < 4 ? 3 - b : b;
+	return b;
+}
+
+// One CTA per chunk of <= PAIR_TRI triples of one problem: phase 1 evaluates the per-row splice / codon rules (nasw-sse.c:91-210)
+// into shared memory with a halo, phase 2 combines them into the pair records, stored per parity of the triple index and
+// field-major (six arrays of 16-byte fields) so that the 32 lanes of a warp -- which are on triples two apart -- read 32
+// consecutive fields with each load.
+__global__ void __launch_bounds__(256) nasw_prep_pair_kernel(const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, NaswConst cst, uint4 *rec)
+{
+	__shared__ uint32_t w[3 * PAIR_TRI + 8];
+	const int ck = blockIdx.x;
+	if (ck >= n_chunks) return;
+	const PrepChunk c = chunks[ck];
+	const DpDev job = jobs[c.job];
+	const int m0 = c.row0, nt = c.n_rows, r0 = 3 * m0 - 3; // smem slot s <-> row r0 + s
+	auto code = [&](int k) { return pair_job_code(packed, job, k); };
+	for (int s = threadIdx.x; s < 3 * nt + 6; s += blockDim.x) {
+		int r = r0 + s;
+		r = r < 0 ? 0 : (r > job.nl ? job.nl : r);
+		w[s] = (job.flag & NS_F_EXT_LEFT) ? prep_row_left(code, job.nl, r, cst.sp, cst.codon, cst.aa_x) : prep_row_forward(code, job.nl, r, cst.sp, cst.codon, cst.aa_x);
+	}
+	__syncthreads();
+	const int nb = pair_rec_blocks(job.nl);
+	uint4 *base = rec + job.rw_off * 2;
+	for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+		const int m = m0 + t;
+		const PairRec r = make_pair_rec([&](int k) { return w[k - r0]; }, m, job.io, cst.ge, cst.fs, 128, PAIR_PROF_HI);
+		uint4 *dst = base + pair_rec_index(nb, m);
+#pragma unroll
+		for (int f = 0; f < 6; ++f) dst[f * 32] = make_uint4(r.w[4 * f], r.w[4 * f + 1], r.w[4 * f + 2], r.w[4 * f + 3]);
+	}
+}
+
+void nasw_launch_prep_pair(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, int4 *rec)
+{
+	if (n_chunks > 0) nasw_prep_pair_kernel<<<n_chunks, 256, 0, st>>>(jobs, chunks, n_chunks, packed, cst, (uint4*)rec);
+}
+
+struct PairEnvDev {
+	uint32_t prof_base; // shared-window address of this thread's word in the low-half table of its warp
+	__device__ __forceinline__ uint32_t prof(uint32_t off) const { return (uint32_t)lds32(prof_base + off); }
+};
+
+// record of triple T - 2p (clamped into the stored range: what a clamped index delivers belongs to rows that are masked out)
+__device__ __forceinline__ void pair_load_rec(const uint4 *base, int nb, int m_max, int T, int p, PairRec &r)
+{
+	int m = T - 2 * p;
+	m = m < 0 ? (m & 1) : (m > m_max ? m_max - ((m ^ m_max) & 1) : m); // keep the parity: the other lanes of the warp are on that parity's array
+	const uint4 *q = base + pair_rec_index(nb, m);
+#pragma unroll
+	for (int f = 0; f < 6; ++f) {
+		const uint4 v = __ldg(q + f * 32);
+		r.w[4 * f] = v.x, r.w[4 * f + 1] = v.y, r.w[4 * f + 2] = v.z, r.w[4 * f + 3] = v.w;
+	}
+}
+
+template <int NW, bool TB>
+__global__ void __launch_bounds__(NW * 32) nasw_pair_kernel(const DpDev *jobs, const int *order, int n_jobs, const uint4 *rec_all, const char *aa, NaswConst cst,
+                                                            int4 *out, uint16_t *tb)
+{
+	extern __shared__ uint32_t prof_all[];       // per warp: low-half table, high-half table (22 amino acids x 32 threads each)
+	uint32_t (*prof)[2 * 22 * 32] = reinterpret_cast<uint32_t (*)[2 * 22 * 32]>(prof_all);
+	__shared__ __align__(16) uint32_t chan[NW > 1 ? NW - 1 : 1][PAIR_SLOTS][16];
+	__shared__ int cons[NW];                     // cons[w]: warp w has taken every slot of macro-steps < cons[w] from its left neighbour
+	__shared__ int ring[TB ? 32 : 32 * 32];      // [slot][lane] row maxima waiting for the warp tracker
+	__shared__ int stop_flag;
+	if ((int)blockIdx.x >= n_jobs) return;
+	const int jid = order[blockIdx.x];
+	const DpDev job = jobs[jid];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int W8 = (job.al + 7) / 8 * 8, nl = job.nl, al = job.al, Wp = job.pad_;
+	const int p = pair_index(warp, lane), col = 2 * p;
+	const bool live = p >= 0 && col < W8;
+	// ---- profile of this thread's two columns
+	{
+		int r0 = -1, r1 = -1;
+		if (p >= 0 && col < al) r0 = cst.aa20[(uint8_t)aa[job.aa_off + ((job.flag & NS_F_EXT_LEFT) ? al - 1 - col : col)]];
+		if (p >= 0 && col + 1 < al) r1 = cst.aa20[(uint8_t)aa[job.aa_off + ((job.flag & NS_F_EXT_LEFT) ? al - 2 - col : col + 1)]];
+		for (int a = 0; a < 22; ++a) {
+			prof[warp][a * 32 + lane] = pk(r0 >= 0 ? cst.mat[a * 22 + r0] : PAIR_DEAD, 0);
+			prof[warp][22 * 32 + a * 32 + lane] = pk(0, r1 >= 0 ? cst.mat[a * 22 + r1] : PAIR_DEAD);
+		}
+	}
+	if (threadIdx.x < NW) cons[threadIdx.x] = 0;
+	if (threadIdx.x == 0) stop_flag = 0;
+	for (int k = threadIdx.x; k < (NW > 1 ? NW - 1 : 1) * PAIR_SLOTS * 16; k += NW * 32) (&chan[0][0][0])[k] = 0xffffffffu; // no slot carries a valid tag yet
+	__syncthreads();
+	const int n_macro = pair_n_macro(nl, W8);
+	PairPar pp;
+	pp.go = cst.go, pp.ge = cst.ge, pp.fs = cst.fs, pp.end_bonus = cst.end_bonus, pp.ngo = pk2(-cst.go), pp.nfs = pk2(-cst.fs);
+	PairGeo g;
+	g.x = p, g.col = col, g.nl = nl, g.al = al, g.W8 = W8, g.first = p == 0;
+	typename std::conditional<TB, PairLaneTb, PairLane>::type L;
+	L.init(g, pp);
+	PairEnvDev env;
+	env.prof_base = smem_addr(&prof[warp][lane]);
+	const uint4 *rec = rec_all + job.rw_off * 2;
+	const int nb = pair_rec_blocks(nl), m_max = 2 * pair_rec_slots(nl) - 1; // records 0 .. m_max exist
+	// ---- who is who in this warp
+	const int p_first = warp == 0 ? 0 : 32 + 31 * (warp - 1), p_last_w = min(p_first + (warp == 0 ? 31 : 30), W8 / 2 - 1); // live pairs of this warp
+	const int p_end = W8 / 2 - 1;                     // the pair that owns the problem's last column
+	const bool trk_warp = !TB && warp == NW - 1;
+	const int lane_end = warp == 0 ? p_end : p_end - p_first + 1; // its lane (meaningful in the last warp)
+	WarpTracker trk;
+	trk.init(PAIR_CB);
+	const uint32_t ring_w = smem_addr(ring) + lane * 4, ring_r = smem_addr(ring) + lane * 128 + (uint32_t)(lane_end & 31) * 4;
+	(void)ring_w, (void)ring_r;
+	const uint32_t ch_in = warp > 0 ? smem_addr(&chan[warp > 0 ? warp - 1 : 0][0][0]) : 0, ch_out = smem_addr(&chan[warp < NW - 1 ? warp : 0][0][0]);
+	const uint32_t cons_mine = smem_addr(&cons[warp]), cons_next = smem_addr(&cons[warp < NW - 1 ? warp + 1 : warp]), sf = smem_addr(&stop_flag);
+	int tb_score = 0;
+	bool have_score = false;
+	const bool has_end_lo = live && col == al - 1, has_end_hi = live && col + 1 == al - 1;
+	uint16_t *tbp = TB ? tb + job.tb_off + col : 0;
+	bool stopped = false;
+
+	// ---- exchange between warps --------------------------------------------------------------------------------------------
+	// take the slot of macro-step T - 1 from the left warp into the relay lane's output registers (T >= 1)
+	auto relay_in = [&](int T) {
+		if (NW == 1 || warp == 0) return;
+		const uint32_t a = ch_in + (uint32_t)((T - 1) & (PAIR_SLOTS - 1)) * 64;
+		for (;;) {
+			bool ok = true;
+			if (lane == 0) {
+				const int4 c0 = lds128(a), c1 = lds128(a + 16), c2 = lds128(a + 32);
+				ok = c0.w == T - 1 && c1.w == T - 1 && c2.w == T - 1;
+				if constexpr (TB) {
+					const int4 c3 = lds128(a + 48);
+					ok = ok && c3.w == T - 1;
+					if (ok) {
+						L.oH[0] = c0.x, L.oQ[0] = c0.y, L.oF[0] = c0.z, L.oS[0] = c1.x, L.oH[1] = c1.y, L.oQ[1] = c1.z;
+						L.oF[1] = c2.x, L.oS[1] = c2.y, L.oH[2] = c2.z, L.oQ[2] = c3.x, L.oF[2] = c3.y, L.oS[2] = c3.z;
+					}
+				} else {
+					if (ok) {
+						L.oH[0] = c0.x, L.oQ[0] = c0.y, L.oXhi[0] = c0.z, L.oH[1] = c1.x, L.oQ[1] = c1.y, L.oXhi[1] = c1.z;
+						L.oH[2] = c2.x, L.oQ[2] = c2.y, L.oXhi[2] = c2.z;
+					}
+				}
+			}
+			if (__all_sync(0xffffffffu, ok)) break;
+			if (lds32(sf)) { stopped = true; break; }
+		}
+		if (lane == 0) sts32(cons_mine, T);
+	};
+	// hand the last lane's outputs of macro-step T to the right warp
+	auto relay_out = [&](int T) {
+		if (NW == 1 || warp == NW - 1) return;
+		while (T - lds32(cons_next) >= PAIR_SLOTS) { // the right warp still needs the slot this one would overwrite
+			if (lds32(sf)) { stopped = true; return; }
+		}
+		if (lane == 31) {
+			const uint32_t a = ch_out + (uint32_t)(T & (PAIR_SLOTS - 1)) * 64;
+			if constexpr (TB) {
+				sts128(a, make_int4(L.oH[0], L.oQ[0], L.oF[0], T)), sts128(a + 16, make_int4(L.oS[0], L.oH[1], L.oQ[1], T));
+				sts128(a + 32, make_int4(L.oF[1], L.oS[1], L.oH[2], T)), sts128(a + 48, make_int4(L.oQ[2], L.oF[2], L.oS[2], T));
+			} else {
+				sts128(a, make_int4(L.oH[0], L.oQ[0], L.oXhi[0], T)), sts128(a + 16, make_int4(L.oH[1], L.oQ[1], L.oXhi[1], T));
+				sts128(a + 32, make_int4(L.oH[2], L.oQ[2], L.oXhi[2], T));
+			}
+		}
+	};
+
+	// ---- one macro-step; hb[PH] receives this step's left H, hb[PH ^ 1] holds the previous step's
+	uint32_t hb[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } };
+#define NSW_PAIR_RECV(PH) \
+		uint32_t rQ[3]; \
+		_Pragma("unroll") for (int r = 0; r < 3; ++r) { \
+			hb[PH][r] = L.left_of(__shfl_up_sync(0xffffffffu, L.oH[r], 1), L.oH[r]); \
+			rQ[r] = L.left_of(__shfl_up_sync(0xffffffffu, L.oQ[r], 1), L.oQ[r]); \
+		}
+	auto tracker_push = [&](int T, bool all_rows) {
+		if constexpr (!TB) {
+			if (!trk_warp) return;
+#pragma unroll
+			for (int r = 0; r < 3; ++r) {
+				const int i_hi = 3 * (T - 2 * p_end) - 1 + r; // row of the last column's value in oXhi[r]
+				if (all_rows || (i_hi >= 2 && i_hi < nl)) trk.push(ring_w, L.oXhi[r]);
+			}
+			if (trk.n_ring >= 30) trk.flush(ring_r, lane, al * 3, cst.pen, cst.xdrop);
+		}
+	};
+	auto step = [&](int T, auto ph_tag, bool steady) {
+		constexpr int PH = decltype(ph_tag)::value;
+		if (T > 0) relay_in(T);
+		if (stopped) return;
+		PairRec rc;
+		pair_load_rec(rec, nb, m_max, T, p < 0 ? 0 : p, rc);
+		NSW_PAIR_RECV(PH)
+		const uint32_t *pv = hb[PH ^ 1], *cu = hb[PH];
+		if constexpr (TB) {
+			uint32_t rF[3], rS[3], wd[3];
+#pragma unroll
+			for (int r = 0; r < 3; ++r) {
+				rF[r] = L.left_of(__shfl_up_sync(0xffffffffu, L.oF[r], 1), L.oF[r]);
+				rS[r] = L.left_of(__shfl_up_sync(0xffffffffu, L.oS[r], 1), L.oS[r]);
+			}
+			auto &LT = L;
+			if (steady) {
+				wd[0] = LT.template row<0>(pp, rc, env, cu[0], pv[2], pv[1], pv[0], rQ[0], rF[0], rS[0]);
+				wd[1] = LT.template row<1>(pp, rc, env, cu[1], cu[0], pv[2], pv[1], rQ[1], rF[1], rS[1]);
+				wd[2] = LT.template row<2>(pp, rc, env, cu[2], cu[1], cu[0], pv[2], rQ[2], rF[2], rS[2]);
+				if (live) {
+#pragma unroll
+					for (int r = 0; r < 3; ++r) *reinterpret_cast<uint32_t*>(tbp + (int64_t)(3 * T + r) * Wp) = wd[r];
+				}
+			} else {
+				const int m = T - 2 * p;
+#pragma unroll
+				for (int r = 0; r < 3; ++r) {
+					const int i_lo = 3 * m + 2 + r, i_hi = i_lo - 3;
+					const bool vlo = live && i_lo >= 2 && i_lo < nl, vhi = live && i_hi >= 2 && i_hi < nl;
+					const uint32_t keep = (vlo ? 0xffffu : 0u) | (vhi ? 0xffff0000u : 0u);
+					const bool bnd = g.first && i_lo == 2;
+					const uint32_t l0 = cu[r], l1 = r == 0 ? pv[2] : cu[r - 1], l2 = r == 0 ? pv[1] : r == 1 ? pv[2] : cu[0], l3 = r == 0 ? pv[0] : r == 1 ? pv[1] : pv[2];
+					if (r == 0) wd[0] = LT.template row_masked<0>(pp, rc, env, l0, l1, l2, l3, rQ[0], rF[0], rS[0], keep, bnd);
+					else if (r == 1) wd[1] = LT.template row_masked<1>(pp, rc, env, l0, l1, l2, l3, rQ[1], rF[1], rS[1], keep, bnd);
+					else wd[2] = LT.template row_masked<2>(pp, rc, env, l0, l1, l2, l3, rQ[2], rF[2], rS[2], keep, bnd);
+					uint16_t *q = tbp + (int64_t)(3 * T + r) * Wp;
+					if (vlo && vhi) *reinterpret_cast<uint32_t*>(q) = wd[r];
+					else if (vlo) q[0] = (uint16_t)(wd[r] & 0xffff);
+					else if (vhi) q[1] = (uint16_t)(wd[r] >> 16);
+					if (vlo && has_end_lo && i_lo == nl - 1) tb_score = lo16(LT.oH[r]) - PAIR_BIAS, have_score = true;
+					if (vhi && has_end_hi && i_hi == nl - 1) tb_score = hi16(LT.oH[r]) - PAIR_BIAS, have_score = true;
+				}
+			}
+		} else {
+			auto &LE = L;
+			int lx[3], xp[3];
+#pragma unroll
+			for (int r = 0; r < 3; ++r) lx[r] = (int)((uint32_t)__shfl_up_sync(0xffffffffu, LE.oXhi[r], 1) & LE.xmask), xp[r] = LE.oXlo[r];
+			if (steady) {
+				LE.template row<0>(pp, rc, env, cu[0], pv[2], pv[1], pv[0], rQ[0], lx[0], xp[0]);
+				LE.template row<1>(pp, rc, env, cu[1], cu[0], pv[2], pv[1], rQ[1], lx[1], xp[1]);
+				LE.template row<2>(pp, rc, env, cu[2], cu[1], cu[0], pv[2], rQ[2], lx[2], xp[2]);
+			} else {
+				const int m = T - 2 * p;
+#pragma unroll
+				for (int r = 0; r < 3; ++r) {
+					const int i_lo = 3 * m + 2 + r, i_hi = i_lo - 3;
+					const bool vlo = live && i_lo >= 2 && i_lo < nl, vhi = live && i_hi >= 2 && i_hi < nl;
+					const uint32_t keep = (vlo ? 0xffffu : 0u) | (vhi ? 0xffff0000u : 0u);
+					const bool bnd = g.first && i_lo == 2;
+					const uint32_t l0 = cu[r], l1 = r == 0 ? pv[2] : cu[r - 1], l2 = r == 0 ? pv[1] : r == 1 ? pv[2] : cu[0], l3 = r == 0 ? pv[0] : r == 1 ? pv[1] : pv[2];
+					if (r == 0) LE.template row_masked<0>(pp, rc, env, l0, l1, l2, l3, rQ[0], lx[0], xp[0], keep, bnd);
+					else if (r == 1) LE.template row_masked<1>(pp, rc, env, l0, l1, l2, l3, rQ[1], lx[1], xp[1], keep, bnd);
+					else LE.template row_masked<2>(pp, rc, env, l0, l1, l2, l3, rQ[2], lx[2], xp[2], keep, bnd);
+				}
+			}
+			tracker_push(T, steady);
+			if (trk_warp && trk.stopped) { if (lane == 0) sts32(sf, 1); stopped = true; return; }
+		}
+		relay_out(T);
+	};
+#undef NSW_PAIR_RECV
+	// steady macro-steps of this warp: both halves of every live thread are on real rows strictly above the last row
+	int t_lo = 2 * p_last_w + 2, t_hi = nl >= 6 ? 2 * p_first + (nl - 6) / 3 + 1 : 0;
+	t_lo += t_lo & 1;
+	if (t_hi < t_lo) t_hi = t_lo;
+	t_hi = t_lo + ((t_hi - t_lo) & ~1);
+	if (p_last_w < p_first) t_lo = t_hi = n_macro; // a warp without live columns (cannot happen: the warp count is minimal)
+	int T = 0;
+	for (; T < t_lo && T < n_macro && !stopped; T += 2) {
+		step(T, std::integral_constant<int, 0>(), false);
+		if (!stopped) step(T + 1, std::integral_constant<int, 1>(), false);
+		if (!TB && NW > 1 && !stopped && lds32(sf)) stopped = true;
+	}
+	for (; T < t_hi && !stopped; T += 2) {
+		step(T, std::integral_constant<int, 0>(), true);
+		if (!stopped) step(T + 1, std::integral_constant<int, 1>(), true);
+		if (!TB && NW > 1 && !stopped && lds32(sf)) stopped = true;
+	}
+	for (; T < n_macro && !stopped; T += 2) {
+		step(T, std::integral_constant<int, 0>(), false);
+		if (!stopped) step(T + 1, std::integral_constant<int, 1>(), false);
+		if (!TB && NW > 1 && !stopped && lds32(sf)) stopped = true;
+	}
+	if (TB) {
+		if (have_score) out[jid] = make_int4(tb_score, nl, al, 0);
+		else if (nl <= 2 && threadIdx.x == 0) out[jid] = make_int4(NEG, nl, al, 0);
+	} else if (trk_warp) {
+		if (trk.n_ring > 0 && !trk.stopped) trk.flush(ring_r, lane, al * 3, cst.pen, cst.xdrop);
+		if (lane == 0) {
+			int4 r;
+			r.x = trk.max_i >= 0 ? trk.max_sc - PAIR_BIAS : INT32_MIN, r.y = trk.max_i + 1, r.z = trk.aa_len(al), r.w = 0;
+			out[jid] = r;
+		}
+	}
+}
+
+template <int NW, bool TB>
+static void launch_pair(cudaStream_t st, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, uint16_t *tb)
+{
+	const int smem = NW * 2 * 22 * 32 * (int)sizeof(uint32_t);
+	static bool attr_set = false;
+	if (!attr_set) { cudaFuncSetAttribute(nasw_pair_kernel<NW, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+	nasw_pair_kernel<NW, TB><<<n, NW * 32, smem, st>>>(jobs, order, n, (const uint4*)rec, aa, cst, out, tb);
+}
+
+// pair-lane kernels: nw = warps per problem (1, 2, 4 or 8: up to 64 / 126 / 250 / 498 padded columns)
+void nasw_launch_pair(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out,
+                      uint16_t *tb)
+{
+	if (n <= 0) return;
+	switch (nw * 2 + (is_tb ? 1 : 0)) {
+	case 2: launch_pair<1, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	case 3: launch_pair<1, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	case 4: launch_pair<2, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	case 5: launch_pair<2, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	case 8: launch_pair<4, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	case 9: launch_pair<4, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	case 16: launch_pair<8, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	default: launch_pair<8, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
+	}
+}
+
+} // namespace cuda
+} // namespace mpb

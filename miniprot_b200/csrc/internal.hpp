@@ -115,6 +115,10 @@ struct Str {                      // growable output buffer
 };
 void format_hit(Str &out, const mp_idx_t *mi, const mp_mapopt_t *opt, const char *qname, int32_t qlen, const char *qseq,
                 const mp_reg1_t *r);
+// everything the reference prints for one hit (PAF, --aln / --trans blocks, GFF3 or GTF, format.c:453); id = running number of
+// the hit in the whole output, hit_idx = its rank for this protein (1-based); r == 0: the unmapped line of -u
+void format_output(Str &out, const mp_idx_t *mi, const mp_mapopt_t *opt, const char *qname, int32_t qlen, const char *qseq,
+                   const mp_reg1_t *r, int64_t id, int32_t hit_idx);
 
 // hits.cpp (hit.c)
 mp_reg1_t *regs_from_chains(const mp_idx_t *mi, int32_t n_u, const uint64_t *u, const uint64_t *a, int32_t *n_reg); // hit.c:32

@@ -199,10 +199,27 @@ void map_batch(Stages *st, const mp_idx_t *mi, const mp_mapopt_t *opt, const Bat
 	lap(5);
 }
 
-// map.c:293-326: per protein, hits in rank order subject to --outn / --outs / --outc; unmapped line with -u
-// formatting is independent per protein: ranges of proteins on the worker pool, each into its own buffer, written in order
-static void write_batch(FILE *out, const mp_idx_t *mi, const mp_mapopt_t *opt, const Batch &b, const int32_t *n_reg, mp_reg1_t *const *reg)
+// map.c:293-326: per protein, hits in rank order subject to --outn / --outs / --outc; unmapped line with -u.  Every printed hit
+// gets the next number of a counter that runs over the whole file (the MP%06d ids of GFF / GTF, map.c:306): the hits each
+// protein will print are counted first, so that formatting -- independent per protein -- can run on the worker pool, each range
+// into its own buffer, written in order.
+static void write_batch(FILE *out, const mp_idx_t *mi, const mp_mapopt_t *opt, const Batch &b, const int32_t *n_reg, mp_reg1_t *const *reg, int64_t *id_counter)
 {
+	auto printed = [&](int32_t q, int32_t j, int32_t best) {
+		const mp_reg1_t *r = &reg[q][j];
+		const int32_t sc = r->p ? r->p->dp_max : r->chn_sc;
+		if (sc <= 0 || sc < (double)best * opt->out_sim) return false;
+		if (r->qe - r->qs < (double)b.len[q] * opt->out_cov) return false;
+		return true;
+	};
+	std::vector<int64_t> id0((size_t)b.n + 1, *id_counter);
+	for (int32_t q = 0; q < b.n; ++q) {
+		int64_t k = 0;
+		const int32_t best = n_reg[q] > 0 ? (reg[q][0].p ? reg[q][0].p->dp_max : reg[q][0].chn_sc) : -1;
+		for (int32_t j = 0; j < n_reg[q] && j < opt->out_n; ++j) k += printed(q, j, best);
+		id0[(size_t)q + 1] = id0[(size_t)q] + k;
+	}
+	*id_counter = id0[(size_t)b.n];
 	std::vector<Str> part(64);
 	const int n_part = par_ranges(b.n, 64, [&](int q_lo, int q_hi, int c) {
 		Str &buf = part[(size_t)c];
@@ -210,14 +227,11 @@ static void write_batch(FILE *out, const mp_idx_t *mi, const mp_mapopt_t *opt, c
 			int32_t best = -1, n_out = 0;
 			if (n_reg[q] > 0) best = reg[q][0].p ? reg[q][0].p->dp_max : reg[q][0].chn_sc;
 			for (int32_t j = 0; j < n_reg[q] && j < opt->out_n; ++j) {
-				const mp_reg1_t *r = &reg[q][j];
-				const int32_t sc = r->p ? r->p->dp_max : r->chn_sc;
-				if (sc <= 0 || sc < (double)best * opt->out_sim) continue;
-				if (r->qe - r->qs < (double)b.len[q] * opt->out_cov) continue;
-				if (!(opt->flag & MP_F_NO_PAF)) format_hit(buf, mi, opt, b.name[q], b.len[q], b.seq[q], r);
+				if (!printed(q, j, best)) continue;
 				++n_out;
+				format_output(buf, mi, opt, b.name[q], b.len[q], b.seq[q], &reg[q][j], id0[(size_t)q] + n_out, j + 1);
 			}
-			if (n_out == 0 && (opt->flag & MP_F_SHOW_UNMAP)) format_hit(buf, mi, opt, b.name[q], b.len[q], b.seq[q], 0);
+			if (n_out == 0) format_output(buf, mi, opt, b.name[q], b.len[q], b.seq[q], 0, 0, 0);
 		}
 	});
 	for (int c = 0; c < n_part; ++c) {
@@ -230,12 +244,11 @@ int32_t map_file(Stages *st, const mp_idx_t *mi, const char *fn, const mp_mapopt
 {
 	FastxReader rd(fn);
 	if (!rd.fp) return -1;
-	if (opt->flag & (MP_F_GFF | MP_F_GTF | MP_F_SHOW_RESIDUE | MP_F_SHOW_TRANS))
-		fprintf(stderr, "[WARNING] GFF/GTF/--aln/--trans output is not produced by miniprot_b200 in this round; writing PAF only\n");
 	std::vector<std::string> names, seqs;
 	std::string name, seq;
 	bool more = true;
-	int64_t n_done = 0;
+	int64_t n_done = 0, id_counter = 0;
+	if (opt->flag & MP_F_GFF) fputs("##gff-version 3\n", out); // map.c:338
 	while (more) {
 		int64_t residues = 0;
 		names.clear(), seqs.clear();
@@ -252,7 +265,7 @@ int32_t map_file(Stages *st, const mp_idx_t *mi, const char *fn, const mp_mapopt
 		Batch b;
 		b.n = n, b.seq = sp.data(), b.len = len.data(), b.name = np.data();
 		map_batch(st, mi, opt, b, n_reg.data(), reg.data());
-		write_batch(out, mi, opt, b, n_reg.data(), reg.data());
+		write_batch(out, mi, opt, b, n_reg.data(), reg.data(), &id_counter);
 		for (int32_t i = 0; i < n; ++i) {
 			for (int32_t j = 0; j < n_reg[(size_t)i]; ++j) free(reg[(size_t)i][j].feat), free(reg[(size_t)i][j].p);
 			free(reg[(size_t)i]);

@@ -6,7 +6,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "miniprot_b200", "csrc")
 OUT = os.path.join(ROOT, "tests", "_build", "libhostcheck.so")
-HOST_SRCS = ["tables.cpp", "ntdb.cpp", "index.cpp", "hits.cpp", "align.cpp", "paf.cpp", "pipeline.cpp"]
+HOST_SRCS = ["tables.cpp", "ntdb.cpp", "index.cpp", "hits.cpp", "align.cpp", "paf.cpp", "annot.cpp", "pipeline.cpp"]
 
 
 def build(force=False):

@@ -32,3 +32,8 @@ if __name__ == "__main__":
     for cfg in ("tiny", "tiny5"):
         gg, pp = synth.generate(synth.CONFIGS[cfg], "/tmp/mpb_golden")
         run([gg, pp], os.path.join(HERE, cfg + ".paf"))
+    # the other output formats (format.c:189-452), on the set that exercises every CIGAR operation, and on DPP3
+    gg, pp = synth.generate(synth.CONFIGS["tiny5"], "/tmp/mpb_golden")
+    for name, args in (("gff", ["--gff"]), ("gtf", ["--gtf"]), ("aln", ["--aln"]), ("trans", ["--trans", "-u"]), ("gff_only", ["--gff-only", "--gff-delim", "#"])):
+        run(args + [gg, pp], os.path.join(HERE, "tiny5_" + name + ".txt"))
+        run(args + [g, p], os.path.join(HERE, "DPP3_" + name + ".txt"))

@@ -10,6 +10,7 @@
 #include <string.h>
 #include <vector>
 #include "cuda/nasw_core.cuh"
+#include "cuda/nasw_pair.cuh"
 
 using namespace nsw;
 
@@ -39,6 +40,8 @@ struct EmuEnv {
 };
 
 struct Problem {
+	std::vector<uint32_t> w; // row words (nasw_core.cuh row_pack): slot x <-> row x - 2, clamped like the prep kernels
+	int io;
 	std::vector<RowRec> rec;
 	std::vector<int> aas;
 	int nl, al, W8;
@@ -275,6 +278,152 @@ void run_v3(const Problem &P, int *score, int *nt_len, int *aa_len, std::vector<
 	}
 }
 
+// pair-lane wavefront (nasw_pair.cuh): W8/2 threads in lockstep, two columns each; thread x <- thread x-1 from the previous
+// macro-step.  Rows in which both halves of every thread are real go through the straight-line row(), the others through
+// row_masked(), like the kernels' steady and general loops.
+struct PairEnv {
+	const uint32_t *lo, *hi; // [22][NT] packed profile words of this thread (value in the low resp. high half)
+	int nt;
+	uint32_t prof(uint32_t off) const { const uint32_t a = off / 128u; return a < 22 ? lo[a * (uint32_t)nt] : hi[(a - 22) * (uint32_t)nt]; }
+};
+
+template <bool TB>
+void run_pair(const Problem &P, int *score, int *nt_len, int *aa_len, std::vector<uint32_t> &cigar)
+{
+	const int NT = P.W8 / 2, M = P.nl > 2 ? (P.nl - 2 + 2) / 3 : 0, n_macro = M > 0 ? M + P.W8 + 1 : 0, Wp = (P.W8 + 63) / 64 * 64, Trows = 3 * (n_macro + 2);
+	PairPar pp;
+	pp.go = P.par.go, pp.ge = P.par.ge, pp.fs = P.par.fs, pp.end_bonus = P.end_bonus, pp.ngo = pk2(-P.par.go), pp.nfs = pk2(-P.par.fs);
+	std::vector<uint32_t> plo((size_t)22 * NT), phi((size_t)22 * NT);
+	for (int x = 0; x < NT; ++x)
+		for (int a = 0; a < 22; ++a) {
+			const int j0 = 2 * x, j1 = 2 * x + 1;
+			plo[(size_t)a * NT + x] = pk(j0 < P.al ? P.mat[a * 22 + P.aas[j0]] : PAIR_DEAD, 0);
+			phi[(size_t)a * NT + x] = pk(0, j1 < P.al ? P.mat[a * 22 + P.aas[j1]] : PAIR_DEAD);
+		}
+	auto rw = [&](int k) { k = k < 0 ? 0 : (k > P.nl ? P.nl : k); return P.w[(size_t)k + 2]; };
+	std::vector<PairGeo> g((size_t)NT);
+	std::vector<PairEnv> env((size_t)NT);
+	std::vector<PairLane> LE((size_t)(TB ? 0 : NT));
+	std::vector<PairLaneTb> LT((size_t)(TB ? NT : 0));
+	std::vector<uint32_t> pH((size_t)NT * 3, 0);
+	for (int x = 0; x < NT; ++x) {
+		g[x].x = x, g[x].col = 2 * x, g[x].nl = P.nl, g[x].al = P.al, g[x].W8 = P.W8, g[x].first = x == 0;
+		env[x].lo = plo.data() + x, env[x].hi = phi.data() + x, env[x].nt = NT;
+		if (TB) LT[x].init(g[x], pp); else LE[x].init(g[x], pp);
+	}
+	ExtTracker trk;
+	trk.init(PAIR_CB);
+	PenTable pt;
+	pen_table_build(P.ie_coef, pt);
+	std::vector<uint16_t> tb(TB ? (size_t)Trows * Wp : 1, 0xffff);
+	int tb_score = 0;
+	bool stop = false;
+	std::vector<uint32_t> sH((size_t)NT * 3), sQ((size_t)NT * 3), sF((size_t)NT * 3), sS((size_t)NT * 3);
+	std::vector<int> sXlo((size_t)NT * 3), sXhi((size_t)NT * 3);
+	for (int T = 0; T < n_macro && !stop; ++T) {
+		for (int x = 0; x < NT; ++x)
+			for (int r = 0; r < 3; ++r) {
+				if (TB) sH[x * 3 + r] = LT[x].oH[r], sQ[x * 3 + r] = LT[x].oQ[r], sF[x * 3 + r] = LT[x].oF[r], sS[x * 3 + r] = LT[x].oS[r];
+				else sH[x * 3 + r] = LE[x].oH[r], sQ[x * 3 + r] = LE[x].oQ[r], sXlo[x * 3 + r] = LE[x].oXlo[r], sXhi[x * 3 + r] = LE[x].oXhi[r];
+			}
+		for (int x = 0; x < NT; ++x) {
+			const int s = x ? x - 1 : 0; // __shfl_up_sync(.., 1): thread 0 gets its own register back
+			const int m = T - 2 * x;
+			const PairRec rec = make_pair_rec(rw, m, P.io, P.par.ge, P.par.fs, 128, 22 * 128);
+			uint32_t rH[3], rQ[3], rF[3], rS[3], keep[3];
+			int lx[3], xp[3];
+			bool bnd[3], all = true;
+			for (int r = 0; r < 3; ++r) {
+				const int i_lo = 3 * m + 2 + r, i_hi = i_lo - 3;
+				keep[r] = (i_lo >= 2 && i_lo < P.nl ? 0xffffu : 0u) | (i_hi >= 2 && i_hi < P.nl ? 0xffff0000u : 0u);
+				bnd[r] = x == 0 && i_lo == 2;
+				all = all && keep[r] == 0xffffffffu && !bnd[r];
+				if (TB) {
+					rH[r] = LT[x].left_of(sH[s * 3 + r], sH[x * 3 + r]), rQ[r] = LT[x].left_of(sQ[s * 3 + r], sQ[x * 3 + r]);
+					rF[r] = LT[x].left_of(sF[s * 3 + r], sF[x * 3 + r]), rS[r] = LT[x].left_of(sS[s * 3 + r], sS[x * 3 + r]);
+				} else {
+					rH[r] = LE[x].left_of(sH[s * 3 + r], sH[x * 3 + r]), rQ[r] = LE[x].left_of(sQ[s * 3 + r], sQ[x * 3 + r]);
+					lx[r] = (int)((uint32_t)sXhi[s * 3 + r] & LE[x].xmask), xp[r] = sXlo[x * 3 + r];
+				}
+			}
+			uint32_t *p = &pH[(size_t)x * 3];
+			uint32_t wd[3] = { 0, 0, 0 };
+			if (TB) {
+				PairLaneTb &L = LT[x];
+				if (all) {
+					wd[0] = L.template row<0>(pp, rec, env[x], rH[0], p[2], p[1], p[0], rQ[0], rF[0], rS[0]);
+					wd[1] = L.template row<1>(pp, rec, env[x], rH[1], rH[0], p[2], p[1], rQ[1], rF[1], rS[1]);
+					wd[2] = L.template row<2>(pp, rec, env[x], rH[2], rH[1], rH[0], p[2], rQ[2], rF[2], rS[2]);
+				} else {
+					wd[0] = L.template row_masked<0>(pp, rec, env[x], rH[0], p[2], p[1], p[0], rQ[0], rF[0], rS[0], keep[0], bnd[0]);
+					wd[1] = L.template row_masked<1>(pp, rec, env[x], rH[1], rH[0], p[2], p[1], rQ[1], rF[1], rS[1], keep[1], bnd[1]);
+					wd[2] = L.template row_masked<2>(pp, rec, env[x], rH[2], rH[1], rH[0], p[2], rQ[2], rF[2], rS[2], keep[2], bnd[2]);
+				}
+				for (int r = 0; r < 3; ++r) {
+					const int i_lo = 3 * m + 2 + r, i_hi = i_lo - 3;
+					if (keep[r] & 0xffffu) {
+						tb[(size_t)(3 * T + r) * Wp + 2 * x] = (uint16_t)(wd[r] & 0xffff);
+						if (i_lo == P.nl - 1 && 2 * x == P.al - 1) tb_score = lo16(L.oH[r]) - PAIR_BIAS;
+					}
+					if (keep[r] >> 16) {
+						tb[(size_t)(3 * T + r) * Wp + 2 * x + 1] = (uint16_t)(wd[r] >> 16);
+						if (i_hi == P.nl - 1 && 2 * x + 1 == P.al - 1) tb_score = hi16(L.oH[r]) - PAIR_BIAS;
+					}
+				}
+			} else {
+				PairLane &L = LE[x];
+				if (all) {
+					L.template row<0>(pp, rec, env[x], rH[0], p[2], p[1], p[0], rQ[0], lx[0], xp[0]);
+					L.template row<1>(pp, rec, env[x], rH[1], rH[0], p[2], p[1], rQ[1], lx[1], xp[1]);
+					L.template row<2>(pp, rec, env[x], rH[2], rH[1], rH[0], p[2], rQ[2], lx[2], xp[2]);
+				} else {
+					L.template row_masked<0>(pp, rec, env[x], rH[0], p[2], p[1], p[0], rQ[0], lx[0], xp[0], keep[0], bnd[0]);
+					L.template row_masked<1>(pp, rec, env[x], rH[1], rH[0], p[2], p[1], rQ[1], lx[1], xp[1], keep[1], bnd[1]);
+					L.template row_masked<2>(pp, rec, env[x], rH[2], rH[1], rH[0], p[2], rQ[2], lx[2], xp[2], keep[2], bnd[2]);
+				}
+				if (x == NT - 1)
+					for (int r = 0; r < 3; ++r) {
+						const int i_hi = 3 * m + 2 + r - 3;
+						if (keep[r] >> 16) trk.row(i_hi, L.oXhi[r], P.al * 3, pt, P.xdrop);
+					}
+			}
+			p[0] = rH[0], p[1] = rH[1], p[2] = rH[2];
+		}
+		if (!TB && trk.stopped) stop = true;
+	}
+	if (TB) {
+		*score = tb_score;
+		auto at = [&](int i, int j) -> uint32_t { return tb[(size_t)(i - 2 + 3 * j) * Wp + j]; };
+		struct CpuScan {
+			decltype(at) &tbf;
+			uint32_t word(int i, int j) const { return tbf(i, j); }
+			int lead(int kind, int i, int j, int &n_valid) const
+			{
+				const int di = kind == 0 ? 3 : kind == 1 ? 0 : kind == 2 ? 3 : 1, dj = kind <= 1 ? 1 : 0;
+				int c = 0;
+				bool open = true;
+				n_valid = 0;
+				for (int k = 0; k < 32; ++k) {
+					const int ii = i - di * k, jj = j - dj * k;
+					if (ii < 2 || jj < 0) break;
+					++n_valid;
+					const uint32_t x = tbf(ii, jj);
+					const bool ok = kind == 0 ? ((x >> 9 & 1) ? false : (x & 0xf) == 0) : (x >> (kind + 3) & 1);
+					if (open && ok) ++c; else open = false;
+				}
+				return c;
+			}
+		} scan{at};
+		const int cap = P.nl + P.al + 8;
+		std::vector<uint32_t> buf((size_t)cap);
+		const int n = backtrack_runs(scan, P.nl, P.al, buf.data(), cap, true);
+		cigar.assign(buf.begin() + (cap - n), buf.end());
+	} else {
+		*score = trk.max_i >= 0 ? trk.max_sc - PAIR_BIAS : INT32_MIN, *nt_len = trk.max_i + 1;
+		*aa_len = trk.aa_len(P.al);
+	}
+}
+
 } // namespace
 
 extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *codon, const int8_t *mat, const int32_t *sp, int go, int ge, int io,
@@ -295,13 +444,23 @@ extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *
 		r = r < 0 ? 0 : (r > nl ? nl : r);
 		w[(size_t)x] = left ? prep_row_left(c, nl, r, sp, codon, aa20['X']) : prep_row_forward(c, nl, r, sp, codon, aa20['X']);
 	}
+	P.w = w, P.io = io;
 	P.rec.resize((size_t)n_rec);
 	for (int r = 0; r < n_rec; ++r) P.rec[(size_t)r] = make_row_rec(P.par, w[(size_t)r], w[(size_t)r + 1], w[(size_t)r + 2], w[(size_t)r + 3]);
 	P.aas.resize((size_t)al);
 	for (int j = 0; j < al; ++j) P.aas[(size_t)j] = aa20[(uint8_t)as[left ? al - 1 - j : j]];
 	*nt_len = nl, *aa_len = al;
 	int n_cig = 0;
-	if (C == 0) { // block-wide wavefront kernels
+	if (C < 0) { // pair-lane kernels (two columns per thread, int16x2)
+		std::vector<uint32_t> cg;
+		if (nl <= 2) { // nothing to compute: the kernels report what the block-wide kernels report
+			if (flag & 6) run_v3<false>(P, score, nt_len, aa_len, cg);
+			else run_v3<true>(P, score, nt_len, aa_len, cg);
+		} else if (flag & 6) run_pair<false>(P, score, nt_len, aa_len, cg);
+		else run_pair<true>(P, score, nt_len, aa_len, cg);
+		n_cig = (int)cg.size();
+		for (int k = 0; k < n_cig && k < cigar_cap; ++k) cigar[k] = cg[(size_t)k];
+	} else if (C == 0) { // block-wide wavefront kernels
 		std::vector<uint32_t> cg;
 		if (flag & 6) run_v3<false>(P, score, nt_len, aa_len, cg);
 		else run_v3<true>(P, score, nt_len, aa_len, cg);

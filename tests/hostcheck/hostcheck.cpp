@@ -133,6 +133,7 @@ int hc_map_file(const char *genome, const char *prot, const char *out_path, uint
 	if (max_intron > 0) mo.max_intron = mo.bw = max_intron;
 	if (sp_model >= 0) mo.sp_model = sp_model;
 	if (mini_batch > 0) mo.mini_batch_size = mini_batch;
+	if (getenv("HC_GFF_DELIM")) mo.gff_delim = getenv("HC_GFF_DELIM")[0]; // --gff-delim (test hook)
 	mp_idx_t *mi = mp_idx_load(genome, &io, n_threads);
 	if (!mi) return -1;
 	if (auto_intron) mp_mapopt_set_max_intron(&mo, mi->nt->l_seq);

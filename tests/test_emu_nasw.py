@@ -31,7 +31,7 @@ def emu(hc, nt, aa, flag, Ccols, mat, par):
     return sc.value, ntl.value, aal.value, [cig[i] for i in range(n)]
 
 
-@pytest.mark.parametrize("Ccols", [0, 1, 2, 4, 8])  # 0 = block-wide wavefront kernels (one thread per column, 3 rows per step)
+@pytest.mark.parametrize("Ccols", [-1, 0, 1, 2, 4, 8])  # 0 = block-wide wavefront kernels (one thread per column, 3 rows per step); -1 = pair-lane kernels (int16x2)
 def test_emu_matches_oracle(hc, Ccols):
     rng = np.random.default_rng(1000 + Ccols)
     tab, mat = ol.ref_tables(), ol.default_mat()
@@ -39,8 +39,8 @@ def test_emu_matches_oracle(hc, Ccols):
         par = dict(ol.DEFAULT_NASW)
         if it % 5 == 0:
             par["sp"] = (8, 15, 21, 30, 4, 4)
-        al_max = (250, 30, 70, 140, 300)[[0, 1, 2, 4, 8].index(Ccols)]
-        if it % 6 == 0:
+        al_max = (250, 250, 30, 70, 140, 300)[[-1, 0, 1, 2, 4, 8].index(Ccols)]
+        if it % 6 == 0 and Ccols >= 0:
             al_max = 32 * Ccols * 2 + 20 if Ccols else (700 if it % 12 else 560)  # force several column passes (256 columns each when Ccols == 0)
         nt, aa = ol.random_dp_problem(rng, al_max=al_max, flank=60)
         if len(nt) < 3:

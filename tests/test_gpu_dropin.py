@@ -23,7 +23,7 @@ need_bins = pytest.mark.skipif(not all(os.path.exists(x) for x in (CLI, EX, EX_R
 
 
 def out(cmd):
-    return subprocess.run(cmd, check=True, capture_output=True).stdout
+    return subprocess.run(cmd, check=True, capture_output=True, timeout=300).stdout
 
 
 @need_bins
@@ -33,7 +33,7 @@ def test_reference_cli_on_our_library(tmp_path):
         assert out([CLI, "-t4", *args, g, p]) == out([ol.REF_BIN, "-t4", *args, g, p]), args
     g, p = synth.generate(synth.CONFIGS["small"], str(tmp_path))
     mpi = str(tmp_path / "ours.mpi")
-    subprocess.run([CLI, "-t8", "-d", mpi, g], check=True, capture_output=True)  # index built and dumped by our library ...
+    subprocess.run([CLI, "-t8", "-d", mpi, g], check=True, capture_output=True, timeout=300)  # index built and dumped by our library ...
     assert out([ol.REF_BIN, "-t8", mpi, p]) == out([CLI, "-t8", mpi, p])        # ... restored by the reference, and by us
     assert out([CLI, "-t8", "-I", g, p]) == out([ol.REF_BIN, "-t8", "-I", g, p])
 

@@ -127,6 +127,27 @@ def test_chain_batch_large_problems(ctx):
             assert len(wu) == len(u) and (wu == u).all() and len(wb) == len(b) and (wb == b).all(), (mode, len(a))
 
 
+def test_chain_batch_gigabase_prechain(ctx):
+    """Pre-chain problems of the size a gigabase genome produces (every one above the shared-memory classes: the
+    warp-cooperative global-memory backtrack): dense block ids and the sparse shape (most anchors alone in their block)."""
+    rng = np.random.default_rng(2024)
+    par = ol.chain_par("pre")
+    lists = [ol.random_chain_problem(rng, n, "pre") for n in (50000, 150000, 300000)]
+    for n in (60000, 200000):  # sparse: block ids spread over 40 n blocks, a few planted collinear runs
+        x = np.sort(rng.integers(1000, 1000 + 40 * n, size=n)).astype(np.uint64)
+        runs = rng.integers(0, n - 40, size=n // 200)
+        for r in runs:
+            x[r:r + 30] = x[r] + np.arange(30, dtype=np.uint64) // 3
+        x = np.sort(x)
+        y = ((x.astype(np.int64) * 85) % 380 + rng.integers(0, 6, size=n) + 5).astype(np.uint64)
+        lists.append(np.ascontiguousarray(np.unique((x << np.uint64(32)) | y), dtype=np.uint64))
+    mpar = mp.ChainPar(**{f: getattr(par, f) for f, _ in mp.ChainPar._fields_})
+    got = mp.chain_batch(ctx, mpar, lists)
+    for a, (u, b) in zip(lists, got):
+        wu, wb = ol.ora_chain(par, a)
+        assert len(wu) == len(u) and (wu == u).all() and len(wb) == len(b) and (wb == b).all(), len(a)
+
+
 def test_seed_batch_matches_oracle(ctx, tmp_path):
     """mpb_seed_batch (sketch, adaptive occupancy cut-off, bucket expansion, sort) against the oracle's restatement of
     map.c:126-177 on the same index, protein by protein."""

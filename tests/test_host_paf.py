@@ -40,3 +40,25 @@ def test_synthetic_golden(hc, tmp_path, cfg):
     assert run(hc, g, p, str(tmp_path / "o.paf")) == want
     # batch boundaries must not matter (SURVEY 8b determinism contract): 3 proteins per mini-batch
     assert run(hc, g, p, str(tmp_path / "o2.paf"), mini_batch=1200) == want
+
+
+FORMATS = {"gff": (0x8, None), "gtf": (0x20, None), "aln": (0x80, None), "trans": (0x100 | 0x4, None), "gff_only": (0x8 | 0x10, "#")}
+
+
+@pytest.mark.parametrize("fmt", sorted(FORMATS))
+def test_other_output_formats_golden(hc, tmp_path, fmt, monkeypatch):
+    """GFF3 / GTF / --aln / --trans / --gff-only with --gff-delim (format.c:189-452) against the reference's output: the set
+    with every CIGAR operation (tiny5) and the bundled DPP3 pair (md5s of SURVEY App. D)."""
+    import gzip
+
+    flag, delim = FORMATS[fmt]
+    if delim:
+        monkeypatch.setenv("HC_GFF_DELIM", delim)
+    g, p = synth.generate(synth.CONFIGS["tiny5"], str(tmp_path))
+    gold = os.path.join(GOLD, f"tiny5_{fmt}.txt")
+    want = gzip.open(gold + ".gz", "rb").read() if os.path.exists(gold + ".gz") else open(gold, "rb").read()
+    assert run(hc, g, p, str(tmp_path / "o.txt"), flag=flag) == want
+    assert run(hc, g, p, str(tmp_path / "o2.txt"), flag=flag, mini_batch=1200) == want  # the hit counter runs across mini-batches
+    if os.path.exists(os.path.join(DATA, "DPP3-hs.gen.fa.gz")):
+        got = run(hc, os.path.join(DATA, "DPP3-hs.gen.fa.gz"), os.path.join(DATA, "DPP3-mm.pep.fa.gz"), str(tmp_path / "d.txt"), flag=flag)
+        assert got == open(os.path.join(GOLD, f"DPP3_{fmt}.txt"), "rb").read()
