@@ -193,6 +193,14 @@ mpb_ctx_t *mpb_ctx_default(void);
 
 /* Make the read-only index resident in HBM (ki, kb, bo, 4-bit genome, contig table). */
 int mpb_idx_upload(mpb_ctx_t *ctx, const mp_idx_t *mi);
+/* Restore a .mpi index straight into HBM: the k-mer tables are streamed from the file through pinned staging buffers and
+ * never materialise on the host (the returned index has ki == kb == NULL; the genome section is kept on the host too).
+ * Replaces mp_idx_restore (index.c:204) + mpb_idx_upload for a process that only maps.  NULL on failure. */
+mp_idx_t *mpb_idx_load_device(mpb_ctx_t *ctx, const char *fn);
+/* Host part of a .mpi file only (options, contig table, block offsets, genome): for the ranks whose k-mer tables arrive by
+ * broadcast (mpb_idx_attach_device).  mpb_idx_device_ptrs: where a context keeps its resident index (broadcast source). */
+mp_idx_t *mpb_idx_load_meta(const char *fn);
+int mpb_idx_device_ptrs(mpb_ctx_t *ctx, void **d_ki, void **d_kb, void **d_seq);
 /* Multi-GPU: adopt device buffers that were filled by an NCCL broadcast from rank 0 instead of
  * uploading from the host (sizes: ki 8*n_bucket, kb 4*n_kb, seq (l_seq+1)/2 bytes). The host-side
  * mp_idx_t must still carry nt->ctg[], bo[], n_kb and opt (small metadata). */

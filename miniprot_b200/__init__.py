@@ -110,6 +110,11 @@ def lib() -> C.CDLL:
         L.mp_idx_dump.argtypes = [C.c_char_p, C.POINTER(Idx)]
         L.mp_idx_destroy.argtypes = [C.POINTER(Idx)]
         L.mpb_idx_upload.argtypes = [C.c_void_p, C.POINTER(Idx)]
+        L.mpb_idx_load_device.restype = C.POINTER(Idx)
+        L.mpb_idx_load_meta.restype = C.POINTER(Idx)
+        L.mpb_idx_load_meta.argtypes = [C.c_char_p]
+        L.mpb_idx_device_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.mpb_idx_load_device.argtypes = [C.c_void_p, C.c_char_p]
         L.mpb_idx_attach_device.argtypes = [C.c_void_p, C.POINTER(Idx), C.c_void_p, C.c_void_p, C.c_void_p]
         L.mpb_map_file_path.restype = C.c_int32
         L.mpb_map_file_path.argtypes = [C.c_void_p, C.POINTER(Idx), C.c_char_p, C.POINTER(MapOpt), C.c_char_p]
@@ -174,6 +179,14 @@ def idx_load(path: str, n_threads: int = 8, io: IdxOpt | None = None):
     mi = lib().mp_idx_load(path.encode(), C.byref(io), n_threads)
     if not mi:
         raise RuntimeError(f"cannot load index from {path}")
+    return mi
+
+
+def idx_load_device(ctx: Context, path: str):
+    """mpb_idx_load_device: restore a .mpi file straight into the context's HBM (no host copy of the k-mer tables)."""
+    mi = lib().mpb_idx_load_device(ctx.h, path.encode())
+    if not mi:
+        raise RuntimeError(f"cannot load index {path} into device memory")
     return mi
 
 

@@ -255,6 +255,7 @@ static void upload_meta(mpb_ctx_s *c, const mp_idx_t *mi)
 int mpb_idx_upload(mpb_ctx_t *c, const mp_idx_t *mi)
 {
 	if (!c || !mi) return -1;
+	if (!mi->ki || !mi->kb) return c->mi == mi && c->d_ki ? 0 : -1; // loaded straight into HBM: already resident in its own context, not uploadable elsewhere
 	MPB_CUDA_OK(cudaSetDevice(c->device));
 	const size_t nb = idx_n_bucket(&mi->opt), seq_bytes = (size_t)((mi->nt->l_seq + 1) >> 1);
 	c->own_ki.reserve(sizeof(int64_t) * (nb + 1));
@@ -268,6 +269,75 @@ int mpb_idx_upload(mpb_ctx_t *c, const mp_idx_t *mi)
 	upload_meta(c, mi);
 	c->mi = mi, c->own_index = true;
 	c->stats.h2d_bytes += (int64_t)(sizeof(int64_t) * nb + sizeof(uint32_t) * (size_t)mi->n_kb + seq_bytes);
+	return 0;
+}
+
+// .mpi file -> HBM: the k-mer tables ki / kb -- 85-90 % of the file, needed on the device only -- never get a
+// host copy: the file is read in 32 MB pieces into two pinned buffers and each piece leaves for the device while the next
+// one is being read.  The genome section is kept on the host as well (statistics, cs tags, output formats read it).  The
+// returned index has ki == kb == NULL; everything of the library works with it except mp_idx_dump / mp_idx_print_stat.
+mp_idx_t *mpb_idx_load_device(mpb_ctx_t *c, const char *fn)
+{
+	if (!c || !fn) return 0;
+	MPB_CUDA_OK(cudaSetDevice(c->device));
+	FILE *fp = fopen(fn, "rb");
+	if (!fp) return 0;
+	mp_idx_t *mi = idx_restore_head(fp);
+	if (!mi) { fclose(fp); return 0; }
+	const size_t nb = idx_n_bucket(&mi->opt), seq_bytes = (size_t)((mi->nt->l_seq + 1) >> 1);
+	c->own_ki.reserve(sizeof(int64_t) * (nb + 1));
+	c->own_kb.reserve(sizeof(uint32_t) * (size_t)(mi->n_kb + 1));
+	c->own_seq.reserve(seq_bytes + 16);
+	MPB_CUDA_OK(cudaMemcpyAsync(c->own_seq.p, mi->nt->seq, seq_bytes, cudaMemcpyHostToDevice, c->stream));
+	const size_t piece = (size_t)32 << 20;
+	c->h_c[1].reserve(piece), c->h_c[2].reserve(piece);
+	cudaEvent_t done[2];
+	MPB_CUDA_OK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+	MPB_CUDA_OK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+	bool ok = true;
+	int turn = 0;
+	auto stream_section = [&](char *dst, size_t bytes) {
+		for (size_t off = 0; off < bytes && ok; off += piece, turn ^= 1) {
+			const size_t n = std::min(piece, bytes - off);
+			PinBuf &pb = c->h_c[1 + turn];
+			MPB_CUDA_OK(cudaEventSynchronize(done[turn])); // the copy that last used this buffer has left
+			ok = fread(pb.p, 1, n, fp) == n;
+			if (!ok) break;
+			MPB_CUDA_OK(cudaMemcpyAsync(dst + off, pb.p, n, cudaMemcpyHostToDevice, c->stream));
+			MPB_CUDA_OK(cudaEventRecord(done[turn], c->stream));
+		}
+	};
+	stream_section((char*)c->own_ki.p, sizeof(int64_t) * nb);
+	stream_section((char*)c->own_kb.p, sizeof(uint32_t) * (size_t)mi->n_kb);
+	fclose(fp);
+	if (ok) MPB_CUDA_OK(cudaMemcpyAsync(c->own_ki.as<int64_t>() + nb, &mi->n_kb, sizeof(int64_t), cudaMemcpyHostToDevice, c->stream)); // sentinel
+	MPB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	cudaEventDestroy(done[0]), cudaEventDestroy(done[1]);
+	if (!ok) { mp_idx_destroy(mi); return 0; }
+	c->d_ki = c->own_ki.as<int64_t>(), c->d_kb = c->own_kb.as<uint32_t>(), c->d_seq = c->own_seq.as<uint8_t>();
+	upload_meta(c, mi);
+	c->mi = mi, c->own_index = true;
+	c->stats.h2d_bytes += (int64_t)(sizeof(int64_t) * nb + sizeof(uint32_t) * (size_t)mi->n_kb + seq_bytes);
+	if (mp_verbose >= 3) fprintf(stderr, "[M::%s@%.3f] loaded the index into device memory\n", __func__, mp_realtime());
+	return mi;
+}
+
+// the head of a .mpi file only (options, contig table, genome): what a rank needs on the host when the k-mer tables reach its GPU
+// through the NCCL broadcast (mpb_idx_attach_device)
+mp_idx_t *mpb_idx_load_meta(const char *fn)
+{
+	FILE *fp = fn ? fopen(fn, "rb") : 0;
+	if (!fp) return 0;
+	mp_idx_t *mi = idx_restore_head(fp);
+	fclose(fp);
+	return mi;
+}
+
+// device addresses of the resident index of a context (the source buffers of the broadcast on the rank that loaded the file)
+int mpb_idx_device_ptrs(mpb_ctx_t *c, void **d_ki, void **d_kb, void **d_seq)
+{
+	if (!c || !c->d_ki) return -1;
+	*d_ki = c->d_ki, *d_kb = c->d_kb, *d_seq = c->d_seq;
 	return 0;
 }
 

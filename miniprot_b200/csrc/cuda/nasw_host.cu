@@ -58,11 +58,19 @@ static PairLimits pair_limits(const ns_opt_t *o)
 	if (dmin < 0) l.dmax = 1 << 20; // negative splice penalties: not a case the value-domain argument covers
 	return l;
 }
+// Which problems they serve by default is a measured choice (profiles/README.md, tools/dp_bench.py on B200): global alignments
+// of up to 64 padded columns (one warp, 1.25-1.4x the block-wide kernel) and extensions of 33..64 columns (one warp instead
+// of two with a barrier); narrower extensions and everything wider stay on the block-wide kernels.  MPB_NASW_KERNEL=pair sends
+// every eligible problem to them (tests of the multi-warp form).
 static inline bool use_pair(const DpDev &j, const ns_opt_t *o, const PairLimits &l)
 {
 	if (g_forced_family == 1 || g_forced_family == 2) return false;
 	const int W8 = (j.al + 7) / 8 * 8;
 	if (nsw::pair_warps_for(W8) == 0 || j.nl < 3) return false;
+	if (g_forced_family != 3) {
+		const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
+		if (W8 > 64 || (!is_tb && W8 <= 32)) return false;
+	}
 	return nsw::pair_eligible(j.al, o->go, o->ge, j.io, o->fs, o->end_bonus, l.smin, l.smax, l.dmax, l.amax);
 }
 
@@ -289,6 +297,10 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	for (int k = 0; k < n; ++k) {
 		const DpDev &j = jobs[lo + k];
 		out.score[lo + k] = ho[k].x, out.nt_len[lo + k] = ho[k].y, out.aa_len[lo + k] = ho[k].z;
+		if (ho[k].y == -2 && ho[k].z == -2) { // the watchdog of the pair-lane kernels (nasw_pair_kernels.cu): never in a correct run
+			fprintf(stderr, "[miniprot_b200] nasw: the warps of problem %d (nl=%d al=%d flag=%d) stopped waiting for each other\n", k, j.nl, j.al, j.flag);
+			abort();
+		}
 		if (!unsupported.empty() && std::find(unsupported.begin(), unsupported.end(), k) != unsupported.end()) {
 			out.score[lo + k] = INT32_MIN, out.nt_len[lo + k] = -1, out.aa_len[lo + k] = 0;
 			out.cig_off[lo + k + 1] = (int64_t)out.cig.size();
@@ -313,7 +325,7 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_
 	if (n == 0) return;
 	{
 		const char *e = getenv("MPB_NASW_KERNEL");
-		g_forced_family = !e ? 0 : strcmp(e, "cols") == 0 ? 1 : strcmp(e, "v3") == 0 ? 2 : 0; // anything else: pair-lane kernels where eligible, block-wide otherwise
+		g_forced_family = !e ? 0 : strcmp(e, "cols") == 0 ? 1 : strcmp(e, "v3") == 0 ? 2 : strcmp(e, "pair") == 0 ? 3 : 0;
 	}
 	NaswConst cst;
 	fill_const(base, cst);

@@ -49,7 +49,14 @@ NSW_HD uint32_t vam_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax
 NSW_HD uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 NSW_HD uint32_t vmax(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
 NSW_HD uint32_t vadd(uint32_t a, uint32_t b) { return __vadd2(a, b); }
-NSW_HD uint32_t bperm(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+// prmt.b32 in its default mode: selector nibble = source byte 0..7 (a, then b); bit 3 of a nibble replicates the SIGN of that byte
+// instead of copying it (PTX ISA).  __byte_perm() only promises the three low bits, hence the instruction itself.
+NSW_HD uint32_t bperm(uint32_t a, uint32_t b, uint32_t sel)
+{
+	uint32_t d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+	return d;
+}
 // max per half; *ge_lo / *ge_hi = (a >= b) of that half (VIMNMX.S16x2 with predicate outputs)
 NSW_HD uint32_t vbmax(uint32_t a, uint32_t b, bool *ge_hi, bool *ge_lo) { return __vibmax_s16x2(a, b, ge_hi, ge_lo); }
 NSW_HD uint32_t vmaxu(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
@@ -145,6 +152,7 @@ NSW_HD PairRec make_pair_rec(const RowWord &rw, int m, int io, int ge, int fs, i
 // RELAY of the left warp's last column (nasw_pair_kernels.cu), so they hold 31 pairs
 NSW_HD int pair_warps_for(int W8) { return W8 <= 64 ? 1 : W8 <= 126 ? 2 : W8 <= 250 ? 4 : W8 <= 498 ? 8 : 0; }
 NSW_HD int pair_index(int warp, int lane) { return warp == 0 ? lane : lane == 0 ? -1 : 32 + 31 * (warp - 1) + lane - 1; } // -1 = relay lane
+NSW_HD int pair_warp_of(int p) { return p < 32 ? 0 : 1 + (p - 32) / 31; }                     // the warp that holds column pair p
 NSW_HD int pair_triples(int nl) { return nl > 2 ? (nl - 2 + 2) / 3 : 0; }
 NSW_HD int pair_rec_slots(int nl) { return (pair_triples(nl) + 2) / 2 + 1; }                  // records 0 .. triples, per parity of the triple index
 // Device layout of the records of one problem, in 16-byte fields: [parity of the triple index][block of 32 records][field 0..5][32 records].

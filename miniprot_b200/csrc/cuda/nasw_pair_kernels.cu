@@ -28,6 +28,7 @@ using namespace nsw;
 
 constexpr int PAIR_TRI = 1024;  // triples per prep CTA
 constexpr int PAIR_SLOTS = 8;   // depth of the ring between neighbouring warps (macro-steps a warp may run ahead of its right neighbour)
+constexpr unsigned PAIR_SPIN_LIMIT = 1u << 26; // polls a warp may spend waiting for its neighbours over a whole problem before it declares the exchange stuck
 constexpr int PAIR_PROF_HI = 22 * 128; // byte offset of the high-half profile table of a warp
 
 __device__ __forceinline__ int pair_job_code(const uint8_t *packed, const DpDev &j, int k)
@@ -136,7 +137,8 @@ __global__ void __launch_bounds__(NW * 32) nasw_pair_kernel(const DpDev *jobs, c
 	// ---- who is who in this warp
 	const int p_first = warp == 0 ? 0 : 32 + 31 * (warp - 1), p_last_w = min(p_first + (warp == 0 ? 31 : 30), W8 / 2 - 1); // live pairs of this warp
 	const int p_end = W8 / 2 - 1;                     // the pair that owns the problem's last column
-	const bool trk_warp = !TB && warp == NW - 1;
+	const int NWL = pair_warp_of(p_end) + 1;          // warps with live columns (the launch rounds the count up to a power of two): the rest sit idle
+	const bool trk_warp = !TB && warp == NWL - 1;
 	const int lane_end = warp == 0 ? p_end : p_end - p_first + 1; // its lane (meaningful in the last warp)
 	WarpTracker trk;
 	trk.init(PAIR_CB);
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(NW * 32) nasw_pair_kernel(const DpDev *jobs, c
 	const bool has_end_lo = live && col == al - 1, has_end_hi = live && col + 1 == al - 1;
 	uint16_t *tbp = TB ? tb + job.tb_off + col : 0;
 	bool stopped = false;
+	unsigned spins = 0; // watchdog of the inter-warp waits
 
 	// ---- exchange between warps --------------------------------------------------------------------------------------------
 	// take the slot of macro-step T - 1 from the left warp into the relay lane's output registers (T >= 1)
@@ -176,14 +179,16 @@ __global__ void __launch_bounds__(NW * 32) nasw_pair_kernel(const DpDev *jobs, c
 			}
 			if (__all_sync(0xffffffffu, ok)) break;
 			if (lds32(sf)) { stopped = true; break; }
+			if (++spins > PAIR_SPIN_LIMIT) { if (lane == 0) sts32(sf, 2); stopped = true; break; } // never in a correct run: give up instead of hanging the GPU
 		}
 		if (lane == 0) sts32(cons_mine, T);
 	};
 	// hand the last lane's outputs of macro-step T to the right warp
 	auto relay_out = [&](int T) {
-		if (NW == 1 || warp == NW - 1) return;
+		if (NW == 1 || warp >= NWL - 1) return;
 		while (T - lds32(cons_next) >= PAIR_SLOTS) { // the right warp still needs the slot this one would overwrite
 			if (lds32(sf)) { stopped = true; return; }
+			if (++spins > PAIR_SPIN_LIMIT) { if (lane == 0) sts32(sf, 2); stopped = true; return; }
 		}
 		if (lane == 31) {
 			const uint32_t a = ch_out + (uint32_t)(T & (PAIR_SLOTS - 1)) * 64;
@@ -199,6 +204,9 @@ __global__ void __launch_bounds__(NW * 32) nasw_pair_kernel(const DpDev *jobs, c
 
 	// ---- one macro-step; hb[PH] receives this step's left H, hb[PH ^ 1] holds the previous step's
 	uint32_t hb[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } };
+	PairRec rcs[2]; // row records of the next even / odd macro-step, fetched two steps ahead
+	pair_load_rec(rec, nb, m_max, 0, p < 0 ? 0 : p, rcs[0]);
+	pair_load_rec(rec, nb, m_max, 1, p < 0 ? 0 : p, rcs[1]);
 #define NSW_PAIR_RECV(PH) \
 		uint32_t rQ[3]; \
 		_Pragma("unroll") for (int r = 0; r < 3; ++r) { \
@@ -220,8 +228,8 @@ __global__ void __launch_bounds__(NW * 32) nasw_pair_kernel(const DpDev *jobs, c
 		constexpr int PH = decltype(ph_tag)::value;
 		if (T > 0) relay_in(T);
 		if (stopped) return;
-		PairRec rc;
-		pair_load_rec(rec, nb, m_max, T, p < 0 ? 0 : p, rc);
+		const PairRec rc = rcs[PH];                               // loaded two macro-steps ago ...
+		pair_load_rec(rec, nb, m_max, T + 2, p < 0 ? 0 : p, rcs[PH]); // ... and the one of step T + 2 leaves now: a whole macro-step to arrive
 		NSW_PAIR_RECV(PH)
 		const uint32_t *pv = hb[PH ^ 1], *cu = hb[PH];
 		if constexpr (TB) {
@@ -288,28 +296,107 @@ __global__ void __launch_bounds__(NW * 32) nasw_pair_kernel(const DpDev *jobs, c
 		}
 		relay_out(T);
 	};
-#undef NSW_PAIR_RECV
 	// steady macro-steps of this warp: both halves of every live thread are on real rows strictly above the last row
 	int t_lo = 2 * p_last_w + 2, t_hi = nl >= 6 ? 2 * p_first + (nl - 6) / 3 + 1 : 0;
 	t_lo += t_lo & 1;
+	if (t_lo > n_macro) t_lo = n_macro; // (n_macro is even)
+	if (t_hi > n_macro) t_hi = n_macro;
 	if (t_hi < t_lo) t_hi = t_lo;
 	t_hi = t_lo + ((t_hi - t_lo) & ~1);
-	if (p_last_w < p_first) t_lo = t_hi = n_macro; // a warp without live columns (cannot happen: the warp count is minimal)
-	int T = 0;
+	int T = warp < NWL ? 0 : n_macro; // a warp without live columns has nothing to do
 	for (; T < t_lo && T < n_macro && !stopped; T += 2) {
 		step(T, std::integral_constant<int, 0>(), false);
 		if (!stopped) step(T + 1, std::integral_constant<int, 1>(), false);
 		if (!TB && NW > 1 && !stopped && lds32(sf)) stopped = true;
 	}
-	for (; T < t_hi && !stopped; T += 2) {
-		step(T, std::integral_constant<int, 0>(), true);
-		if (!stopped) step(T + 1, std::integral_constant<int, 1>(), true);
-		if (!TB && NW > 1 && !stopped && lds32(sf)) stopped = true;
+	// the steady loop, straight-line: no row checks, the row records of step T + 2 are fetched AFTER the rows of step T used the old
+	// ones (same registers, a whole macro-step to arrive), and the only exits are a stuck / stopped neighbour and the x-drop
+	const int pq = p < 0 ? 0 : p;
+#define NSW_PAIR_STEADY(PH) { \
+		if (NW > 1) { relay_in(T + PH); if (stopped) break; } \
+		NSW_PAIR_RECV(PH) \
+		const uint32_t *pv = hb[PH ^ 1], *cu = hb[PH]; \
+		if constexpr (TB) { \
+			uint32_t rF[3], rS[3]; \
+			_Pragma("unroll") for (int r = 0; r < 3; ++r) { \
+				rF[r] = L.left_of(__shfl_up_sync(0xffffffffu, L.oF[r], 1), L.oF[r]); \
+				rS[r] = L.left_of(__shfl_up_sync(0xffffffffu, L.oS[r], 1), L.oS[r]); \
+			} \
+			const uint32_t w0 = L.template row<0>(pp, rcs[PH], env, cu[0], pv[2], pv[1], pv[0], rQ[0], rF[0], rS[0]); \
+			const uint32_t w1 = L.template row<1>(pp, rcs[PH], env, cu[1], cu[0], pv[2], pv[1], rQ[1], rF[1], rS[1]); \
+			const uint32_t w2 = L.template row<2>(pp, rcs[PH], env, cu[2], cu[1], cu[0], pv[2], rQ[2], rF[2], rS[2]); \
+			if (live) { \
+				uint32_t *q = reinterpret_cast<uint32_t*>(tbs); \
+				q[0] = w0, q[Wp / 2] = w1, q[Wp] = w2; \
+			} \
+			tbs += 3 * Wp; \
+		} else { \
+			int lx[3], xp[3]; \
+			_Pragma("unroll") for (int r = 0; r < 3; ++r) lx[r] = (int)((uint32_t)__shfl_up_sync(0xffffffffu, L.oXhi[r], 1) & L.xmask), xp[r] = L.oXlo[r]; \
+			L.template row<0>(pp, rcs[PH], env, cu[0], pv[2], pv[1], pv[0], rQ[0], lx[0], xp[0]); \
+			L.template row<1>(pp, rcs[PH], env, cu[1], cu[0], pv[2], pv[1], rQ[1], lx[1], xp[1]); \
+			L.template row<2>(pp, rcs[PH], env, cu[2], cu[1], cu[0], pv[2], rQ[2], lx[2], xp[2]); \
+			if (trk_warp) { \
+				_Pragma("unroll") for (int r = 0; r < 3; ++r) sts32(ring_w + (trk.n_ring + r) * 128, L.oXhi[r]); \
+				trk.n_ring += 3; \
+				if (trk.n_ring >= 30) trk.flush(ring_r, lane, al * 3, cst.pen, cst.xdrop); \
+			} \
+		} \
+		{ /* record of step T + PH + 2: slot ks + 1 of the parity array of this step (advanced once per loop iteration) */ \
+			const uint4 *q = rq[PH] + (ks + 1 + ((ks + 1) >> 5) * 160); \
+			_Pragma("unroll") for (int f = 0; f < 6; ++f) { \
+				const uint4 v = __ldg(q + f * 32); \
+				rcs[PH].w[4 * f] = v.x, rcs[PH].w[4 * f + 1] = v.y, rcs[PH].w[4 * f + 2] = v.z, rcs[PH].w[4 * f + 3] = v.w; \
+			} \
+		} \
+		if (NW > 1) { relay_out(T + PH); if (stopped) break; } }
+	{
+		uint16_t *tbs = TB ? tbp + (int64_t)3 * T * Wp : 0;
+		(void)tbs;
+		// In the steady range every live thread is on stored records (no clamping); idle threads to the right of the last column
+		// read the records of the last live pair.  Record m of a thread sits at slot k = m >> 1 of its parity: slot k of a parity
+		// array is at 16-byte index (k >> 5) * 192 + (k & 31) = k + (k >> 5) * 160.
+		const int ps = pq > p_last_w ? p_last_w : pq;
+		const uint4 *rq[2] = { rec, rec + (size_t)nb * 192 }; // even / odd triples (T is even at the loop head: step T + PH has parity PH)
+		int ks = (T - 2 * ps) >> 1;                           // slot of step T (and of step T + 1)
+		if (T < t_hi) { // the general loop fetched with clamped indices: re-fetch the two records in flight for THIS thread mapping
+			pair_load_rec(rec, nb, m_max, T, ps, rcs[0]);
+			pair_load_rec(rec, nb, m_max, T + 1, ps, rcs[1]);
+		}
+		for (; T < t_hi && !stopped; T += 2, ++ks) {
+			if ((T & 14) == 0) { // every eighth iteration (warp-uniform): a lane moves on by one 16-byte record per iteration, so its lines 32 records ahead are due
+				const uint4 *pf = rq[0] + (ks + 40 + ((ks + 40) >> 5) * 160);
+#pragma unroll
+				for (int f = 0; f < 6; ++f) {
+					asm volatile("prefetch.global.L1 [%0];" :: "l"(pf + f * 32));
+					asm volatile("prefetch.global.L1 [%0];" :: "l"(pf + (size_t)nb * 192 + f * 32));
+				}
+			}
+			NSW_PAIR_STEADY(0)
+			NSW_PAIR_STEADY(1)
+			if (!TB) {
+				if (trk_warp) { if (trk.stopped) { if (NW > 1 && lane == 0) sts32(sf, 1); stopped = true; } }
+				else if (NW > 1 && lds32(sf)) stopped = true;
+			}
+		}
+	}
+#undef NSW_PAIR_STEADY
+#undef NSW_PAIR_RECV
+	if (T < n_macro && !stopped) { // back to the general loop: its records (clamped indices, own pair) for the next two steps
+		pair_load_rec(rec, nb, m_max, T, pq, rcs[0]);
+		pair_load_rec(rec, nb, m_max, T + 1, pq, rcs[1]);
 	}
 	for (; T < n_macro && !stopped; T += 2) {
 		step(T, std::integral_constant<int, 0>(), false);
 		if (!stopped) step(T + 1, std::integral_constant<int, 1>(), false);
 		if (!TB && NW > 1 && !stopped && lds32(sf)) stopped = true;
+	}
+	if (NW > 1) { // a stuck exchange (stop_flag == 2) is reported instead of a result: the host aborts the wave loudly
+		__syncthreads();
+		if (stop_flag == 2) {
+			if (threadIdx.x == 0) out[jid] = make_int4(INT32_MIN, -2, -2, 0);
+			return;
+		}
 	}
 	if (TB) {
 		if (have_score) out[jid] = make_int4(tb_score, nl, al, 0);

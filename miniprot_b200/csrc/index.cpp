@@ -163,6 +163,7 @@ void mp_idx_destroy(mp_idx_t *mi)
 
 int mp_idx_dump(const char *fn, const mp_idx_t *mi) // index.c:189-202
 {
+	if (!mi->ki || !mi->kb) return -1; // an index that was loaded straight into HBM (mpb_idx_load_device) has no host copy of ki / kb
 	FILE *fp = strcmp(fn, "-") == 0 ? stdout : fopen(fn, "wb");
 	if (!fp) return -1;
 	fwrite(MP_IDX_MAGIC, 1, 4, fp);
@@ -175,12 +176,14 @@ int mp_idx_dump(const char *fn, const mp_idx_t *mi) // index.c:189-202
 	return 0;
 }
 
-mp_idx_t *mp_idx_restore(const char *fn) // index.c:204-229
+} // extern "C"
+
+// Head of a .mpi file (index.c:204-220): magic, index options, n_kb and the genome section; on return fp stands at the first
+// byte of ki (8 * n_bucket bytes, followed by 4 * n_kb bytes of kb).  The result has no ki / kb yet.
+mp_idx_t *mpb::idx_restore_head(FILE *fp)
 {
-	FILE *fp = strcmp(fn, "-") == 0 ? stdin : fopen(fn, "rb");
 	char magic[4];
-	if (!fp) return 0;
-	if (fread(magic, 1, 4, fp) != 4 || memcmp(magic, MP_IDX_MAGIC, 4) != 0) { if (fp != stdin) fclose(fp); return 0; }
+	if (fread(magic, 1, 4, fp) != 4 || memcmp(magic, MP_IDX_MAGIC, 4) != 0) return 0;
 	mp_idx_t *mi = (mp_idx_t*)calloc(1, sizeof(mp_idx_t));
 	bool ok = fread(&mi->opt, sizeof(mi->opt), 1, fp) == 1 && fread(&mi->n_kb, 8, 1, fp) == 1;
 	if (ok) {
@@ -188,7 +191,21 @@ mp_idx_t *mp_idx_restore(const char *fn) // index.c:204-229
 		mi->nt = ntdb_restore(fp);
 		ok = mi->nt != 0;
 	}
-	if (ok) {
+	if (!ok) { mp_idx_destroy(mi); return 0; }
+	mi->bo = block_offsets(mi->nt, mi->opt.bbit, &mi->n_block);
+	return mi;
+}
+
+extern "C" {
+
+mp_idx_t *mp_idx_restore(const char *fn) // index.c:204-229
+{
+	FILE *fp = strcmp(fn, "-") == 0 ? stdin : fopen(fn, "rb");
+	if (!fp) return 0;
+	mp_idx_t *mi = idx_restore_head(fp);
+	if (!mi) { if (fp != stdin) fclose(fp); return 0; }
+	bool ok = true;
+	{
 		const uint32_t nb = idx_n_bucket(&mi->opt);
 		mi->ki = (int64_t*)malloc(sizeof(int64_t) * nb);
 		mi->kb = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(mi->n_kb ? mi->n_kb : 1));
@@ -196,7 +213,6 @@ mp_idx_t *mp_idx_restore(const char *fn) // index.c:204-229
 	}
 	if (fp != stdin) fclose(fp);
 	if (!ok) { mp_idx_destroy(mi); return 0; }
-	mi->bo = block_offsets(mi->nt, mi->opt.bbit, &mi->n_block);
 	if (mp_verbose >= 3) fprintf(stderr, "[M::%s@%.3f] loaded the index\n", __func__, mp_realtime());
 	return mi;
 }

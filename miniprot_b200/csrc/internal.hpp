@@ -1,6 +1,7 @@
 // internal.hpp -- declarations shared by the host side of libminiprot_b200 (not installed).
 #pragma once
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
@@ -34,6 +35,7 @@ static inline uint8_t nt_at_v(const mp_ntdb_t *db, uint32_t vid, int64_t pos) //
 // ---------------------------------------------------------------- index (index.cpp)
 extern void (*g_idx_destroy_hook)(const mp_idx_t *);                           // set by the CUDA backend
 int32_t idx_block2vid(const mp_idx_t *mi, uint32_t block);                  // index.c:41
+mp_idx_t *idx_restore_head(FILE *fp);                                        // .mpi up to (not including) ki / kb
 static inline uint32_t idx_n_bucket(const mp_idxopt_t *io) { return 1U << (io->kmer * 4 - io->mod_bit); }
 uint32_t hash32_mask(uint32_t key, uint32_t mask);                           // sketch.c:7
 // genome-side sketch of one strand (sketch.c:62); host code, used by the index builder only

@@ -63,3 +63,26 @@ def test_small_vs_reference_cli(ctx, tmp_path, cfg, args, over):
         a, b = got.decode().splitlines(), want.decode().splitlines()
         diff = [(x[:200], y[:200]) for x, y in zip(a, b) if x != y][:3]
         pytest.fail(f"{cfg} {args}: {len(a)} vs {len(b)} lines; first diffs: {diff}")
+
+
+def test_index_loaded_straight_into_hbm(ctx, tmp_path):
+    """mpb_idx_load_device: the .mpi file goes to the device through pinned staging buffers, the host keeps no ki / kb
+    (SURVEY 8f #3); mapping with it gives the golden PAF, and an index written by the reference CLI loads the same way."""
+    g, p = synth.generate(synth.CONFIGS["tiny"], str(tmp_path))
+    want = open(os.path.join(GOLD, "tiny.paf"), "rb").read()
+    L = mp.lib()
+    mi0 = mp.idx_load(g, 4)
+    ours = str(tmp_path / "ours.mpi")
+    assert L.mp_idx_dump(ours.encode(), mi0) == 0
+    L.mp_idx_destroy(mi0)
+    files = [ours]
+    if os.path.exists(ol.REF_BIN):
+        ref = str(tmp_path / "ref.mpi")
+        subprocess.run([ol.REF_BIN, "-t4", "-d", ref, g], check=True, capture_output=True)
+        files.append(ref)
+    for f in files:
+        mi = mp.idx_load_device(ctx, f)
+        assert not mi.contents.ki and not mi.contents.kb
+        mp.map_file(ctx, mi, p, str(tmp_path / "o.paf"))
+        L.mp_idx_destroy(mi)
+        assert open(str(tmp_path / "o.paf"), "rb").read() == want

@@ -31,10 +31,10 @@ def _par(opt):
                 sp_null_bonus=opt.sp_null_bonus, ie_coef=opt.ie_coef)
 
 
-@pytest.mark.parametrize("model,family", [(1, "auto"), (2, "v3"), (1, "v3"), (2, "cols")])
+@pytest.mark.parametrize("model,family", [(1, "auto"), (2, "pair"), (1, "pair"), (2, "v3"), (1, "v3"), (2, "cols")])
 def test_nasw_batch_matches_oracle(ctx, model, family, monkeypatch):
-    """family: which kernel family serves the problems -- the block-wide wavefront (v3), the column-pass kernels, or the
-    production heuristic (long problems v3, short ones column passes)."""
+    """family: which kernel family serves the problems -- the pair-lane kernels for everything they are eligible for (incl. their
+    multi-warp form), the block-wide wavefront (v3), the column-pass kernels, or the production choice (auto)."""
     if family != "auto":
         monkeypatch.setenv("MPB_NASW_KERNEL", family)
     rng = np.random.default_rng(77 + model)

@@ -42,6 +42,13 @@ def _worker(rank, world, d, port, q):
     for t in (ki, kb, sq):
         dist.broadcast(t, 0)
     ok = bool((ki[:nb].numpy() == own_ki).all() and int(ki[nb]) == n_kb and (kb.numpy() == own_kb).all() and (sq.numpy() == own_sq).all())
+    # what a rank other than 0 loads in bench.py: the head of the file only (no host copy of ki / kb)
+    meta = L.mpb_idx_load_meta(mpi.encode())
+    ok = ok and bool(meta) and not meta.contents.ki and not meta.contents.kb and meta.contents.n_kb == n_kb and meta.contents.nt.contents.l_seq == l_seq
+    ok = ok and meta.contents.n_block == mi.contents.n_block and meta.contents.nt.contents.n_ctg == mi.contents.nt.contents.n_ctg
+    n_bo = 2 * mi.contents.nt.contents.n_ctg + 1
+    ok = ok and bytes(C.string_at(meta.contents.bo, 4 * n_bo)) == bytes(C.string_at(mi.contents.bo, 4 * n_bo))
+    L.mp_idx_destroy(meta)
     shard = synth.shard_queries(spec, d, rank)
     names = [l[1:].strip() for l in open(shard) if l.startswith(">")]
     q.put((rank, ok, names[:3], len(names)))
