@@ -47,7 +47,7 @@ struct NaswConst {              // problem-independent parameters, passed by val
 
 // pair-lane family (nasw_pair_kernels.cu): chunks carry {job, first triple, number of triples}
 void nasw_launch_prep_pair(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, int4 *rec);
-void nasw_launch_pair(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out,
+void nasw_launch_pair(cudaStream_t st, bool is_tb, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out,
                       uint16_t *tb);
 void nasw_launch_prep(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, int4 *rec);
 void nasw_launch_ext(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, int *carry);

@@ -58,18 +58,19 @@ static PairLimits pair_limits(const ns_opt_t *o)
 	if (dmin < 0) l.dmax = 1 << 20; // negative splice penalties: not a case the value-domain argument covers
 	return l;
 }
-// Which problems they serve by default is a measured choice (profiles/README.md, tools/dp_bench.py on B200): global alignments
-// of up to 64 padded columns (one warp, 1.25-1.4x the block-wide kernel) and extensions of 33..64 columns (one warp instead
-// of two with a barrier); narrower extensions and everything wider stay on the block-wide kernels.  MPB_NASW_KERNEL=pair sends
-// every eligible problem to them (tests of the multi-warp form).
+// Which problems they serve by default is a measured choice (profiles/README.md; tools/dp_bench.py and bench.py A/B on B200): global
+// alignments of up to 64 padded columns, where one warp of the pair-lane kernel replaces one or two warps of the block-wide kernel at
+// 1.25-1.4x its speed.  Score-only extensions stay on the block-wide kernels: there the pair-lane form needs 172-189 cycles per row
+// against 137 (<= 32 columns) / 152 (33..64 columns, two warps) -- its 64 columns per warp do not pay for the 32-bit row-maximum
+// bookkeeping that an extension carries per cell.  MPB_NASW_KERNEL=pair sends every problem of up to 64 columns to them (tests, A/B).
 static inline bool use_pair(const DpDev &j, const ns_opt_t *o, const PairLimits &l)
 {
 	if (g_forced_family == 1 || g_forced_family == 2) return false;
 	const int W8 = (j.al + 7) / 8 * 8;
-	if (nsw::pair_warps_for(W8) == 0 || j.nl < 3) return false;
+	if (W8 > nsw::PAIR_MAX_W8 || j.nl < 3) return false;
 	if (g_forced_family != 3) {
 		const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
-		if (W8 > 64 || (!is_tb && W8 <= 32)) return false;
+		if (!is_tb) return false;
 	}
 	return nsw::pair_eligible(j.al, o->go, o->ge, j.io, o->fs, o->end_bonus, l.smin, l.smax, l.dmax, l.amax);
 }
@@ -108,7 +109,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	std::vector<int> unsupported;
 	const PairLimits plim = pair_limits(nso);
 	constexpr int NCLS = 13;
-	std::vector<int> order[2][NCLS]; // [is_tb][class]: 0..3 block-wide wavefront with 1/2/4/8 warps; 4..7 column passes C = 1/2/4/8; 8 multi-pass; 9..12 pair-lane kernels with 1/2/4/8 warps
+	std::vector<int> order[2][NCLS]; // [is_tb][class]: 0..3 block-wide wavefront with 1/2/4/8 warps; 4..7 column passes C = 1/2/4/8; 8 multi-pass; 9 pair-lane kernels (one warp per problem)
 	for (int k = 0; k < n; ++k) {
 		DpDev &j = jobs[lo + k];
 		const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
@@ -119,8 +120,8 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 			continue;
 		}
 		if (use_pair(j, nso, plim)) { // pair-lane kernels: pair records (96 B per triple of rows), wavefront-major traceback of 64 columns per warp
-			const int W8 = (j.al + 7) / 8 * 8, pw = nsw::pair_warps_for(W8), K = nsw::pair_rec_slots(j.nl), n_macro = nsw::pair_n_macro(j.nl, W8);
-			j.C = 0, j.pad_ = 64 * pw;
+			const int W8 = (j.al + 7) / 8 * 8, K = nsw::pair_rec_slots(j.nl), n_macro = nsw::pair_n_macro(j.nl, W8);
+			j.C = 0, j.pad_ = 64;
 			j.rw_off = rw_tot, rw_tot += (int64_t)192 * nsw::pair_rec_blocks(j.nl); // two parities x blocks x 192 sixteen-byte fields, in units of 32 bytes
 			j.tb_off = j.cig_off = 0, j.cig_cap = 0, j.carry_off = 0;
 			if (is_tb) {
@@ -130,7 +131,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 			}
 			const int n_tri = 2 * K; // record indices 0 .. 2K-1 (the tail past the last real triple is never read unmasked)
 			for (int m = 0; m < n_tri; m += 1024) pchunks.push_back(PrepChunk{ k, m, std::min(1024, n_tri - m), 0 });
-			order[is_tb][9 + (pw == 1 ? 0 : pw == 2 ? 1 : pw == 4 ? 2 : 3)].push_back(k);
+			order[is_tb][9].push_back(k);
 			(is_tb ? ctx->stats.dp_cells_tb : ctx->stats.dp_cells_ext) += (int64_t)j.nl * j.al;
 			(is_tb ? ctx->stats.n_dp_tb : ctx->stats.n_dp_ext) += 1;
 			continue;
@@ -209,7 +210,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
 		MPB_CUDA_OK(cudaEventRecord(ctx->ev_k0[g.sid], ss));
 		if (c >= 9) {
-			nasw_launch_pair(ss, Cs[c], b == 1, dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>());
+			nasw_launch_pair(ss, b == 1, dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>());
 			ctx->stats.kernel_launches += 1;
 			MPB_CUDA_OK(cudaEventRecord(ctx->ev_km[g.sid], ss));
 			if (b == 1) {

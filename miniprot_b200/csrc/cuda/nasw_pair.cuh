@@ -148,11 +148,8 @@ NSW_HD PairRec make_pair_rec(const RowWord &rw, int m, int io, int ge, int fs, i
 	return r;
 }
 
-// ---- geometry of a problem on the kernels: a warp holds 32 column pairs; the warps after the first give their lane 0 to the
-// RELAY of the left warp's last column (nasw_pair_kernels.cu), so they hold 31 pairs
-NSW_HD int pair_warps_for(int W8) { return W8 <= 64 ? 1 : W8 <= 126 ? 2 : W8 <= 250 ? 4 : W8 <= 498 ? 8 : 0; }
-NSW_HD int pair_index(int warp, int lane) { return warp == 0 ? lane : lane == 0 ? -1 : 32 + 31 * (warp - 1) + lane - 1; } // -1 = relay lane
-NSW_HD int pair_warp_of(int p) { return p < 32 ? 0 : 1 + (p - 32) / 31; }                     // the warp that holds column pair p
+// ---- geometry of a problem on the kernels: one warp = 32 column pairs = up to 64 padded columns
+constexpr int PAIR_MAX_W8 = 64;
 NSW_HD int pair_triples(int nl) { return nl > 2 ? (nl - 2 + 2) / 3 : 0; }
 NSW_HD int pair_rec_slots(int nl) { return (pair_triples(nl) + 2) / 2 + 1; }                  // records 0 .. triples, per parity of the triple index
 // Device layout of the records of one problem, in 16-byte fields: [parity of the triple index][block of 32 records][field 0..5][32 records].

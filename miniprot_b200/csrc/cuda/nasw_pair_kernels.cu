@@ -4,13 +4,11 @@
 //
 //   nasw_prep_pair_kernel   packed genome -> pair records (one 96-byte record per triple of rows, entries paired with the row
 //                           three above: what a thread needs when its low column is on triple m and its high column on m-1)
-//   nasw_pair_kernel<NW,TB> one CTA of NW warps per problem, 64 columns in the first warp and 62 in every further one.
-//                           Inside a warp the wavefront moves by shuffles.  BETWEEN warps there is no block-wide barrier: the
-//                           last lane of a warp drops what its right neighbour needs (3 rows x 3..4 registers + the macro-step
-//                           number as a tag in every 16-byte chunk) into a ring of PAIR_SLOTS slots in shared memory; lane 0 of
-//                           the next warp is a RELAY -- it owns no columns, loads that slot straight into its own output registers
-//                           and so feeds lane 1 through the same shuffle as everybody else.  Warps run as far apart as the ring
-//                           allows, each at the speed of a single warp.
+//   nasw_pair_kernel<TB>    one WARP per problem of up to 64 padded columns: the wavefront moves by shuffles only (no shared-memory
+//                           exchange, no barrier).  Wider problems stay on the block-wide kernels of nasw_kernels.cu: a form of this
+//                           kernel with several warps per problem (neighbouring warps linked by a ring of tagged slots in shared
+//                           memory instead of a block-wide barrier) was built and measured in this round and lost to them -- 326 against
+//                           181 cycles per row for 120 columns, independent of the load (profiles/README.md) -- so it is not kept.
 //                           TB = false: score-only extension with the warp-parallel x-drop tracker (nasw_warp.cuh);
 //                           TB = true : global alignment, two traceback words per thread and row in one 32-bit store, in the
 //                           wavefront-major layout nasw_bt_kernel walks.
@@ -27,8 +25,6 @@ namespace cuda {
 using namespace nsw;
 
 constexpr int PAIR_TRI = 1024;  // triples per prep CTA
-constexpr int PAIR_SLOTS = 8;   // depth of the ring between neighbouring warps (macro-steps a warp may run ahead of its right neighbour)
-constexpr unsigned PAIR_SPIN_LIMIT = 1u << 26; // polls a warp may spend waiting for its neighbours over a whole problem before it declares the exchange stuck
 constexpr int PAIR_PROF_HI = 22 * 128; // byte offset of the high-half profile table of a warp
 
 __device__ __forceinline__ int pair_job_code(const uint8_t *packed, const DpDev &j, int k)
@@ -92,37 +88,29 @@ __device__ __forceinline__ void pair_load_rec(const uint4 *base, int nb, int m_m
 	}
 }
 
-template <int NW, bool TB>
-__global__ void __launch_bounds__(NW * 32) nasw_pair_kernel(const DpDev *jobs, const int *order, int n_jobs, const uint4 *rec_all, const char *aa, NaswConst cst,
-                                                            int4 *out, uint16_t *tb)
+template <bool TB>
+__global__ void __launch_bounds__(32) nasw_pair_kernel(const DpDev *jobs, const int *order, int n_jobs, const uint4 *rec_all, const char *aa, NaswConst cst, int4 *out,
+                                                       uint16_t *tb)
 {
-	extern __shared__ uint32_t prof_all[];       // per warp: low-half table, high-half table (22 amino acids x 32 threads each)
-	uint32_t (*prof)[2 * 22 * 32] = reinterpret_cast<uint32_t (*)[2 * 22 * 32]>(prof_all);
-	__shared__ __align__(16) uint32_t chan[NW > 1 ? NW - 1 : 1][PAIR_SLOTS][16];
-	__shared__ int cons[NW];                     // cons[w]: warp w has taken every slot of macro-steps < cons[w] from its left neighbour
+	__shared__ uint32_t prof[2 * 22 * 32];       // low-half table, high-half table (22 amino acids x 32 threads each)
 	__shared__ int ring[TB ? 32 : 32 * 32];      // [slot][lane] row maxima waiting for the warp tracker
-	__shared__ int stop_flag;
 	if ((int)blockIdx.x >= n_jobs) return;
 	const int jid = order[blockIdx.x];
 	const DpDev job = jobs[jid];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x;
 	const int W8 = (job.al + 7) / 8 * 8, nl = job.nl, al = job.al, Wp = job.pad_;
-	const int p = pair_index(warp, lane), col = 2 * p;
-	const bool live = p >= 0 && col < W8;
-	// ---- profile of this thread's two columns
-	{
+	const int p = lane, col = 2 * p;             // this thread's column pair
+	const bool live = col < W8;
+	{ // profile of this thread's two columns
 		int r0 = -1, r1 = -1;
-		if (p >= 0 && col < al) r0 = cst.aa20[(uint8_t)aa[job.aa_off + ((job.flag & NS_F_EXT_LEFT) ? al - 1 - col : col)]];
-		if (p >= 0 && col + 1 < al) r1 = cst.aa20[(uint8_t)aa[job.aa_off + ((job.flag & NS_F_EXT_LEFT) ? al - 2 - col : col + 1)]];
+		if (col < al) r0 = cst.aa20[(uint8_t)aa[job.aa_off + ((job.flag & NS_F_EXT_LEFT) ? al - 1 - col : col)]];
+		if (col + 1 < al) r1 = cst.aa20[(uint8_t)aa[job.aa_off + ((job.flag & NS_F_EXT_LEFT) ? al - 2 - col : col + 1)]];
 		for (int a = 0; a < 22; ++a) {
-			prof[warp][a * 32 + lane] = pk(r0 >= 0 ? cst.mat[a * 22 + r0] : PAIR_DEAD, 0);
-			prof[warp][22 * 32 + a * 32 + lane] = pk(0, r1 >= 0 ? cst.mat[a * 22 + r1] : PAIR_DEAD);
+			prof[a * 32 + lane] = pk(r0 >= 0 ? cst.mat[a * 22 + r0] : PAIR_DEAD, 0);
+			prof[22 * 32 + a * 32 + lane] = pk(0, r1 >= 0 ? cst.mat[a * 22 + r1] : PAIR_DEAD);
 		}
 	}
-	if (threadIdx.x < NW) cons[threadIdx.x] = 0;
-	if (threadIdx.x == 0) stop_flag = 0;
-	for (int k = threadIdx.x; k < (NW > 1 ? NW - 1 : 1) * PAIR_SLOTS * 16; k += NW * 32) (&chan[0][0][0])[k] = 0xffffffffu; // no slot carries a valid tag yet
-	__syncthreads();
+	__syncwarp();
 	const int n_macro = pair_n_macro(nl, W8);
 	PairPar pp;
 	pp.go = cst.go, pp.ge = cst.ge, pp.fs = cst.fs, pp.end_bonus = cst.end_bonus, pp.ngo = pk2(-cst.go), pp.nfs = pk2(-cst.fs);
@@ -131,107 +119,37 @@ __global__ void __launch_bounds__(NW * 32) nasw_pair_kernel(const DpDev *jobs, c
 	typename std::conditional<TB, PairLaneTb, PairLane>::type L;
 	L.init(g, pp);
 	PairEnvDev env;
-	env.prof_base = smem_addr(&prof[warp][lane]);
+	env.prof_base = smem_addr(&prof[lane]);
 	const uint4 *rec = rec_all + job.rw_off * 2;
 	const int nb = pair_rec_blocks(nl), m_max = 2 * pair_rec_slots(nl) - 1; // records 0 .. m_max exist
-	// ---- who is who in this warp
-	const int p_first = warp == 0 ? 0 : 32 + 31 * (warp - 1), p_last_w = min(p_first + (warp == 0 ? 31 : 30), W8 / 2 - 1); // live pairs of this warp
-	const int p_end = W8 / 2 - 1;                     // the pair that owns the problem's last column
-	const int NWL = pair_warp_of(p_end) + 1;          // warps with live columns (the launch rounds the count up to a power of two): the rest sit idle
-	const bool trk_warp = !TB && warp == NWL - 1;
-	const int lane_end = warp == 0 ? p_end : p_end - p_first + 1; // its lane (meaningful in the last warp)
+	const int p_end = W8 / 2 - 1;                // the pair (= lane) that owns the problem's last column
 	WarpTracker trk;
 	trk.init(PAIR_CB);
-	const uint32_t ring_w = smem_addr(ring) + lane * 4, ring_r = smem_addr(ring) + lane * 128 + (uint32_t)(lane_end & 31) * 4;
+	const uint32_t ring_w = smem_addr(ring) + lane * 4, ring_r = smem_addr(ring) + lane * 128 + (uint32_t)p_end * 4;
 	(void)ring_w, (void)ring_r;
-	const uint32_t ch_in = warp > 0 ? smem_addr(&chan[warp > 0 ? warp - 1 : 0][0][0]) : 0, ch_out = smem_addr(&chan[warp < NW - 1 ? warp : 0][0][0]);
-	const uint32_t cons_mine = smem_addr(&cons[warp]), cons_next = smem_addr(&cons[warp < NW - 1 ? warp + 1 : warp]), sf = smem_addr(&stop_flag);
 	int tb_score = 0;
 	bool have_score = false;
 	const bool has_end_lo = live && col == al - 1, has_end_hi = live && col + 1 == al - 1;
 	uint16_t *tbp = TB ? tb + job.tb_off + col : 0;
-	bool stopped = false;
-	unsigned spins = 0; // watchdog of the inter-warp waits
 
-	// ---- exchange between warps --------------------------------------------------------------------------------------------
-	// take the slot of macro-step T - 1 from the left warp into the relay lane's output registers (T >= 1)
-	auto relay_in = [&](int T) {
-		if (NW == 1 || warp == 0) return;
-		const uint32_t a = ch_in + (uint32_t)((T - 1) & (PAIR_SLOTS - 1)) * 64;
-		for (;;) {
-			bool ok = true;
-			if (lane == 0) {
-				const int4 c0 = lds128(a), c1 = lds128(a + 16), c2 = lds128(a + 32);
-				ok = c0.w == T - 1 && c1.w == T - 1 && c2.w == T - 1;
-				if constexpr (TB) {
-					const int4 c3 = lds128(a + 48);
-					ok = ok && c3.w == T - 1;
-					if (ok) {
-						L.oH[0] = c0.x, L.oQ[0] = c0.y, L.oF[0] = c0.z, L.oS[0] = c1.x, L.oH[1] = c1.y, L.oQ[1] = c1.z;
-						L.oF[1] = c2.x, L.oS[1] = c2.y, L.oH[2] = c2.z, L.oQ[2] = c3.x, L.oF[2] = c3.y, L.oS[2] = c3.z;
-					}
-				} else {
-					if (ok) {
-						L.oH[0] = c0.x, L.oQ[0] = c0.y, L.oXhi[0] = c0.z, L.oH[1] = c1.x, L.oQ[1] = c1.y, L.oXhi[1] = c1.z;
-						L.oH[2] = c2.x, L.oQ[2] = c2.y, L.oXhi[2] = c2.z;
-					}
-				}
-			}
-			if (__all_sync(0xffffffffu, ok)) break;
-			if (lds32(sf)) { stopped = true; break; }
-			if (++spins > PAIR_SPIN_LIMIT) { if (lane == 0) sts32(sf, 2); stopped = true; break; } // never in a correct run: give up instead of hanging the GPU
-		}
-		if (lane == 0) sts32(cons_mine, T);
-	};
-	// hand the last lane's outputs of macro-step T to the right warp
-	auto relay_out = [&](int T) {
-		if (NW == 1 || warp >= NWL - 1) return;
-		while (T - lds32(cons_next) >= PAIR_SLOTS) { // the right warp still needs the slot this one would overwrite
-			if (lds32(sf)) { stopped = true; return; }
-			if (++spins > PAIR_SPIN_LIMIT) { if (lane == 0) sts32(sf, 2); stopped = true; return; }
-		}
-		if (lane == 31) {
-			const uint32_t a = ch_out + (uint32_t)(T & (PAIR_SLOTS - 1)) * 64;
-			if constexpr (TB) {
-				sts128(a, make_int4(L.oH[0], L.oQ[0], L.oF[0], T)), sts128(a + 16, make_int4(L.oS[0], L.oH[1], L.oQ[1], T));
-				sts128(a + 32, make_int4(L.oF[1], L.oS[1], L.oH[2], T)), sts128(a + 48, make_int4(L.oQ[2], L.oF[2], L.oS[2], T));
-			} else {
-				sts128(a, make_int4(L.oH[0], L.oQ[0], L.oXhi[0], T)), sts128(a + 16, make_int4(L.oH[1], L.oQ[1], L.oXhi[1], T));
-				sts128(a + 32, make_int4(L.oH[2], L.oQ[2], L.oXhi[2], T));
-			}
-		}
-	};
-
-	// ---- one macro-step; hb[PH] receives this step's left H, hb[PH ^ 1] holds the previous step's
-	uint32_t hb[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } };
-	PairRec rcs[2]; // row records of the next even / odd macro-step, fetched two steps ahead
-	pair_load_rec(rec, nb, m_max, 0, p < 0 ? 0 : p, rcs[0]);
-	pair_load_rec(rec, nb, m_max, 1, p < 0 ? 0 : p, rcs[1]);
+	uint32_t hb[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } }; // H of the columns to the left: this macro-step's (hb[PH]) and the previous one's
+	PairRec rcs[2];                                   // row records of the next even / odd macro-step, fetched two steps ahead
+	pair_load_rec(rec, nb, m_max, 0, p, rcs[0]);
+	pair_load_rec(rec, nb, m_max, 1, p, rcs[1]);
 #define NSW_PAIR_RECV(PH) \
 		uint32_t rQ[3]; \
 		_Pragma("unroll") for (int r = 0; r < 3; ++r) { \
 			hb[PH][r] = L.left_of(__shfl_up_sync(0xffffffffu, L.oH[r], 1), L.oH[r]); \
 			rQ[r] = L.left_of(__shfl_up_sync(0xffffffffu, L.oQ[r], 1), L.oQ[r]); \
 		}
-	auto tracker_push = [&](int T, bool all_rows) {
-		if constexpr (!TB) {
-			if (!trk_warp) return;
-#pragma unroll
-			for (int r = 0; r < 3; ++r) {
-				const int i_hi = 3 * (T - 2 * p_end) - 1 + r; // row of the last column's value in oXhi[r]
-				if (all_rows || (i_hi >= 2 && i_hi < nl)) trk.push(ring_w, L.oXhi[r]);
-			}
-			if (trk.n_ring >= 30) trk.flush(ring_r, lane, al * 3, cst.pen, cst.xdrop);
-		}
-	};
-	auto step = [&](int T, auto ph_tag, bool steady) {
+	// ---- general macro-step (ramp-up, ramp-down, tiny problems): every row checked, results committed per half
+	auto step = [&](int T, auto ph_tag) {
 		constexpr int PH = decltype(ph_tag)::value;
-		if (T > 0) relay_in(T);
-		if (stopped) return;
-		const PairRec rc = rcs[PH];                               // loaded two macro-steps ago ...
-		pair_load_rec(rec, nb, m_max, T + 2, p < 0 ? 0 : p, rcs[PH]); // ... and the one of step T + 2 leaves now: a whole macro-step to arrive
+		const PairRec rc = rcs[PH];
+		pair_load_rec(rec, nb, m_max, T + 2, p, rcs[PH]);
 		NSW_PAIR_RECV(PH)
 		const uint32_t *pv = hb[PH ^ 1], *cu = hb[PH];
+		const int m = T - 2 * p;
 		if constexpr (TB) {
 			uint32_t rF[3], rS[3], wd[3];
 #pragma unroll
@@ -239,81 +157,63 @@ __global__ void __launch_bounds__(NW * 32) nasw_pair_kernel(const DpDev *jobs, c
 				rF[r] = L.left_of(__shfl_up_sync(0xffffffffu, L.oF[r], 1), L.oF[r]);
 				rS[r] = L.left_of(__shfl_up_sync(0xffffffffu, L.oS[r], 1), L.oS[r]);
 			}
-			auto &LT = L;
-			if (steady) {
-				wd[0] = LT.template row<0>(pp, rc, env, cu[0], pv[2], pv[1], pv[0], rQ[0], rF[0], rS[0]);
-				wd[1] = LT.template row<1>(pp, rc, env, cu[1], cu[0], pv[2], pv[1], rQ[1], rF[1], rS[1]);
-				wd[2] = LT.template row<2>(pp, rc, env, cu[2], cu[1], cu[0], pv[2], rQ[2], rF[2], rS[2]);
-				if (live) {
 #pragma unroll
-					for (int r = 0; r < 3; ++r) *reinterpret_cast<uint32_t*>(tbp + (int64_t)(3 * T + r) * Wp) = wd[r];
-				}
-			} else {
-				const int m = T - 2 * p;
-#pragma unroll
-				for (int r = 0; r < 3; ++r) {
-					const int i_lo = 3 * m + 2 + r, i_hi = i_lo - 3;
-					const bool vlo = live && i_lo >= 2 && i_lo < nl, vhi = live && i_hi >= 2 && i_hi < nl;
-					const uint32_t keep = (vlo ? 0xffffu : 0u) | (vhi ? 0xffff0000u : 0u);
-					const bool bnd = g.first && i_lo == 2;
-					const uint32_t l0 = cu[r], l1 = r == 0 ? pv[2] : cu[r - 1], l2 = r == 0 ? pv[1] : r == 1 ? pv[2] : cu[0], l3 = r == 0 ? pv[0] : r == 1 ? pv[1] : pv[2];
-					if (r == 0) wd[0] = LT.template row_masked<0>(pp, rc, env, l0, l1, l2, l3, rQ[0], rF[0], rS[0], keep, bnd);
-					else if (r == 1) wd[1] = LT.template row_masked<1>(pp, rc, env, l0, l1, l2, l3, rQ[1], rF[1], rS[1], keep, bnd);
-					else wd[2] = LT.template row_masked<2>(pp, rc, env, l0, l1, l2, l3, rQ[2], rF[2], rS[2], keep, bnd);
-					uint16_t *q = tbp + (int64_t)(3 * T + r) * Wp;
-					if (vlo && vhi) *reinterpret_cast<uint32_t*>(q) = wd[r];
-					else if (vlo) q[0] = (uint16_t)(wd[r] & 0xffff);
-					else if (vhi) q[1] = (uint16_t)(wd[r] >> 16);
-					if (vlo && has_end_lo && i_lo == nl - 1) tb_score = lo16(LT.oH[r]) - PAIR_BIAS, have_score = true;
-					if (vhi && has_end_hi && i_hi == nl - 1) tb_score = hi16(LT.oH[r]) - PAIR_BIAS, have_score = true;
-				}
+			for (int r = 0; r < 3; ++r) {
+				const int i_lo = 3 * m + 2 + r, i_hi = i_lo - 3;
+				const bool vlo = live && i_lo >= 2 && i_lo < nl, vhi = live && i_hi >= 2 && i_hi < nl;
+				const uint32_t keep = (vlo ? 0xffffu : 0u) | (vhi ? 0xffff0000u : 0u);
+				const bool bnd = g.first && i_lo == 2;
+				const uint32_t l0 = cu[r], l1 = r == 0 ? pv[2] : cu[r - 1], l2 = r == 0 ? pv[1] : r == 1 ? pv[2] : cu[0], l3 = r == 0 ? pv[0] : r == 1 ? pv[1] : pv[2];
+				if (r == 0) wd[0] = L.template row_masked<0>(pp, rc, env, l0, l1, l2, l3, rQ[0], rF[0], rS[0], keep, bnd);
+				else if (r == 1) wd[1] = L.template row_masked<1>(pp, rc, env, l0, l1, l2, l3, rQ[1], rF[1], rS[1], keep, bnd);
+				else wd[2] = L.template row_masked<2>(pp, rc, env, l0, l1, l2, l3, rQ[2], rF[2], rS[2], keep, bnd);
+				uint16_t *q = tbp + (int64_t)(3 * T + r) * Wp;
+				if (vlo && vhi) *reinterpret_cast<uint32_t*>(q) = wd[r];
+				else if (vlo) q[0] = (uint16_t)(wd[r] & 0xffff);
+				else if (vhi) q[1] = (uint16_t)(wd[r] >> 16);
+				if (vlo && has_end_lo && i_lo == nl - 1) tb_score = lo16(L.oH[r]) - PAIR_BIAS, have_score = true;
+				if (vhi && has_end_hi && i_hi == nl - 1) tb_score = hi16(L.oH[r]) - PAIR_BIAS, have_score = true;
 			}
 		} else {
-			auto &LE = L;
 			int lx[3], xp[3];
 #pragma unroll
-			for (int r = 0; r < 3; ++r) lx[r] = (int)((uint32_t)__shfl_up_sync(0xffffffffu, LE.oXhi[r], 1) & LE.xmask), xp[r] = LE.oXlo[r];
-			if (steady) {
-				LE.template row<0>(pp, rc, env, cu[0], pv[2], pv[1], pv[0], rQ[0], lx[0], xp[0]);
-				LE.template row<1>(pp, rc, env, cu[1], cu[0], pv[2], pv[1], rQ[1], lx[1], xp[1]);
-				LE.template row<2>(pp, rc, env, cu[2], cu[1], cu[0], pv[2], rQ[2], lx[2], xp[2]);
-			} else {
-				const int m = T - 2 * p;
+			for (int r = 0; r < 3; ++r) lx[r] = (int)((uint32_t)__shfl_up_sync(0xffffffffu, L.oXhi[r], 1) & L.xmask), xp[r] = L.oXlo[r];
 #pragma unroll
-				for (int r = 0; r < 3; ++r) {
-					const int i_lo = 3 * m + 2 + r, i_hi = i_lo - 3;
-					const bool vlo = live && i_lo >= 2 && i_lo < nl, vhi = live && i_hi >= 2 && i_hi < nl;
-					const uint32_t keep = (vlo ? 0xffffu : 0u) | (vhi ? 0xffff0000u : 0u);
-					const bool bnd = g.first && i_lo == 2;
-					const uint32_t l0 = cu[r], l1 = r == 0 ? pv[2] : cu[r - 1], l2 = r == 0 ? pv[1] : r == 1 ? pv[2] : cu[0], l3 = r == 0 ? pv[0] : r == 1 ? pv[1] : pv[2];
-					if (r == 0) LE.template row_masked<0>(pp, rc, env, l0, l1, l2, l3, rQ[0], lx[0], xp[0], keep, bnd);
-					else if (r == 1) LE.template row_masked<1>(pp, rc, env, l0, l1, l2, l3, rQ[1], lx[1], xp[1], keep, bnd);
-					else LE.template row_masked<2>(pp, rc, env, l0, l1, l2, l3, rQ[2], lx[2], xp[2], keep, bnd);
-				}
+			for (int r = 0; r < 3; ++r) {
+				const int i_lo = 3 * m + 2 + r, i_hi = i_lo - 3;
+				const bool vlo = live && i_lo >= 2 && i_lo < nl, vhi = live && i_hi >= 2 && i_hi < nl;
+				const uint32_t keep = (vlo ? 0xffffu : 0u) | (vhi ? 0xffff0000u : 0u);
+				const bool bnd = g.first && i_lo == 2;
+				const uint32_t l0 = cu[r], l1 = r == 0 ? pv[2] : cu[r - 1], l2 = r == 0 ? pv[1] : r == 1 ? pv[2] : cu[0], l3 = r == 0 ? pv[0] : r == 1 ? pv[1] : pv[2];
+				if (r == 0) L.template row_masked<0>(pp, rc, env, l0, l1, l2, l3, rQ[0], lx[0], xp[0], keep, bnd);
+				else if (r == 1) L.template row_masked<1>(pp, rc, env, l0, l1, l2, l3, rQ[1], lx[1], xp[1], keep, bnd);
+				else L.template row_masked<2>(pp, rc, env, l0, l1, l2, l3, rQ[2], lx[2], xp[2], keep, bnd);
 			}
-			tracker_push(T, steady);
-			if (trk_warp && trk.stopped) { if (lane == 0) sts32(sf, 1); stopped = true; return; }
+#pragma unroll
+			for (int r = 0; r < 3; ++r) { // the last column's rows of this step, if real, go to the tracker
+				const int i_hi = 3 * (T - 2 * p_end) - 1 + r;
+				if (i_hi >= 2 && i_hi < nl) trk.push(ring_w, L.oXhi[r]);
+			}
+			if (trk.n_ring >= 30) trk.flush(ring_r, lane, al * 3, cst.pen, cst.xdrop);
 		}
-		relay_out(T);
 	};
-	// steady macro-steps of this warp: both halves of every live thread are on real rows strictly above the last row
-	int t_lo = 2 * p_last_w + 2, t_hi = nl >= 6 ? 2 * p_first + (nl - 6) / 3 + 1 : 0;
-	t_lo += t_lo & 1;
-	if (t_lo > n_macro) t_lo = n_macro; // (n_macro is even)
+	// steady macro-steps: both halves of every live thread are on real rows strictly above the last row
+	int t_lo = 2 * p_end + 2, t_hi = nl >= 6 ? (nl - 6) / 3 + 1 : 0;
+	if (t_lo > n_macro) t_lo = n_macro; // (both even)
 	if (t_hi > n_macro) t_hi = n_macro;
 	if (t_hi < t_lo) t_hi = t_lo;
 	t_hi = t_lo + ((t_hi - t_lo) & ~1);
-	int T = warp < NWL ? 0 : n_macro; // a warp without live columns has nothing to do
-	for (; T < t_lo && T < n_macro && !stopped; T += 2) {
-		step(T, std::integral_constant<int, 0>(), false);
-		if (!stopped) step(T + 1, std::integral_constant<int, 1>(), false);
-		if (!TB && NW > 1 && !stopped && lds32(sf)) stopped = true;
+	int T = 0;
+	for (; T < t_lo; T += 2) {
+		step(T, std::integral_constant<int, 0>());
+		step(T + 1, std::integral_constant<int, 1>());
+		if (!TB && trk.stopped) break;
 	}
-	// the steady loop, straight-line: no row checks, the row records of step T + 2 are fetched AFTER the rows of step T used the old
-	// ones (same registers, a whole macro-step to arrive), and the only exits are a stuck / stopped neighbour and the x-drop
-	const int pq = p < 0 ? 0 : p;
+	// The steady loop, straight-line: no row checks; the row records of step T + 2 are fetched AFTER the rows of step T used the
+	// old ones (same registers, a whole macro-step to arrive).  Record m of a thread sits at slot k = m >> 1 of its parity, i.e.
+	// at 16-byte index k + (k >> 5) * 160 of that parity's array (nasw_pair.cuh pair_rec_index); idle threads to the right of the
+	// last column read the records of the last live pair.
 #define NSW_PAIR_STEADY(PH) { \
-		if (NW > 1) { relay_in(T + PH); if (stopped) break; } \
 		NSW_PAIR_RECV(PH) \
 		const uint32_t *pv = hb[PH ^ 1], *cu = hb[PH]; \
 		if constexpr (TB) { \
@@ -336,35 +236,27 @@ __global__ void __launch_bounds__(NW * 32) nasw_pair_kernel(const DpDev *jobs, c
 			L.template row<0>(pp, rcs[PH], env, cu[0], pv[2], pv[1], pv[0], rQ[0], lx[0], xp[0]); \
 			L.template row<1>(pp, rcs[PH], env, cu[1], cu[0], pv[2], pv[1], rQ[1], lx[1], xp[1]); \
 			L.template row<2>(pp, rcs[PH], env, cu[2], cu[1], cu[0], pv[2], rQ[2], lx[2], xp[2]); \
-			if (trk_warp) { \
-				_Pragma("unroll") for (int r = 0; r < 3; ++r) sts32(ring_w + (trk.n_ring + r) * 128, L.oXhi[r]); \
-				trk.n_ring += 3; \
-				if (trk.n_ring >= 30) trk.flush(ring_r, lane, al * 3, cst.pen, cst.xdrop); \
-			} \
+			_Pragma("unroll") for (int r = 0; r < 3; ++r) sts32(ring_w + (trk.n_ring + r) * 128, L.oXhi[r]); \
+			trk.n_ring += 3; \
+			if (trk.n_ring >= 30) trk.flush(ring_r, lane, al * 3, cst.pen, cst.xdrop); \
 		} \
-		{ /* record of step T + PH + 2: slot ks + 1 of the parity array of this step (advanced once per loop iteration) */ \
+		{ \
 			const uint4 *q = rq[PH] + (ks + 1 + ((ks + 1) >> 5) * 160); \
 			_Pragma("unroll") for (int f = 0; f < 6; ++f) { \
 				const uint4 v = __ldg(q + f * 32); \
 				rcs[PH].w[4 * f] = v.x, rcs[PH].w[4 * f + 1] = v.y, rcs[PH].w[4 * f + 2] = v.z, rcs[PH].w[4 * f + 3] = v.w; \
 			} \
-		} \
-		if (NW > 1) { relay_out(T + PH); if (stopped) break; } }
-	{
+		} }
+	if (T < t_hi && !(!TB && trk.stopped)) {
 		uint16_t *tbs = TB ? tbp + (int64_t)3 * T * Wp : 0;
 		(void)tbs;
-		// In the steady range every live thread is on stored records (no clamping); idle threads to the right of the last column
-		// read the records of the last live pair.  Record m of a thread sits at slot k = m >> 1 of its parity: slot k of a parity
-		// array is at 16-byte index (k >> 5) * 192 + (k & 31) = k + (k >> 5) * 160.
-		const int ps = pq > p_last_w ? p_last_w : pq;
+		const int ps = p > p_end ? p_end : p;
 		const uint4 *rq[2] = { rec, rec + (size_t)nb * 192 }; // even / odd triples (T is even at the loop head: step T + PH has parity PH)
 		int ks = (T - 2 * ps) >> 1;                           // slot of step T (and of step T + 1)
-		if (T < t_hi) { // the general loop fetched with clamped indices: re-fetch the two records in flight for THIS thread mapping
-			pair_load_rec(rec, nb, m_max, T, ps, rcs[0]);
-			pair_load_rec(rec, nb, m_max, T + 1, ps, rcs[1]);
-		}
-		for (; T < t_hi && !stopped; T += 2, ++ks) {
-			if ((T & 14) == 0) { // every eighth iteration (warp-uniform): a lane moves on by one 16-byte record per iteration, so its lines 32 records ahead are due
+		pair_load_rec(rec, nb, m_max, T, ps, rcs[0]);         // the two records in flight, for THIS mapping of threads to records
+		pair_load_rec(rec, nb, m_max, T + 1, ps, rcs[1]);
+		for (; T < t_hi; T += 2, ++ks) {
+			if ((T & 14) == 0) { // every eighth iteration: a lane moves on by one 16-byte record per iteration, so its 128-byte lines 32 records ahead are due
 				const uint4 *pf = rq[0] + (ks + 40 + ((ks + 40) >> 5) * 160);
 #pragma unroll
 				for (int f = 0; f < 6; ++f) {
@@ -374,34 +266,25 @@ __global__ void __launch_bounds__(NW * 32) nasw_pair_kernel(const DpDev *jobs, c
 			}
 			NSW_PAIR_STEADY(0)
 			NSW_PAIR_STEADY(1)
-			if (!TB) {
-				if (trk_warp) { if (trk.stopped) { if (NW > 1 && lane == 0) sts32(sf, 1); stopped = true; } }
-				else if (NW > 1 && lds32(sf)) stopped = true;
-			}
+			if (!TB && trk.stopped) break;
+		}
+		if (T < n_macro) { // back to the general loop: its records (clamped indices, own pair) for the next two steps
+			pair_load_rec(rec, nb, m_max, T, p, rcs[0]);
+			pair_load_rec(rec, nb, m_max, T + 1, p, rcs[1]);
 		}
 	}
 #undef NSW_PAIR_STEADY
-#undef NSW_PAIR_RECV
-	if (T < n_macro && !stopped) { // back to the general loop: its records (clamped indices, own pair) for the next two steps
-		pair_load_rec(rec, nb, m_max, T, pq, rcs[0]);
-		pair_load_rec(rec, nb, m_max, T + 1, pq, rcs[1]);
-	}
-	for (; T < n_macro && !stopped; T += 2) {
-		step(T, std::integral_constant<int, 0>(), false);
-		if (!stopped) step(T + 1, std::integral_constant<int, 1>(), false);
-		if (!TB && NW > 1 && !stopped && lds32(sf)) stopped = true;
-	}
-	if (NW > 1) { // a stuck exchange (stop_flag == 2) is reported instead of a result: the host aborts the wave loudly
-		__syncthreads();
-		if (stop_flag == 2) {
-			if (threadIdx.x == 0) out[jid] = make_int4(INT32_MIN, -2, -2, 0);
-			return;
+	if (!(!TB && trk.stopped)) {
+		for (; T < n_macro; T += 2) {
+			step(T, std::integral_constant<int, 0>());
+			step(T + 1, std::integral_constant<int, 1>());
+			if (!TB && trk.stopped) break;
 		}
 	}
+#undef NSW_PAIR_RECV
 	if (TB) {
 		if (have_score) out[jid] = make_int4(tb_score, nl, al, 0);
-		else if (nl <= 2 && threadIdx.x == 0) out[jid] = make_int4(NEG, nl, al, 0);
-	} else if (trk_warp) {
+	} else {
 		if (trk.n_ring > 0 && !trk.stopped) trk.flush(ring_r, lane, al * 3, cst.pen, cst.xdrop);
 		if (lane == 0) {
 			int4 r;
@@ -411,30 +294,12 @@ __global__ void __launch_bounds__(NW * 32) nasw_pair_kernel(const DpDev *jobs, c
 	}
 }
 
-template <int NW, bool TB>
-static void launch_pair(cudaStream_t st, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, uint16_t *tb)
-{
-	const int smem = NW * 2 * 22 * 32 * (int)sizeof(uint32_t);
-	static bool attr_set = false;
-	if (!attr_set) { cudaFuncSetAttribute(nasw_pair_kernel<NW, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-	nasw_pair_kernel<NW, TB><<<n, NW * 32, smem, st>>>(jobs, order, n, (const uint4*)rec, aa, cst, out, tb);
-}
-
-// pair-lane kernels: nw = warps per problem (1, 2, 4 or 8: up to 64 / 126 / 250 / 498 padded columns)
-void nasw_launch_pair(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out,
-                      uint16_t *tb)
+// pair-lane kernels: one warp per problem of up to 64 padded columns
+void nasw_launch_pair(cudaStream_t st, bool is_tb, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, uint16_t *tb)
 {
 	if (n <= 0) return;
-	switch (nw * 2 + (is_tb ? 1 : 0)) {
-	case 2: launch_pair<1, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	case 3: launch_pair<1, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	case 4: launch_pair<2, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	case 5: launch_pair<2, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	case 8: launch_pair<4, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	case 9: launch_pair<4, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	case 16: launch_pair<8, false>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	default: launch_pair<8, true>(st, jobs, order, n, rec, aa, cst, out, tb); break;
-	}
+	if (is_tb) nasw_pair_kernel<true><<<n, 32, 0, st>>>(jobs, order, n, (const uint4*)rec, aa, cst, out, tb);
+	else nasw_pair_kernel<false><<<n, 32, 0, st>>>(jobs, order, n, (const uint4*)rec, aa, cst, out, tb);
 }
 
 } // namespace cuda
