@@ -299,7 +299,10 @@ def main():
         t_up = time.perf_counter() - t0
     l_seq = mi.contents.nt.contents.l_seq
 
-    prot = synth.shard_queries(spec, d, rank)
+    shard = int(os.environ.get("MPB_BENCH_SHARD", rank))  # (diagnostics: map another rank's shard on this GPU)
+    if shard != rank:
+        synth.shard_queries(spec, d, shard)
+    prot = synth.shard_queries(spec, d, shard)
     names, seqs = read_fasta(prot)
     n = len(seqs)
     mo = mp.mapopt()

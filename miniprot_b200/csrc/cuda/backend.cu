@@ -214,7 +214,7 @@ void mpb_ctx_destroy(mpb_ctx_t *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = { &c->own_ki, &c->own_kb, &c->own_seq, &c->own_bo, &c->own_ctg, &c->b_jobs, &c->b_order, &c->b_chunks, &c->b_rw, &c->b_aa, &c->b_out,
-	                   &c->b_carry, &c->b_tb, &c->b_cigar, &c->b_cigpack, &c->b_cigoff, &c->b_packed };
+	                   &c->b_carry, &c->b_tb, &c->b_cigar, &c->b_cigpack, &c->b_cigoff, &c->b_packed, &c->b_units };
 	for (DevBuf *b : bufs) b->release();
 	for (DevBuf &b : c->b_c) b.release();
 	c->h_out.release(), c->h_cigar.release();

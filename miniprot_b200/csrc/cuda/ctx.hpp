@@ -27,7 +27,7 @@ struct mpb_ctx_s {
 	mpb::cuda::DevBuf own_ki, own_kb, own_seq, own_bo, own_ctg;
 
 	// nasw arenas
-	mpb::cuda::DevBuf b_jobs, b_order, b_chunks, b_rw, b_aa, b_out, b_carry, b_tb, b_cigar, b_cigpack, b_cigoff, b_packed;
+	mpb::cuda::DevBuf b_jobs, b_order, b_chunks, b_rw, b_aa, b_out, b_carry, b_tb, b_cigar, b_cigpack, b_cigoff, b_packed, b_units;
 	mpb::cuda::PinBuf h_out, h_cigar;
 	// chaining / seeding / refinement arenas
 	mpb::cuda::DevBuf b_c[16];

@@ -54,7 +54,7 @@ void nasw_launch_ext(cudaStream_t st, int C, const DpDev *jobs, const int *order
 void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, int *carry,
                     uint16_t *tb);
 void nasw_launch_v3(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out,
-                    uint16_t *tb, int warps_per_sm = 0, int *carry = 0, bool multi = false);
+                    uint16_t *tb, int warps_per_sm = 0, int *carry = 0, bool multi = false, const int2 *units = 0, int *progress = 0);
 // packs the CIGARs of a wave (each written at the end of its own worst-case slot) back to back in job order, so that the
 // device-to-host copy moves what was produced instead of the slots; offs[] (n + 1 entries) is scratch
 void nasw_launch_pack(cudaStream_t st, const DpDev *jobs, int n, const int4 *out, const uint32_t *cigar, int64_t *offs, uint32_t *packed);

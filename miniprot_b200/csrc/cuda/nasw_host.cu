@@ -37,10 +37,19 @@ static inline bool use_v3(int al, int nl)
 	(void)al, (void)nl;
 	return g_forced_family != 1; // default: latency first (a wave is bounded by its longest problems); wide problems run in passes
 }
+// Warps per CTA of the block-wide kernels.  A problem wider than one CTA (256 columns) runs as column PASSES, one CTA per pass,
+// all passes of a problem concurrently (pass q a few dozen rows behind pass q - 1, linked by a per-row carry array and a progress
+// counter), so a 350-column extension over a 100 k-row window costs the rows of one pass, not of two (44 -> 23 ms for the widest
+// problem of the bench's shard 7).  MPB_NASW_PASS_WARPS=2 cuts every problem wider than 64 columns into 64-column passes
+// instead: per row a two-warp CTA is the faster one (152 against 240 cycles), but the publishing fence, the carry traffic and
+// above all the start-up lag of each further pass (short global alignments!) cost more than that gains -- C2 step 45 ms against
+// 34 ms (profiles/README.md) -- so CTAs of up to 8 warps stay the default.
+static int g_pass_warps = 8;
 static inline int v3_warps(int al)
 {
 	const int nw = ((al + 7) / 8 * 8 + 31) / 32;
-	return nw <= 1 ? 1 : nw <= 2 ? 2 : nw <= 4 ? 4 : 8;
+	const int r = nw <= 1 ? 1 : nw <= 2 ? 2 : nw <= 4 ? 4 : 8;
+	return r < g_pass_warps ? r : g_pass_warps;
 }
 
 // Pair-lane kernels (nasw_pair.cuh: two columns per thread as packed int16x2) serve every problem whose scores provably stay
@@ -105,7 +114,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	const double t_in = mp_realtime();
 	int64_t rw_tot = 0, tb_tot = 0, cig_tot = 0, carry_tot = 0;
 	std::vector<PrepChunk> chunks, pchunks; // row-record chunks of the 32-bit families, pair-record chunks of the pair-lane family
-	bool wide3[2] = { false, false }; // does the widest block-wide class hold problems of more than one pass?
+	bool wide3[2][4] = { { false, false, false, false }, { false, false, false, false } }; // does a block-wide class hold problems of more than one pass?
 	std::vector<int> unsupported;
 	const PairLimits plim = pair_limits(nso);
 	constexpr int NCLS = 13;
@@ -154,7 +163,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		}
 		if (n_pass > 1) j.carry_off = carry_tot, carry_tot += ((int64_t)j.nl + 2) * 4; // four ints per row
 		for (int r = 0; r < rec_rows; r += PREP_ROWS) chunks.push_back(PrepChunk{ k, r, std::min(PREP_ROWS, rec_rows - r), 0 });
-		if (v3 && n_pass > 1) wide3[is_tb] = true;
+		if (v3 && n_pass > 1) wide3[is_tb][nw == 1 ? 0 : nw == 2 ? 1 : nw == 4 ? 2 : 3] = true;
 		order[is_tb][v3 ? (nw == 1 ? 0 : nw == 2 ? 1 : nw == 4 ? 2 : 3) : n_pass > 1 ? 8 : j.C == 1 ? 4 : j.C == 2 ? 5 : j.C == 4 ? 6 : 7].push_back(k);
 		(is_tb ? ctx->stats.dp_cells_tb : ctx->stats.dp_cells_ext) += (int64_t)j.nl * j.al;
 		(is_tb ? ctx->stats.n_dp_tb : ctx->stats.n_dp_ext) += 1;
@@ -168,6 +177,26 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 			first[b][c] = flat.size(), count[b][c] = v.size();
 			flat.insert(flat.end(), v.begin(), v.end());
 		}
+	// units of the multi-pass launches: (slot in the class's order list, pass), passes of a problem consecutive
+	std::vector<int2> units;
+	int unit_first[2][4] = { { 0 } }, unit_count[2][4] = { { 0 } }, n_units_tot = 0;
+	for (int b = 0; b < 2; ++b)
+		for (int c = 0; c < 4; ++c) {
+			unit_first[b][c] = (int)units.size();
+			if (wide3[b][c])
+				for (size_t s = 0; s < count[b][c]; ++s) {
+					const DpDev &jj = jobs[lo + flat[first[b][c] + s]];
+					const int Wp = 32 << c, np = ((jj.al + 7) / 8 * 8 + Wp - 1) / Wp;
+					for (int q = 0; q < np; ++q) units.push_back(make_int2((int)s, q));
+				}
+			unit_count[b][c] = (int)units.size() - unit_first[b][c];
+		}
+	n_units_tot = (int)units.size();
+	if (n_units_tot) {
+		ctx->b_units.reserve((sizeof(int2) + sizeof(int)) * (size_t)n_units_tot + 64);
+		MPB_CUDA_OK(cudaMemcpyAsync(ctx->b_units.p, units.data(), sizeof(int2) * units.size(), cudaMemcpyHostToDevice, st));
+		MPB_CUDA_OK(cudaMemsetAsync(ctx->b_units.as<int2>() + n_units_tot, 0, sizeof(int) * (size_t)n_units_tot, st));
+	}
 	ctx->b_jobs.reserve(sizeof(DpDev) * n);
 	ctx->b_order.reserve(sizeof(int) * (flat.size() + 1));
 	ctx->b_chunks.reserve(sizeof(PrepChunk) * (chunks.size() + pchunks.size() + 1));
@@ -218,8 +247,15 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 				ctx->stats.kernel_launches += 1;
 			}
 		} else if (c < 4) {
-			nasw_launch_v3(ss, Cs[c], b == 1, dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>(),
-			               wsm_env > 0 ? wsm_env : 0, ctx->b_carry.as<int>(), c == 3 && wide3[b]);
+			const bool multi = wide3[b][c];
+			const int2 *d_units = 0;
+			int *d_prog = 0, n_launch = cnt;
+			if (multi) { // one CTA per (problem, column pass): the passes of a problem run concurrently, linked by progress counters
+				d_units = ctx->b_units.as<int2>() + unit_first[b][c], d_prog = (int*)(ctx->b_units.as<int2>() + n_units_tot) + unit_first[b][c];
+				n_launch = unit_count[b][c];
+			}
+			nasw_launch_v3(ss, Cs[c], b == 1, dj, ord, n_launch, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>(),
+			               wsm_env > 0 ? wsm_env : 0, ctx->b_carry.as<int>(), multi, d_units, d_prog);
 			ctx->stats.kernel_launches += 1;
 			MPB_CUDA_OK(cudaEventRecord(ctx->ev_km[g.sid], ss));
 			if (b == 1) {
@@ -326,6 +362,8 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_
 	if (n == 0) return;
 	{
 		const char *e = getenv("MPB_NASW_KERNEL");
+		const char *pw = getenv("MPB_NASW_PASS_WARPS");
+		g_pass_warps = pw && atoi(pw) == 2 ? 2 : 8;
 		g_forced_family = !e ? 0 : strcmp(e, "cols") == 0 ? 1 : strcmp(e, "v3") == 0 ? 2 : strcmp(e, "pair") == 0 ? 3 : 0;
 	}
 	NaswConst cst;

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(NASW_WARPS * 32) nasw_tb_kernel(const DpDev *j
 // chain: one int4 per row) in the carry array, the first column of the next pass reads it back two macro-steps ahead.
 template <int NW, bool TB, bool MP>
 __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, const int *order, int n_jobs, const int4 *rec, const char *aa, NaswConst cst,
-                                                          int4 *out, uint16_t *tb, int4 *carry_all)
+                                                          int4 *out, uint16_t *tb, int4 *carry_all, const int2 *units, int *progress)
 {
 	extern __shared__ int smem[];
 	constexpr int Wp = 32 * NW;
@@ -293,21 +293,25 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 	__shared__ int ring[TB ? 32 : 32 * 32];           // [slot][lane] row maxima waiting for the warp tracker (WarpTracker)
 	__shared__ int stop_flag[2]; // written by the last column during macro-step Tm into slot Tm & 1, read by everyone after that step's barrier
 	if ((int)blockIdx.x >= n_jobs) return;
-	const int jid = order[blockIdx.x];
+	// MP: one CTA per (problem, column pass), listed in units[] pass after pass: the passes of a problem run CONCURRENTLY, pass q
+	// a few dozen rows behind pass q - 1, whose last column publishes how many of its carry rows are complete (progress[])
+	const int unit_pass = MP ? units[blockIdx.x].y : 0;
+	const int jid = order[MP ? units[blockIdx.x].x : (int)blockIdx.x];
 	const DpDev job = jobs[jid];
 	const int x = threadIdx.x, lane = x & 31, warp = x >> 5;
 	const int W8all = (job.al + 7) / 8 * 8, n_pass = MP ? (W8all + Wp - 1) / Wp : 1;
+	volatile int *prog_out = MP ? progress + blockIdx.x : 0;
+	volatile const int *prog_in = MP && unit_pass > 0 ? progress + blockIdx.x - 1 : 0;
 	int4 *carry = MP ? carry_all + job.carry_off / 4 : 0; // one int4 per row
 	Par par;
 	par.go = cst.go, par.ge = cst.ge, par.io = job.io, par.fs = cst.fs, par.gei_stop = cst.fs;
 	WarpTracker trk; // meaningful in the warp that owns the last column (of the last pass)
 	trk.init(code_bits(job.al));
 	int tb_score = NEG;
-	for (int pass = 0; pass < n_pass; ++pass) {
+	for (int pass = unit_pass; pass <= unit_pass; ++pass) {
 	const bool last_pass = pass == n_pass - 1, carry_in = MP && pass > 0 && x == 0, carry_out = MP && !last_pass && x == Wp - 1;
 	Geo3 g;
 	g.x = x, g.col = pass * Wp + x, g.nl = job.nl, g.al = job.al, g.W8 = W8all, g.live = g.col < g.W8, g.first = g.col == 0;
-	if (MP && pass > 0) __syncthreads(); // everybody is done with the previous pass's profile and carry rows
 	// profile: 22 x Wp, column x of row a at smem[a * Wp + x]
 	{
 		int rcode = -1;
@@ -327,11 +331,23 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 	L.init(g, cst.end_bonus, par.fs, env);
 	// carry rows of the first column, fetched two macro-steps ahead: cb[T & 1][r] = row 3 T + 2 + r
 	int4 cb[2][3];
+	int prog_seen = 0; // what the first column last read from the previous pass's counter
 	auto carry_fetch = [&](int Tm, int4 *dst) {
 		if (carry_in) {
+			const int need = min(3 * Tm + 5, g.nl); // rows below `need` must have left the previous pass
+			if (prog_seen < need) {
+				while ((prog_seen = *prog_in) < need) __nanosleep(200);
+				__threadfence(); // the rows were written before the counter moved
+			}
 #pragma unroll
 			for (int r = 0; r < 3; ++r) { const int i = 3 * Tm + 2 + r; dst[r] = __ldcg(carry + (i < g.nl ? i : g.nl)); }
 		}
+	};
+	// the last column of a pass that has a successor: every 32nd macro-step (and at the end) it publishes the number of finished rows
+	// (the fence is not free, and a lag of a hundred rows is nothing against the tens of thousands of a long problem)
+	auto carry_publish = [&](int rows_done) {
+		__threadfence();
+		*prog_out = rows_done;
 	};
 	if (MP) carry_fetch(0, cb[0]), carry_fetch(1, cb[1]);
 	const int n_macro = g.nl > 2 ? (g.nl - 2 + 2) / 3 + Wp : 0; // rows 2..nl-1 in triples, plus the skew of the last column
@@ -372,6 +388,7 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 		if (MP && carry_out) { \
 			_Pragma("unroll") for (int r = 0; r < 3; ++r) if (done >> r & 1) \
 				carry[Lane3<TB>::row_of(g, T + PH, r)] = make_int4(L.oH[r], L.oI[r], L.oX[r], TB ? L.oS[r] : 0); \
+			if (done) carry_publish(min(Lane3<TB>::row_of(g, T + PH, 0) + 3, g.nl)); \
 		} \
 		if (!TB && warp == NW - 1 && last_pass) { /* the last column sees the complete row maxima; its rows are real when 2 <= i < nl */ \
 			(void)done; \
@@ -388,6 +405,7 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 		if (TB) { if (g.live) { _Pragma("unroll") for (int r = 0; r < 3; ++r) tbs[r * Wp] = (uint16_t)wd[r]; } tbs += 3 * Wp; } \
 		if (MP && carry_out) { \
 			_Pragma("unroll") for (int r = 0; r < 3; ++r) carry[Lane3<TB>::row_of(g, T + PH, r)] = make_int4(L.oH[r], L.oI[r], L.oX[r], TB ? L.oS[r] : 0); \
+			if (((T + PH) & 31) == 31) carry_publish(Lane3<TB>::row_of(g, T + PH, 0) + 3); \
 		} \
 		if (!TB && warp == NW - 1 && last_pass) { \
 			_Pragma("unroll") for (int r = 0; r < 3; ++r) sts32(ring_w + (trk.n_ring + r) * 128, L.oX[r]); \
@@ -421,11 +439,12 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 #undef NSW_V3_MACRO
 	if (!TB && warp == NW - 1 && last_pass && trk.n_ring > 0) trk.flush(ring_r, lane, g.al * 3, cst.pen, cst.xdrop); // the last, partial batch
 	if (TB && g.col == (job.al > 0 ? job.al - 1 : 0)) tb_score = L.score; // the thread that owns column al-1 holds H(nl-1, al-1)
+	if (MP && carry_out) carry_publish(g.nl); // whatever is left
 	} // passes
 	if (TB) {
 		const int c_end = job.al > 0 ? job.al - 1 : 0;
-		if (x == c_end % Wp) out[jid] = make_int4(tb_score, job.nl, job.al, 0);
-	} else if (x == Wp - 1) {
+		if (x == c_end % Wp && c_end / Wp == unit_pass) out[jid] = make_int4(tb_score, job.nl, job.al, 0);
+	} else if (x == Wp - 1 && unit_pass == n_pass - 1) {
 		int4 r;
 		r.x = trk.max_sc, r.y = trk.max_i + 1;
 		r.z = trk.aa_len(job.al);
@@ -540,7 +559,7 @@ void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order,
 // thousands of short ones.  (228 KB per SM, 1 KB reserved per block, static arrays included.)
 template <int NW, bool TB, bool MP>
 static void launch_v3(cudaStream_t st, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, uint16_t *tb,
-                      int warps_per_sm, int *carry)
+                      int warps_per_sm, int *carry, const int2 *units = 0, int *progress = 0)
 {
 	int smem = 22 * 32 * NW * (int)sizeof(int);
 	if (warps_per_sm > 0) {
@@ -554,28 +573,36 @@ static void launch_v3(cudaStream_t st, const DpDev *jobs, const int *order, int 
 		const int share = (int)((int64_t)233472 * NW / warps_per_sm) - 1024 - stat;
 		smem = std::max(smem, std::min(share, 232448 - stat)) & ~15;
 	}
-	nasw_v3_kernel<NW, TB, MP><<<n, NW * 32, smem, st>>>(jobs, order, n, rec, aa, cst, out, tb, (int4*)carry);
+	nasw_v3_kernel<NW, TB, MP><<<n, NW * 32, smem, st>>>(jobs, order, n, rec, aa, cst, out, tb, (int4*)carry, units, progress);
 }
 
 // block-wide wavefront kernels: nw = warps per problem (1, 2, 4 or 8); multi = some problem of the launch is wider than 256
 // columns (nw == 8 only: column passes with a carry)
+// multi: some problem of the launch is wider than one CTA (nw == 2 or 8); then n = number of (problem, pass) units, units[] lists
+// them pass after pass per problem and progress[] (n zeroed ints) links consecutive passes
 void nasw_launch_v3(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out,
-                    uint16_t *tb, int warps_per_sm, int *carry, bool multi)
+                    uint16_t *tb, int warps_per_sm, int *carry, bool multi, const int2 *units, int *progress)
 {
 	if (n <= 0) return;
 	switch (nw * 2 + (is_tb ? 1 : 0)) {
 	case 2: launch_v3<1, false, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
 	case 3: launch_v3<1, true, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
-	case 4: launch_v3<2, false, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
-	case 5: launch_v3<2, true, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
+	case 4:
+		if (multi) launch_v3<2, false, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry, units, progress);
+		else launch_v3<2, false, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
+		break;
+	case 5:
+		if (multi) launch_v3<2, true, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry, units, progress);
+		else launch_v3<2, true, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
+		break;
 	case 8: launch_v3<4, false, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
 	case 9: launch_v3<4, true, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
 	case 16:
-		if (multi) launch_v3<8, false, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
+		if (multi) launch_v3<8, false, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry, units, progress);
 		else launch_v3<8, false, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
 		break;
 	default:
-		if (multi) launch_v3<8, true, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
+		if (multi) launch_v3<8, true, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry, units, progress);
 		else launch_v3<8, true, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
 		break;
 	}
