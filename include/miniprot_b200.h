@@ -263,6 +263,9 @@ typedef struct { int32_t qid; uint32_t vid; int64_t as, ae; } mpb_window_t;
 int mpb_refine_batch(mpb_ctx_t *ctx, const mp_idx_t *mi, const mp_mapopt_t *opt, int32_t n_seq, const char *const *seqs, const int32_t *lens,
                      int32_t n_win, const mpb_window_t *win, int64_t *a_off, uint64_t **a, int32_t *sc);
 
+/* The segmented sort of the seeding / refinement stages alone: keys[off[s] .. off[s+1]) sorted ascending for every s, in place. */
+int mpb_sort_segments(mpb_ctx_t *ctx, int32_t n_seg, const int64_t *off, uint64_t *keys);
+
 void mpb_free(void *p);                                   /* free() for buffers this library malloc'ed */
 void mpb_regs_free(int32_t n, const int32_t *n_reg, mp_reg1_t **reg); /* free what mpb_map_batch returned */
 int32_t mpb_map_file_path(mpb_ctx_t *ctx, const mp_idx_t *mi, const char *fn, const mp_mapopt_t *opt, const char *out_path);

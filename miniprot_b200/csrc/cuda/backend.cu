@@ -6,6 +6,7 @@
 #include <sched.h>
 #include "ctx.hpp"
 #include "stages_dev.hpp"
+#include "seed_dev.hpp"
 #include "../align.hpp"
 
 using namespace mpb;
@@ -506,6 +507,22 @@ int mpb_refine_batch(mpb_ctx_t *c, const mp_idx_t *mi, const mp_mapopt_t *opt, i
 	for (int32_t k = 0; k < n_win; ++k) a_off[k + 1] = rs.off[(size_t)k + 1], sc[k] = rs.sc[(size_t)k];
 	*a = (uint64_t*)malloc(sizeof(uint64_t) * (rs.a.size() + 1));
 	if (!rs.a.empty()) memcpy(*a, rs.a.data(), sizeof(uint64_t) * rs.a.size());
+	return 0;
+}
+
+// stage-level entry for tests: the segmented sort alone (seg_sort.cu), on host keys, in place
+int mpb_sort_segments(mpb_ctx_t *c, int32_t n_seg, const int64_t *off, uint64_t *keys)
+{
+	if (!c || n_seg < 0) return -1;
+	MPB_CUDA_OK(cudaSetDevice(c->device));
+	const size_t N = n_seg ? (size_t)off[n_seg] : 0;
+	if (N == 0) return 0;
+	c->b_c[1].reserve(sizeof(uint64_t) * (N + 2)), c->b_c[2].reserve(sizeof(uint64_t) * (N + 2));
+	MPB_CUDA_OK(cudaMemcpyAsync(c->b_c[1].p, keys, sizeof(uint64_t) * N, cudaMemcpyHostToDevice, c->stream));
+	seg_sort_u64(c, c->stream, c->b_c[1].as<uint64_t>(), c->b_c[2].as<uint64_t>(), n_seg, off, off + 1);
+	MPB_CUDA_OK(cudaMemcpyAsync(keys, c->b_c[1].p, sizeof(uint64_t) * N, cudaMemcpyDeviceToHost, c->stream));
+	MPB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	MPB_CUDA_OK(cudaGetLastError());
 	return 0;
 }
 

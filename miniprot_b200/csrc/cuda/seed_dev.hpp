@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+struct mpb_ctx_s;
+
 namespace mpb {
 namespace cuda {
 
@@ -38,8 +40,8 @@ void win_launch_emit(cudaStream_t st, const WinJob *jobs, int n_jobs, const uint
                      const int32_t *aa_off, const int32_t *n_pk, const int32_t *grp, const int64_t *a_off, uint64_t *a);
 
 // segmented ascending sort of 64-bit keys (device-wide primitive; see seg_sort.cu)
-void seg_sort_u64(cudaStream_t st, uint64_t *keys, uint64_t *tmp, int64_t n_items, int n_seg, const int64_t *seg_begin, const int64_t *seg_end,
-                  void **scratch, size_t *scratch_cap);
+// segmented ascending sort of 64-bit keys, in place (seg_sort.cu); the segment bounds are host arrays
+void seg_sort_u64(mpb_ctx_s *ctx, cudaStream_t st, uint64_t *keys, uint64_t *tmp, int n_seg, const int64_t *h_begin, const int64_t *h_end);
 
 } // namespace cuda
 } // namespace mpb

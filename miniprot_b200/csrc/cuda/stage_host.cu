@@ -209,7 +209,7 @@ static void seed_run(mpb_ctx_s *ctx, const mp_idx_t *mi, int32_t max_occ, const 
 	ctx->b_c[2].reserve(sizeof(uint64_t) * (N + 2));
 	uint64_t *d_a = ctx->b_c[1].as<uint64_t>(), *d_tmp = ctx->b_c[2].as<uint64_t>();
 	seed_launch_expand(st, d_aa_off, n_q, ctx->d_ki, ctx->d_kb, sd_hash, sd_pos, sd_cnt, sd_aoff, d_nsd, d_a_off, d_a);
-	seg_sort_u64(st, d_a, d_tmp, (int64_t)N, n_q, d_a_off, d_a_off + 1, &ctx->b_c[3].p, &ctx->b_c[3].cap);
+	seg_sort_u64(ctx, st, d_a, d_tmp, n_q, a_off.data(), a_off.data() + 1);
 	ctx->stats.ms_seed += ctx->time_end();
 	ctx->stats.kernel_launches += 3;
 	ctx->stats.n_anchors += (int64_t)N;
@@ -286,7 +286,7 @@ void refine_run(mpb_ctx_s *ctx, const mp_idx_t *mi, const mp_mapopt_t *opt, cons
 	for (int q = 0; q < n_q; ++q) seg_b[(size_t)q] = aa_off[(size_t)q], seg_e[(size_t)q] = aa_off[(size_t)q] + n_pk[(size_t)q];
 	MPB_CUDA_OK(cudaMemcpyAsync(d_seg_b, seg_b.data(), sizeof(int64_t) * (size_t)n_q, cudaMemcpyHostToDevice, st));
 	MPB_CUDA_OK(cudaMemcpyAsync(d_seg_e, seg_e.data(), sizeof(int64_t) * (size_t)n_q, cudaMemcpyHostToDevice, st));
-	seg_sort_u64(st, d_pk, d_pk_tmp, (int64_t)R, n_q, d_seg_b, d_seg_e, &ctx->b_c[3].p, &ctx->b_c[3].cap);
+	seg_sort_u64(ctx, st, d_pk, d_pk_tmp, n_q, seg_b.data(), seg_e.data());
 	int64_t go = 0;
 	for (int j = 0; j < n_j; ++j) {
 		const RefineJob &r = jobs[(size_t)j];
@@ -309,7 +309,7 @@ void refine_run(mpb_ctx_s *ctx, const mp_idx_t *mi, const mp_mapopt_t *opt, cons
 	ctx->b_c[6].reserve(sizeof(uint64_t) * (N + 2));
 	uint64_t *d_a = ctx->b_c[5].as<uint64_t>(), *d_tmp = ctx->b_c[6].as<uint64_t>();
 	win_launch_emit(st, d_wj, n_j, ctx->d_seq, cst, k2, mi->opt.min_aa_len, d_pk, d_aa_off, d_npk, d_grp, d_a_off, d_a);
-	seg_sort_u64(st, d_a, d_tmp, (int64_t)N, n_j, d_a_off, d_a_off + 1, &ctx->b_c[3].p, &ctx->b_c[3].cap);
+	seg_sort_u64(ctx, st, d_a, d_tmp, n_j, a_off.data(), a_off.data() + 1);
 	ctx->stats.ms_refine += ctx->time_end();
 	ctx->stats.kernel_launches += 5;
 	ctx->stats.n_refine_regions += n_j;

@@ -265,3 +265,22 @@ def test_nasw_global_score_end_column_first_of_pass(ctx):
     for (nt, aa, flag, io), g in zip(probs, got):
         w = ol.ora_nasw(tab, nt, aa, flag, mat, _par(opt))
         assert w[0] == g[0] and list(w[3]) == list(g[3]), (len(nt), len(aa), w[0], g[0])
+
+
+def test_segmented_sort(ctx):
+    """seg_sort.cu through mpb_sort_segments: empty / tiny segments, the small-tile class, one large tile, and several tiles with
+    one to six merge passes, against numpy's sort."""
+    rng = np.random.default_rng(8)
+    sizes = [0, 1, 2, 3, 31, 33, 1000, 1024, 1025, 5000, 8191, 8192, 8193, 16384, 20000, 47000, 100000, 300001, 7, 0, 9000]
+    off = np.zeros(len(sizes) + 1, np.int64)
+    off[1:] = np.cumsum(sizes)
+    keys = rng.integers(0, 1 << 62, size=int(off[-1]), dtype=np.int64).astype(np.uint64)
+    keys[off[9]:off[9] + 100] = keys[off[9]]  # duplicates are legal input
+    want = keys.copy()
+    for s in range(len(sizes)):
+        want[off[s]:off[s + 1]].sort()
+    L = mp.lib()
+    L.mpb_sort_segments.restype = C.c_int
+    L.mpb_sort_segments.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    assert L.mpb_sort_segments(ctx.h, len(sizes), off.ctypes.data, keys.ctypes.data) == 0
+    assert (keys == want).all()
