@@ -75,7 +75,7 @@ Fill RegionPlan::make_fill(const mp_idx_t *mi, const mp_mapopt_t *opt, const cha
 		f.score = sc, f.ungapped = true;
 	} else {
 		DpJob j;
-		j.qid = qid, j.vid = r->vid, j.nt_st = vs0 + ne0, j.nl = nlen, j.aa_st = ae0, j.al = alen, j.flag = NS_F_CIGAR, j.io = opt->io;
+		j.qid = qid, j.vid = r->vid, j.win_st = as, j.nt_st = vs0 + ne0, j.nl = nlen, j.aa_st = ae0, j.al = alen, j.flag = NS_F_CIGAR, j.io = opt->io;
 		f.job = (int32_t)jobs.size();
 		jobs.push_back(j);
 	}
@@ -106,7 +106,7 @@ bool RegionPlan::plan(const mp_idx_t *mi, const mp_mapopt_t *opt, int32_t qid_, 
 	as1 = (int32_t)(r->a[i0] & 0x7fffffffU) + 1;
 	{
 		DpJob j;
-		j.qid = qid, j.vid = r->vid, j.nt_st = as, j.nl = (int32_t)(vs1 - as), j.aa_st = 0, j.al = as1, j.flag = NS_F_EXT_LEFT, j.io = opt->io;
+		j.qid = qid, j.vid = r->vid, j.win_st = as, j.nt_st = as, j.nl = (int32_t)(vs1 - as), j.aa_st = 0, j.al = as1, j.flag = NS_F_EXT_LEFT, j.io = opt->io;
 		jobL = (int32_t)jobs.size();
 		jobs.push_back(j);
 	}
@@ -123,7 +123,7 @@ bool RegionPlan::plan(const mp_idx_t *mi, const mp_mapopt_t *opt, int32_t qid_, 
 	has_right = qe_pin < qlen && ve_pin < ae && ae - ve_pin >= 3;
 	if (has_right) {
 		DpJob j;
-		j.qid = qid, j.vid = r->vid, j.nt_st = ve_pin, j.nl = (int32_t)(ae - ve_pin), j.aa_st = qe_pin, j.al = qlen - qe_pin, j.flag = NS_F_EXT_RIGHT, j.io = opt->io;
+		j.qid = qid, j.vid = r->vid, j.win_st = as, j.nt_st = ve_pin, j.nl = (int32_t)(ae - ve_pin), j.aa_st = qe_pin, j.al = qlen - qe_pin, j.flag = NS_F_EXT_RIGHT, j.io = opt->io;
 		jobR = (int32_t)jobs.size();
 		jobs.push_back(j);
 	}
@@ -142,7 +142,7 @@ void RegionPlan::after_wave1(const mp_mapopt_t *opt, const DpSet &w1, std::vecto
 	if (l_aa != as1 && l_nt < opt->max_ext && opt->io > opt->io_end) { // align.c:290-296: 5'-end exon
 		const int64_t as_alt = vs1 - as > opt->max_ext ? vs1 - opt->max_ext : as;
 		DpJob j;
-		j.qid = qid, j.vid = r->vid, j.nt_st = as_alt, j.nl = (int32_t)(vs1 - as_alt), j.aa_st = 0, j.al = as1, j.flag = NS_F_EXT_LEFT, j.io = opt->io_end;
+		j.qid = qid, j.vid = r->vid, j.win_st = as, j.nt_st = as_alt, j.nl = (int32_t)(vs1 - as_alt), j.aa_st = 0, j.al = as1, j.flag = NS_F_EXT_LEFT, j.io = opt->io_end;
 		jobL2 = (int32_t)retry.size();
 		retry.push_back(j);
 	}
@@ -151,7 +151,7 @@ void RegionPlan::after_wave1(const mp_mapopt_t *opt, const DpSet &w1, std::vecto
 		if (r_aa < qlen - qe_pin && r_nt < opt->max_ext && opt->io > opt->io_end) { // align.c:324-330: 3'-end exon
 			const int32_t l_ext = ae - ve_pin < opt->max_ext ? (int32_t)(ae - ve_pin) : opt->max_ext;
 			DpJob j;
-			j.qid = qid, j.vid = r->vid, j.nt_st = ve_pin, j.nl = l_ext, j.aa_st = qe_pin, j.al = qlen - qe_pin, j.flag = NS_F_EXT_RIGHT, j.io = opt->io_end;
+			j.qid = qid, j.vid = r->vid, j.win_st = as, j.nt_st = ve_pin, j.nl = l_ext, j.aa_st = qe_pin, j.al = qlen - qe_pin, j.flag = NS_F_EXT_RIGHT, j.io = opt->io_end;
 			jobR2 = (int32_t)retry.size();
 			retry.push_back(j);
 		}

@@ -30,7 +30,55 @@ DpDev make_dev_job(const mp_idx_t *mi, const DpJob &j, int32_t aa_base)
 	}
 	d.comp = rev ? 1 : 0;
 	d.nl = j.nl, d.al = j.al, d.aa_off = aa_base + j.aa_st, d.flag = j.flag, d.io = j.io;
+	d.ss_off = -1, d.ss_excl = -1;
+	if (mi->nt->spsc) { // --spsc: the dense table is indexed like the genome, the - strand in its second half
+		d.ss_off = rev ? mi->nt->l_seq : 0;
+		if (j.win_st >= 0) d.ss_excl = d.ss_off + (rev ? c->off + c->len - 1 - j.win_st : c->off + j.win_st);
+	}
 	return d;
+}
+
+// one thread per (position, byte) entry of the sparse --spsc arrays
+__global__ void spsc_scatter_kernel(const uint64_t *e, int64_t n, uint8_t *ss)
+{
+	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) ss[e[k] >> 8] = (uint8_t)(e[k] & 0xff);
+}
+
+// mi->nt->spsc (sorted (pos, byte) arrays per contig and strand, ntseq.c:234-296) -> dense byte table in HBM.  Where several
+// entries share a position the reference keeps the largest byte while it fills a window (ntseq.c:146-152); the arrays are
+// sorted on the whole word, so that is the last entry of the position.
+void build_spsc_table(mpb_ctx_s *c, const mp_idx_t *mi)
+{
+	const mp_ntdb_t *nt = mi->nt;
+	const size_t bytes = (size_t)nt->l_seq * 2;
+	c->own_ss.reserve(bytes + 16);
+	MPB_CUDA_OK(cudaMemsetAsync(c->own_ss.p, 0xff, bytes + 16, c->stream));
+	std::vector<uint64_t> e;
+	const size_t piece = (size_t)4 << 20;
+	auto flush = [&]() {
+		if (e.empty()) return;
+		c->b_c[14].reserve(sizeof(uint64_t) * piece);
+		MPB_CUDA_OK(cudaMemcpyAsync(c->b_c[14].p, e.data(), sizeof(uint64_t) * e.size(), cudaMemcpyHostToDevice, c->stream));
+		spsc_scatter_kernel<<<(unsigned)((e.size() + 255) / 256), 256, 0, c->stream>>>(c->b_c[14].as<uint64_t>(), (int64_t)e.size(), c->own_ss.as<uint8_t>());
+		MPB_CUDA_OK(cudaStreamSynchronize(c->stream)); // e is reused
+		c->stats.h2d_bytes += (int64_t)(sizeof(uint64_t) * e.size()), c->stats.kernel_launches += 1;
+		e.clear();
+	};
+	for (int32_t j = 0; j < nt->n_ctg * 2; ++j) {
+		const mp_spsc_t *s = &nt->spsc[j];
+		const mp_ctg_t *ct = &nt->ctg[j >> 1];
+		for (uint32_t k = 0; k < s->n; ++k) {
+			if (k + 1 < s->n && s->a[k + 1] >> 8 == s->a[k] >> 8) continue;
+			const int64_t pos = (int64_t)(s->a[k] >> 8);
+			const int64_t idx = (j & 1) ? nt->l_seq + ct->off + ct->len - 1 - pos : ct->off + pos;
+			e.push_back((uint64_t)idx << 8 | (s->a[k] & 0xff));
+			if (e.size() == piece) flush();
+		}
+	}
+	flush();
+	MPB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	c->d_ss = c->own_ss.as<uint8_t>(), c->ss_src = nt->spsc, c->ss_l_seq = nt->l_seq;
 }
 
 struct CudaStages : Stages {
@@ -94,7 +142,8 @@ struct CudaStages : Stages {
 		const char *d_aa = upload_residues(b, off);
 		std::vector<DpDev> dj(jobs.size());
 		for (size_t k = 0; k < jobs.size(); ++k) dj[k] = make_dev_job(mi, jobs[k], off[(size_t)jobs[k].qid]);
-		nasw_run(ctx, ctx->d_seq, d_aa, base, dj, out);
+		if (mi->nt->spsc && ctx->ss_src != mi->nt->spsc) build_spsc_table(ctx, mi);
+		nasw_run(ctx, ctx->d_seq, mi->nt->spsc ? ctx->d_ss : 0, d_aa, base, dj, out);
 	}
 };
 
@@ -412,10 +461,13 @@ int mpb_nasw_batch(mpb_ctx_t *c, const ns_opt_t *opt, int32_t n, const mpb_dp_pr
 	MPB_CUDA_OK(cudaSetDevice(c->device));
 	// pack the host sequences the way the genome is stored, so that the same kernels serve both paths
 	int64_t nt_tot = 0, aa_tot = 0;
+	bool any_ss = false;
 	for (int32_t i = 0; i < n; ++i) {
-		if (prob[i].ss) { fprintf(stderr, "[miniprot_b200] splice-score bytes (ss) are not supported on the device yet\n"); return -2; }
+		if (prob[i].ss) any_ss = true;
 		nt_tot += prob[i].nl + 2, aa_tot += prob[i].al;
 	}
+	std::vector<uint8_t> ssb;
+	if (any_ss) ssb.assign((size_t)nt_tot + 16, 0xff);
 	std::vector<uint8_t> packed((size_t)(nt_tot / 2 + 2), 0);
 	std::vector<char> aa((size_t)aa_tot + 1);
 	std::vector<DpDev> jobs((size_t)n);
@@ -429,16 +481,22 @@ int mpb_nasw_batch(mpb_ctx_t *c, const ns_opt_t *opt, int32_t n, const mpb_dp_pr
 		const bool left = p.flag & NS_F_EXT_LEFT;
 		d.g_start = left ? g + p.nl - 1 : g, d.dir = left ? -1 : 1, d.comp = 0;
 		d.nl = p.nl, d.al = p.al, d.aa_off = (int32_t)a, d.flag = p.flag, d.io = p.io;
+		d.ss_off = -1, d.ss_excl = -1;
+		if (p.ss) memcpy(ssb.data() + g, p.ss, (size_t)p.nl), d.ss_off = 0; // splice bytes travel laid out like the packed bases
 		g += p.nl + 2, a += p.al;
 	}
 	c->b_packed.reserve(packed.size() + 16);
 	c->b_aa.reserve(aa.size() + 16);
 	MPB_CUDA_OK(cudaMemcpyAsync(c->b_packed.p, packed.data(), packed.size(), cudaMemcpyHostToDevice, c->stream));
 	MPB_CUDA_OK(cudaMemcpyAsync(c->b_aa.p, aa.data(), aa.size(), cudaMemcpyHostToDevice, c->stream));
+	if (any_ss) {
+		c->b_c[15].reserve(ssb.size());
+		MPB_CUDA_OK(cudaMemcpyAsync(c->b_c[15].p, ssb.data(), ssb.size(), cudaMemcpyHostToDevice, c->stream));
+	}
 	MPB_CUDA_OK(cudaStreamSynchronize(c->stream));
-	c->stats.h2d_bytes += (int64_t)(packed.size() + aa.size());
+	c->stats.h2d_bytes += (int64_t)(packed.size() + aa.size() + ssb.size());
 	DpSet out;
-	nasw_run(c, c->b_packed.as<uint8_t>(), c->b_aa.as<char>(), opt, jobs, out);
+	nasw_run(c, c->b_packed.as<uint8_t>(), any_ss ? c->b_c[15].as<uint8_t>() : 0, c->b_aa.as<char>(), opt, jobs, out);
 	for (int32_t i = 0; i < n; ++i) {
 		rst[i].score = out.score[(size_t)i], rst[i].nt_len = out.nt_len[(size_t)i], rst[i].aa_len = out.aa_len[(size_t)i];
 		const int64_t nc = out.cig_off[(size_t)i + 1] - out.cig_off[(size_t)i];

@@ -25,6 +25,12 @@ struct mpb_ctx_s {
 	int64_t *d_ctg = 0;       // per contig {off, len}
 	bool own_index = false;
 	mpb::cuda::DevBuf own_ki, own_kb, own_seq, own_bo, own_ctg;
+	// --spsc splice scores as a dense table: one byte per base and strand, [strand * l_seq + offset of the base in the packed genome]
+	// (0xff = no score), built from mi->nt->spsc when a DP wave first needs it
+	uint8_t *d_ss = 0;
+	const void *ss_src = 0;   // the mi->nt->spsc the table was built from
+	int64_t ss_l_seq = 0;
+	mpb::cuda::DevBuf own_ss;
 
 	// nasw arenas
 	mpb::cuda::DevBuf b_jobs, b_order, b_chunks, b_rw, b_aa, b_out, b_carry, b_tb, b_cigar, b_cigpack, b_cigoff, b_packed, b_units;
@@ -45,7 +51,7 @@ namespace cuda {
 
 // One nasw wave over device-resident sequences.  `packed` is the nibble array the jobs' g_start refer to,
 // `d_aa` the residue buffer their aa_off refer to.  jobs[].{g_start,dir,comp,nl,al,aa_off,flag,io} must be set.
-void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_opt_t *base, std::vector<DpDev> &jobs, DpSet &out);
+void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_ss, const char *d_aa, const ns_opt_t *base, std::vector<DpDev> &jobs, DpSet &out);
 
 int nasw_check_ie_coef(float ie_coef); // 0 if the extension length penalty fits the kernels' step table
 

@@ -542,8 +542,21 @@ struct Lane3 {
 // FORWARD orientation is used for global alignment and right extension; the LEFT variant sees the slice
 // already reversed (c(k) = original[nl-1-k], not complemented) and applies the mirrored rules.
 // ------------------------------------------------------------------------------------------------
-template <class Code>
-NSW_HD uint32_t prep_row_forward(const Code &c, int nl, int i, const int *sp /*[6]*/, const uint8_t *codon_tab, int aa_x)
+// --spsc (nasw-sse.c:138-152,189-203): s = splice byte of one nucleotide (ntseq.c:130-156; 0xff = no score, else
+// (score + 64) << 1 | is_acceptor), applied to the int8 donor / acceptor entries of one row with the reference's int8 wrap.
+// acc_if_odd: in the forward orientation an odd byte adjusts the acceptor, in the reversed slice of a left extension the donor.
+struct SpscPar { int max_spsc, null_bonus; }; // (io + 1) / 2 - 1 of the problem, ns_opt_t::sp_null_bonus
+NSW_HD void spsc_adjust(int s, const SpscPar &q, bool acc_if_odd, int &don, int &acc)
+{
+	if (s == 0xff) { don = (int)(int8_t)(don - q.null_bonus), acc = (int)(int8_t)(acc - q.null_bonus); return; }
+	int v = (s >> 1) - 64;
+	if (v > q.max_spsc) v = q.max_spsc;
+	if (((s & 1) != 0) == acc_if_odd) acc = (int)(int8_t)(acc - v); else don = (int)(int8_t)(don - v);
+}
+struct NoSpsc { NSW_HD int operator()(int) const { return -1; } }; // byte of DP row k's nucleotide, -1 = the problem has no splice bytes
+
+template <class Code, class Spsc>
+NSW_HD uint32_t prep_row_forward(const Code &c, int nl, int i, const int *sp /*[6]*/, const uint8_t *codon_tab, int aa_x, const Spsc &ss, const SpscPar &sq)
 {
 	int don = sp[3], acc = sp[3], nas = aa_x;
 	if (i < nl) {
@@ -570,11 +583,20 @@ NSW_HD uint32_t prep_row_forward(const Code &c, int nl, int i, const int *sp /*[
 			if (a < 4 && b < 4 && d < 4) nas = codon_tab[a << 4 | b << 2 | d];
 		}
 	} else don = (int)(int8_t)sp[3], acc = (int)(int8_t)sp[3];
+	if (i + 1 < nl) { // nasw-sse.c:140-151: ss[i+1] belongs to donor[i] / acceptor[i]
+		const int s = ss(i + 1);
+		if (s >= 0) spsc_adjust(s, sq, true, don, acc);
+	}
 	return row_pack(nas, don, acc);
 }
-
 template <class Code>
-NSW_HD uint32_t prep_row_left(const Code &c, int nl, int i, const int *sp, const uint8_t *codon_tab, int aa_x)
+NSW_HD uint32_t prep_row_forward(const Code &c, int nl, int i, const int *sp, const uint8_t *codon_tab, int aa_x)
+{
+	return prep_row_forward(c, nl, i, sp, codon_tab, aa_x, NoSpsc(), SpscPar{ 0, 0 });
+}
+
+template <class Code, class Spsc>
+NSW_HD uint32_t prep_row_left(const Code &c, int nl, int i, const int *sp, const uint8_t *codon_tab, int aa_x, const Spsc &ss, const SpscPar &sq)
 {
 	int don = (int)(int8_t)sp[3], acc = (int)(int8_t)sp[3], nas = aa_x;
 	if (i < nl) {
@@ -601,8 +623,15 @@ NSW_HD uint32_t prep_row_left(const Code &c, int nl, int i, const int *sp, const
 			const int a = c(i), b = c(i - 1), d = c(i - 2);
 			if (a < 4 && b < 4 && d < 4) nas = codon_tab[a << 4 | b << 2 | d];
 		}
+		const int s = ss(i); // nasw-sse.c:191-202: ss[x] of the original slice belongs to row nl - 1 - x, i.e. to the row of that nucleotide
+		if (s >= 0) spsc_adjust(s, sq, false, don, acc);
 	}
 	return row_pack(nas, don, acc);
+}
+template <class Code>
+NSW_HD uint32_t prep_row_left(const Code &c, int nl, int i, const int *sp, const uint8_t *codon_tab, int aa_x)
+{
+	return prep_row_left(c, nl, i, sp, codon_tab, aa_x, NoSpsc(), SpscPar{ 0, 0 });
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -30,6 +30,8 @@ struct DpDev {                  // one DP problem, resident in HBM for the durat
 	int32_t cig_cap;
 	int32_t pad_;               // block-wide wavefront: traceback row width (32 * warps per problem)
 	int64_t carry_off;          // per-row carry between column passes (int units)
+	int64_t ss_off;             // --spsc: byte of DP row k = ss[ss_off + g_start + dir * k]; < 0 = the problem has no splice bytes
+	int64_t ss_excl;            // ... except at this index, which reads 0xff (the first position of the region's window, ntseq.c:130-156); -1 = none
 };
 
 struct PrepChunk { int32_t job, row0, n_rows, pad_; };
@@ -42,14 +44,15 @@ struct NaswConst {              // problem-independent parameters, passed by val
 	int32_t go, ge, fs, xdrop, end_bonus;
 	float ie_coef;
 	int32_t aa_x;               // code of 'X'
+	int32_t sp_null_bonus;      // --spsc0 (nasw-sse.c:143-145)
 	nsw::PenTable pen;          // extension length penalty as a step table (nasw-sse.c:426, FP32 done on the host)
 };
 
 // pair-lane family (nasw_pair_kernels.cu): chunks carry {job, first triple, number of triples}
-void nasw_launch_prep_pair(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, int4 *rec);
+void nasw_launch_prep_pair(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const uint8_t *ss, const NaswConst &cst, int4 *rec);
 void nasw_launch_pair(cudaStream_t st, bool is_tb, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out,
                       uint16_t *tb);
-void nasw_launch_prep(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, int4 *rec);
+void nasw_launch_prep(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const uint8_t *ss, const NaswConst &cst, int4 *rec);
 void nasw_launch_ext(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, int *carry);
 void nasw_launch_tb(cudaStream_t st, int C, const DpDev *jobs, const int *order, int n, const int4 *rec, const char *aa, const NaswConst &cst, int4 *out, int *carry,
                     uint16_t *tb);

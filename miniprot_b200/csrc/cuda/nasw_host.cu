@@ -77,6 +77,7 @@ static inline bool use_pair(const DpDev &j, const ns_opt_t *o, const PairLimits 
 	if (g_forced_family == 1 || g_forced_family == 2) return false;
 	const int W8 = (j.al + 7) / 8 * 8;
 	if (W8 > nsw::PAIR_MAX_W8 || j.nl < 3) return false;
+	if (j.ss_off >= 0) return false; // --spsc makes donor / acceptor entries negative: outside the value-domain argument of the pair-lane kernels
 	if (g_forced_family != 3) {
 		const bool is_tb = !(j.flag & (NS_F_EXT_LEFT | NS_F_EXT_RIGHT));
 		if (!is_tb) return false;
@@ -92,6 +93,7 @@ static void fill_const(const ns_opt_t *o, NaswConst &c)
 	for (int i = 0; i < 6; ++i) c.sp[i] = o->sp[i];
 	c.go = o->go, c.ge = o->ge, c.fs = o->fs, c.xdrop = o->xdrop, c.end_bonus = o->end_bonus, c.ie_coef = o->ie_coef;
 	c.aa_x = ns_tab_aa20[(uint8_t)'X'];
+	c.sp_null_bonus = o->sp_null_bonus;
 	nsw::pen_table_build(o->ie_coef, c.pen);
 }
 
@@ -106,7 +108,7 @@ int nasw_check_ie_coef(float ie_coef)
 }
 
 // run jobs[lo, hi) as one sub-wave
-static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const NaswConst &cst, const ns_opt_t *nso, std::vector<DpDev> &jobs, size_t lo, size_t hi, DpSet &out)
+static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_ss, const char *d_aa, const NaswConst &cst, const ns_opt_t *nso, std::vector<DpDev> &jobs, size_t lo, size_t hi, DpSet &out)
 {
 	const int n = (int)(hi - lo);
 	if (n == 0) return;
@@ -216,8 +218,8 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 	const DpDev *dj = ctx->b_jobs.as<DpDev>();
 	const int *dord = ctx->b_order.as<int>();
 	MPB_CUDA_OK(cudaEventRecord(ctx->ev_p0, st));
-	nasw_launch_prep(st, dj, ctx->b_chunks.as<PrepChunk>(), (int)chunks.size(), packed, cst, ctx->b_rw.as<int4>());
-	nasw_launch_prep_pair(st, dj, ctx->b_chunks.as<PrepChunk>() + chunks.size(), (int)pchunks.size(), packed, cst, ctx->b_rw.as<int4>());
+	nasw_launch_prep(st, dj, ctx->b_chunks.as<PrepChunk>(), (int)chunks.size(), packed, d_ss, cst, ctx->b_rw.as<int4>());
+	nasw_launch_prep_pair(st, dj, ctx->b_chunks.as<PrepChunk>() + chunks.size(), (int)pchunks.size(), packed, d_ss, cst, ctx->b_rw.as<int4>());
 	ctx->stats.kernel_launches += (chunks.empty() ? 0 : 1) + (pchunks.empty() ? 0 : 1);
 	static const int Cs[NCLS] = { 1, 2, 4, 8, 1, 2, 4, 8, 16, 1, 2, 4, 8 }; // warps per problem (classes 0..3, 9..12) or columns per lane (4..8)
 	// Scheduling of a big wave.  It is bounded by its longest extensions (100 k rows next to thousands of short problems):
@@ -354,7 +356,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa,
 		        (t_synced - t_launched) * 1e3, (mp_realtime() - t_synced) * 1e3);
 }
 
-void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_opt_t *base, std::vector<DpDev> &jobs, DpSet &out)
+void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_ss, const char *d_aa, const ns_opt_t *base, std::vector<DpDev> &jobs, DpSet &out)
 {
 	const size_t n = jobs.size();
 	out.score.assign(n, 0), out.nt_len.assign(n, 0), out.aa_len.assign(n, 0);
@@ -380,7 +382,7 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const char *d_aa, const ns_
 			if (hi > lo && (tb_bytes + tbb > kTbBudget || rw_bytes + rwb > kRwBudget)) break;
 			tb_bytes += tbb, rw_bytes += rwb, ++hi;
 		}
-		run_subwave(ctx, packed, d_aa, cst, base, jobs, lo, hi, out);
+		run_subwave(ctx, packed, d_ss, d_aa, cst, base, jobs, lo, hi, out);
 		lo = hi;
 	}
 }

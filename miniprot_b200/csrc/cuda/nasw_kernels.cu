@@ -44,11 +44,19 @@ __device__ __forceinline__ int job_code(const uint8_t *packed, const DpDev &j, i
 	return b;
 }
 
+// --spsc byte of the nucleotide of row k (-1: this problem has none); the table is laid out like the genome, one byte per base and strand
+__device__ __forceinline__ int job_spsc(const uint8_t *ss, const DpDev &j, int k)
+{
+	if (j.ss_off < 0) return -1;
+	const int64_t g = j.ss_off + j.g_start + (int64_t)j.dir * k;
+	return g == j.ss_excl ? 0xff : (int)ss[g];
+}
+
 // ------------------------------------------------------------------ prep
 // One CTA per chunk of <= PREP_ROWS rows of one problem: phase 1 evaluates the per-row splice / codon rules into shared
 // memory (with a halo of 2 rows before and 1 after), phase 2 combines rows i-2..i+1 into the 32-byte record of row i.
 __global__ void __launch_bounds__(256) nasw_prep_kernel(const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed,
-                                                        NaswConst cst, int4 *rec)
+                                                        const uint8_t *ss, NaswConst cst, int4 *rec)
 {
 	__shared__ uint32_t w[PREP_ROWS + 4];
 	const int ck = blockIdx.x;
@@ -56,10 +64,12 @@ __global__ void __launch_bounds__(256) nasw_prep_kernel(const DpDev *jobs, const
 	const PrepChunk c = chunks[ck];
 	const DpDev job = jobs[c.job];
 	auto code = [&](int k) { return job_code(packed, job, k); };
+	auto sbyte = [&](int k) { return job_spsc(ss, job, k); };
+	const SpscPar sq = { (job.io + 1) / 2 - 1, cst.sp_null_bonus };
 	for (int x = threadIdx.x; x < c.n_rows + 3; x += blockDim.x) { // smem slot x <-> row c.row0 - 2 + x
 		int r = c.row0 - 2 + x;
 		r = r < 0 ? 0 : (r > job.nl ? job.nl : r);
-		w[x] = (job.flag & NS_F_EXT_LEFT) ? prep_row_left(code, job.nl, r, cst.sp, cst.codon, cst.aa_x) : prep_row_forward(code, job.nl, r, cst.sp, cst.codon, cst.aa_x);
+		w[x] = (job.flag & NS_F_EXT_LEFT) ? prep_row_left(code, job.nl, r, cst.sp, cst.codon, cst.aa_x, sbyte, sq) : prep_row_forward(code, job.nl, r, cst.sp, cst.codon, cst.aa_x, sbyte, sq);
 	}
 	__syncthreads();
 	Par par;
@@ -521,9 +531,9 @@ static void launch_tb(cudaStream_t st, const DpDev *jobs, const int *order, int 
 	nasw_tb_kernel<C, MULTI><<<(n + NASW_WARPS - 1) / NASW_WARPS, NASW_WARPS * 32, smem, st>>>(jobs, order, n, rec, aa, cst, out, carry, tb);
 }
 
-void nasw_launch_prep(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, int4 *rec)
+void nasw_launch_prep(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const uint8_t *ss, const NaswConst &cst, int4 *rec)
 {
-	if (n_chunks > 0) nasw_prep_kernel<<<n_chunks, 256, 0, st>>>(jobs, chunks, n_chunks, packed, cst, rec);
+	if (n_chunks > 0) nasw_prep_kernel<<<n_chunks, 256, 0, st>>>(jobs, chunks, n_chunks, packed, ss, cst, rec);
 }
 
 // C = 1, 2, 4, 8: single-pass problems (at most 32*C padded columns); C = 16 stands for "8 columns per lane, several passes"

@@ -39,7 +39,7 @@ __device__ __forceinline__ int pair_job_code(const uint8_t *packed, const DpDev 
 // into shared memory with a halo, phase 2 combines them into the pair records, stored per parity of the triple index and
 // field-major (six arrays of 16-byte fields) so that the 32 lanes of a warp -- which are on triples two apart -- read 32
 // consecutive fields with each load.
-__global__ void __launch_bounds__(256) nasw_prep_pair_kernel(const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, NaswConst cst, uint4 *rec)
+__global__ void __launch_bounds__(256) nasw_prep_pair_kernel(const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const uint8_t *ss, NaswConst cst, uint4 *rec)
 {
 	__shared__ uint32_t w[3 * PAIR_TRI + 8];
 	const int ck = blockIdx.x;
@@ -48,10 +48,16 @@ __global__ void __launch_bounds__(256) nasw_prep_pair_kernel(const DpDev *jobs, 
 	const DpDev job = jobs[c.job];
 	const int m0 = c.row0, nt = c.n_rows, r0 = 3 * m0 - 3; // smem slot s <-> row r0 + s
 	auto code = [&](int k) { return pair_job_code(packed, job, k); };
+	auto sbyte = [&](int k) { // --spsc byte of row k's nucleotide (nasw_kernels.cu job_spsc)
+		if (job.ss_off < 0) return -1;
+		const int64_t g = job.ss_off + job.g_start + (int64_t)job.dir * k;
+		return g == job.ss_excl ? 0xff : (int)ss[g];
+	};
+	const SpscPar sq = { (job.io + 1) / 2 - 1, cst.sp_null_bonus };
 	for (int s = threadIdx.x; s < 3 * nt + 6; s += blockDim.x) {
 		int r = r0 + s;
 		r = r < 0 ? 0 : (r > job.nl ? job.nl : r);
-		w[s] = (job.flag & NS_F_EXT_LEFT) ? prep_row_left(code, job.nl, r, cst.sp, cst.codon, cst.aa_x) : prep_row_forward(code, job.nl, r, cst.sp, cst.codon, cst.aa_x);
+		w[s] = (job.flag & NS_F_EXT_LEFT) ? prep_row_left(code, job.nl, r, cst.sp, cst.codon, cst.aa_x, sbyte, sq) : prep_row_forward(code, job.nl, r, cst.sp, cst.codon, cst.aa_x, sbyte, sq);
 	}
 	__syncthreads();
 	const int nb = pair_rec_blocks(job.nl);
@@ -65,9 +71,9 @@ __global__ void __launch_bounds__(256) nasw_prep_pair_kernel(const DpDev *jobs, 
 	}
 }
 
-void nasw_launch_prep_pair(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const NaswConst &cst, int4 *rec)
+void nasw_launch_prep_pair(cudaStream_t st, const DpDev *jobs, const PrepChunk *chunks, int n_chunks, const uint8_t *packed, const uint8_t *ss, const NaswConst &cst, int4 *rec)
 {
-	if (n_chunks > 0) nasw_prep_pair_kernel<<<n_chunks, 256, 0, st>>>(jobs, chunks, n_chunks, packed, cst, (uint4*)rec);
+	if (n_chunks > 0) nasw_prep_pair_kernel<<<n_chunks, 256, 0, st>>>(jobs, chunks, n_chunks, packed, ss, cst, (uint4*)rec);
 }
 
 struct PairEnvDev {

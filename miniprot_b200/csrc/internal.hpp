@@ -18,6 +18,7 @@ void sort_128x(mp128_t *beg, mp128_t *end);       // by .x, reference tie order 
 // ---------------------------------------------------------------- genome store (ntdb.cpp)
 mp_ntdb_t *ntdb_read_fasta(const char *fn);                                  // ntseq.c:29
 void ntdb_destroy(mp_ntdb_t *db);
+int32_t ntdb_read_spsc(mp_ntdb_t *nt, const char *fn, int32_t max_sc); // ntseq.c:234
 void ntdb_dump(FILE *fp, const mp_ntdb_t *db);                               // ntseq.c:163
 mp_ntdb_t *ntdb_restore(FILE *fp);                                           // ntseq.c:176
 // bases [st,en) of contig cid as codes 0..4, reverse-complemented if rev (ntseq.c:89)
@@ -80,6 +81,7 @@ struct DpJob {                   // one ns_global_gs16b call (align.c:288/296/73
 	int32_t aa_st, al;
 	int32_t flag;                // NS_F_*
 	int32_t io;
+	int64_t win_st = -1;         // start of the region's window on strand vid: the --spsc byte of that one position reads "unset" (ntseq.c:130-156)
 };
 
 struct DpSet {

@@ -5,6 +5,9 @@
 // and everything else 4; contig c covers [ctg[c].off, ctg[c].off + ctg[c].len).  The same array is what
 // gets uploaded to HBM, so the device kernels unpack windows with the identical rule.
 #include <stdio.h>
+#include <algorithm>
+#include <string>
+#include <unordered_map>
 #include "internal.hpp"
 #include "fastx.hpp"
 
@@ -50,8 +53,79 @@ mp_ntdb_t *ntdb_read_fasta(const char *fn)
 void ntdb_destroy(mp_ntdb_t *db)
 {
 	if (!db) return;
+	if (db->spsc) for (int32_t i = 0; i < db->n_ctg * 2; ++i) free(db->spsc[i].a);
 	free(db->seq); free(db->ctg); free(db->name); free(db->spsc);
 	free(db);
+}
+
+// ntseq.c:234-296: "ctg offset +|- D|A score" lines -> per (contig, strand) a sorted array of pos << 8 | (score + 64) << 1 | is_acceptor,
+// positions counted on that strand.  The quirks of the reference reader are kept: any strand character but '+' means '-', lines with
+// fewer than five fields or an unknown contig / type are skipped, scores are clamped to +-max_sc, sites at either contig end ignored.
+int32_t ntdb_read_spsc(mp_ntdb_t *nt, const char *fn, int32_t max_sc)
+{
+	gzFile fp = fn && strcmp(fn, "-") != 0 ? gzopen(fn, "rb") : gzdopen(0, "rb");
+	if (fp == 0) return -1;
+	if (max_sc > 63) max_sc = 63;
+	std::unordered_map<std::string, int32_t> name2id;
+	for (int32_t i = 0; i < nt->n_ctg; ++i)
+		if (!name2id.emplace(nt->ctg[i].name, i).second) fprintf(stderr, "ERROR: duplicated contig name!\n");
+	if (nt->spsc) for (int32_t i = 0; i < nt->n_ctg * 2; ++i) free(nt->spsc[i].a);
+	free(nt->spsc);
+	nt->spsc = (mp_spsc_t*)calloc((size_t)nt->n_ctg * 2, sizeof(mp_spsc_t));
+	std::vector<std::vector<uint64_t>> per((size_t)nt->n_ctg * 2);
+	std::string line;
+	std::vector<char> buf(1 << 16);
+	int64_t n_read = 0;
+	auto take_line = [&]() {
+		char *f[5];
+		int n_f = 0;
+		char *q = &line[0];
+		for (char *p = q;; ++p) {
+			if (*p == '\t' || *p == 0) {
+				const char c = *p;
+				*p = 0;
+				f[n_f++] = q;
+				if (n_f == 5 || c == 0) break;
+				q = p + 1;
+			}
+		}
+		if (n_f < 5) return;
+		const int64_t pos0 = atol(f[1]);
+		const int strand = *f[2] == '+' ? 1 : -1;
+		const int type = *f[3] == 'D' ? 0 : *f[3] == 'A' ? 1 : -1;
+		int score = atoi(f[4]);
+		if (score > max_sc) score = max_sc;
+		if (score < -max_sc) score = -max_sc;
+		const auto it = name2id.find(f[0]);
+		if (it == name2id.end() || type < 0 || pos0 < 0) return;
+		const int32_t cid = it->second;
+		const int64_t pos = strand < 0 ? nt->ctg[cid].len - pos0 : pos0;
+		if (pos > 0 && pos < nt->ctg[cid].len) {
+			per[(size_t)cid << 1 | (strand > 0 ? 0 : 1)].push_back((uint64_t)pos << 8 | (uint64_t)((score + 64) << 1 | type));
+			++n_read;
+		}
+	};
+	for (bool more = true; more;) {
+		line.clear();
+		while (line.empty() || line.back() != '\n') {
+			if (gzgets(fp, buf.data(), (int)buf.size()) == 0) { more = false; break; }
+			line += buf.data();
+		}
+		while (!line.empty() && (line.back() == '\n' || line.back() == '\r')) line.pop_back();
+		if (!line.empty()) take_line();
+	}
+	gzclose(fp);
+	for (size_t j = 0; j < per.size(); ++j) {
+		std::vector<uint64_t> &v = per[j];
+		if (v.empty()) continue;
+		std::sort(v.begin(), v.end());
+		mp_spsc_t *sp = &nt->spsc[j];
+		sp->n = sp->m = (uint32_t)v.size();
+		sp->a = (uint64_t*)malloc(sizeof(uint64_t) * v.size());
+		memcpy(sp->a, v.data(), sizeof(uint64_t) * v.size());
+	}
+	if (mp_verbose >= 3) fprintf(stderr, "[M::%s] read %ld splice scores\n", "mp_ntseq_read_spsc", (long)n_read);
+	return 0;
 }
 
 int64_t nt_fetch(const mp_ntdb_t *db, int32_t cid, int64_t st, int64_t en, int32_t rev, uint8_t *out)

@@ -270,14 +270,16 @@ long mp_peakrss(void) // sys.c:116-127
 mp_tbuf_t *mp_tbuf_init(void) { return (mp_tbuf_t*)calloc(1, 16); } // scratch lives in the GPU context; kept for ABI (map.c:16)
 void mp_tbuf_destroy(mp_tbuf_t *b) { free(b); }
 
-int32_t mp_ntseq_read_spsc(mp_ntdb_t *, const char *fn, int32_t)
+int32_t mp_ntseq_read_spsc(mp_ntdb_t *nt, const char *fn, int32_t max_sc) { return mpb::ntdb_read_spsc(nt, fn, max_sc); } // ntseq.c:234
+
+void mp_set_spsc(const char *fn, mp_idx_t *mi, mp_mapopt_t *mo, int32_t keep_io) // index.c:239-248
 {
-	if (fn) fprintf(stderr, "[WARNING] --spsc splice scores are not served by miniprot_b200 yet; ignored\n");
-	return -1;
-}
-void mp_set_spsc(const char *fn, mp_idx_t *, mp_mapopt_t *, int32_t)
-{
-	if (fn) fprintf(stderr, "[WARNING] --spsc splice scores are not served by miniprot_b200 yet; ignored\n");
+	if (fn == 0) return;
+	if (!keep_io) mo->io += 10, mo->io_end += 10;
+	int32_t max_sc = (mo->io + 1) / 2 - 1;
+	if (max_sc > mo->io - mo->go) max_sc = mo->io - mo->go;
+	if (max_sc > mo->sp_max_bonus) max_sc = mo->sp_max_bonus;
+	mp_ntseq_read_spsc(mi->nt, fn, max_sc);
 }
 
 } // extern "C"

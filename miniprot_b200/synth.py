@@ -222,3 +222,41 @@ if __name__ == "__main__":
     ap.add_argument("outdir")
     a = ap.parse_args()
     print(*generate(CONFIGS[a.config], a.outdir))
+
+
+def make_spsc(genome_fa: str, out_path: str, seed: int = 1, p_site: float = 0.6, p_noise: float = 0.002) -> str:
+    """A splice-score file for --spsc ("ctg offset +|- D|A score", reference ntseq.c:234-296) over a FASTA genome: scores at a share of
+    the GT / AG dinucleotides of both strands (donor: offset of the G; acceptor: offset just past the AG -- the offsets at which
+    nasw-sse.c:138-152 applies them to those sites) plus a sprinkle of sites elsewhere, a few of them duplicated with another score."""
+    rng = np.random.default_rng(seed)
+    comp = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+    ctgs, name, seq = [], None, []
+    with open(genome_fa, "rb") as f:
+        for ln in f:
+            if ln.startswith(b">"):
+                if name is not None:
+                    ctgs.append((name, b"".join(seq)))
+                name, seq = ln[1:].split()[0].decode(), []
+            else:
+                seq.append(ln.strip())
+    if name is not None:
+        ctgs.append((name, b"".join(seq)))
+    with open(out_path, "w") as out:
+        for name, s in ctgs:
+            n = len(s)
+            for strand, t in (("+", s.upper()), ("-", s.translate(comp)[::-1].upper())):
+                a = np.frombuffer(t, dtype=np.uint8)
+                gt = np.flatnonzero((a[:-1] == ord("G")) & (a[1:] == ord("T")))
+                ag = np.flatnonzero((a[:-1] == ord("A")) & (a[1:] == ord("G"))) + 2
+                for typ, pos in (("D", gt), ("A", ag)):
+                    pos = pos[rng.random(len(pos)) < p_site]
+                    sc = rng.integers(-8, 16, len(pos))
+                    for p, v in zip(pos, sc):
+                        out.write(f"{name}\t{p if strand == '+' else n - p}\t{strand}\t{typ}\t{v}\n")
+                        if rng.random() < 0.01:  # the same site again with another score: the larger byte wins (ntseq.c:146-152)
+                            out.write(f"{name}\t{p if strand == '+' else n - p}\t{strand}\t{typ}\t{int(v) - 3}\n")
+                noise = np.flatnonzero(rng.random(n) < p_noise)
+                for p in noise:
+                    out.write(f"{name}\t{p if strand == '+' else n - p}\t{strand}\t{'DA'[int(rng.integers(0, 2))]}\t{int(rng.integers(-20, 21))}\n")
+        out.write("no_such_contig\t10\t+\tD\t5\n" + f"{ctgs[0][0]}\t12\t+\n")  # lines the reader skips
+    return out_path

@@ -426,9 +426,10 @@ void run_pair(const Problem &P, int *score, int *nt_len, int *aa_len, std::vecto
 
 } // namespace
 
-extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *codon, const int8_t *mat, const int32_t *sp, int go, int ge, int io,
-                        int fs, int xdrop, int end_bonus, float ie_coef, int flag, int C, const uint8_t *ns, int nl, const char *as, int al,
-                        int *score, int *nt_len, int *aa_len, uint32_t *cigar, int cigar_cap)
+// ss = --spsc bytes of the slice (NULL: none), null_bonus = ns_opt_t::sp_null_bonus; problems with ss never run on the pair-lane kernels
+extern "C" int emu_nasw_ss(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *codon, const int8_t *mat, const int32_t *sp, int go, int ge, int io,
+                           int fs, int xdrop, int end_bonus, float ie_coef, int flag, int C, const uint8_t *ns, int nl, const char *as, int al,
+                           int *score, int *nt_len, int *aa_len, uint32_t *cigar, int cigar_cap, const uint8_t *ss, int null_bonus)
 {
 	Problem P;
 	P.nl = nl, P.al = al, P.W8 = (al + 7) / 8 * 8, P.mat = mat, P.end_bonus = end_bonus, P.xdrop = xdrop, P.ie_coef = ie_coef;
@@ -437,12 +438,14 @@ extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *
 	std::vector<int> code((size_t)nl);
 	for (int k = 0; k < nl; ++k) code[(size_t)k] = nt4[ns[left ? nl - 1 - k : k]];
 	auto c = [&](int k) { return code[(size_t)k]; };
+	auto sbyte = [&](int k) { return ss ? (int)ss[left ? nl - 1 - k : k] : -1; }; // byte of the nucleotide of DP row k
+	const SpscPar sq = { (io + 1) / 2 - 1, null_bonus };
 	const int n_rec = std::max(nl + 1, 2 + 3 * v3_triples(nl)); // rows past nl repeat the clamped rules, like the prep kernel
 	std::vector<uint32_t> w((size_t)n_rec + 3);
 	for (int x = 0; x < n_rec + 3; ++x) { // slot x <-> row x - 2, clamped like the prep kernel
 		int r = x - 2;
 		r = r < 0 ? 0 : (r > nl ? nl : r);
-		w[(size_t)x] = left ? prep_row_left(c, nl, r, sp, codon, aa20['X']) : prep_row_forward(c, nl, r, sp, codon, aa20['X']);
+		w[(size_t)x] = left ? prep_row_left(c, nl, r, sp, codon, aa20['X'], sbyte, sq) : prep_row_forward(c, nl, r, sp, codon, aa20['X'], sbyte, sq);
 	}
 	P.w = w, P.io = io;
 	P.rec.resize((size_t)n_rec);
@@ -485,6 +488,13 @@ extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *
 		for (int k = 0; k < n_cig && k < cigar_cap; ++k) cigar[k] = cg[(size_t)k];
 	}
 	return n_cig;
+}
+
+extern "C" int emu_nasw(const uint8_t *nt4, const uint8_t *aa20, const uint8_t *codon, const int8_t *mat, const int32_t *sp, int go, int ge, int io,
+                        int fs, int xdrop, int end_bonus, float ie_coef, int flag, int C, const uint8_t *ns, int nl, const char *as, int al,
+                        int *score, int *nt_len, int *aa_len, uint32_t *cigar, int cigar_cap)
+{
+	return emu_nasw_ss(nt4, aa20, codon, mat, sp, go, ge, io, fs, xdrop, end_bonus, ie_coef, flag, C, ns, nl, as, al, score, nt_len, aa_len, cigar, cigar_cap, 0, 0);
 }
 
 // step-table form of the extension length penalty vs the direct FP32 formula, for x in [0, xmax]

@@ -107,3 +107,54 @@ def test_emu_score_when_end_column_is_first_of_a_pass(hc):
             a = ol.ora_nasw(tab, nt, aa, 1, mat, par)
             b = emu(hc, nt, aa, 1, 0, mat, par)
             assert a[0] == b[0] and a[3] == b[3], (al, nl, a[0], b[0])
+
+
+def random_spsc(rng, nt, max_sc=14, p_set=0.3):
+    """--spsc bytes for a slice (ntseq.c:130-156): 0xff = unset, else (score + 64) << 1 | is_acceptor."""
+    n = len(nt)
+    ss = np.full(n, 0xff, dtype=np.uint8)
+    k = rng.random(n) < p_set
+    sc = rng.integers(-max_sc, max_sc + 1, n)
+    ty = rng.integers(0, 2, n)
+    ss[k] = ((sc[k] + 64) << 1 | ty[k]).astype(np.uint8)
+    return ss
+
+
+def emu_ss(hc, nt, aa, flag, Ccols, mat, par, ss):
+    r = ol.ref()
+    hc.emu_nasw_ss.restype = C.c_int
+    hc.emu_nasw_ss.argtypes = [C.c_void_p] * 5 + [C.c_int] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_int] + \
+        [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int]
+    sp = (C.c_int32 * 6)(*par["sp"])
+    sc, ntl, aal = C.c_int(), C.c_int(), C.c_int()
+    cig = (C.c_uint32 * (len(nt) + len(aa) + 16))()
+    n = hc.emu_nasw_ss(C.addressof(C.c_uint8.in_dll(r, "ref_ns_tab_nt4")), C.addressof(C.c_uint8.in_dll(r, "ref_ns_tab_aa20")),
+                       C.addressof(C.c_uint8.in_dll(r, "ref_ns_tab_codon")), mat.ctypes.data, C.addressof(sp), par["go"], par["ge"],
+                       par["io"], par["fs"], par["xdrop"], par["end_bonus"], par["ie_coef"], flag, Ccols,
+                       nt.ctypes.data, len(nt), aa, len(aa), C.addressof(sc), C.addressof(ntl), C.addressof(aal), C.addressof(cig), len(cig),
+                       ss.ctypes.data, par["sp_null_bonus"])
+    return sc.value, ntl.value, aal.value, [cig[i] for i in range(n)]
+
+
+@pytest.mark.parametrize("Ccols", [0, 1, 8])
+def test_emu_with_splice_scores_matches_reference(hc, Ccols):
+    """--spsc (nasw-sse.c:138-152,189-203): donor / acceptor entries shifted by per-base scores, negative ones included.  The same
+    per-row preparation the prep kernels compile, against the reference's own ns_global_gs16b and the oracle."""
+    rng = np.random.default_rng(4242 + Ccols)
+    tab, mat = ol.ref_tables(), ol.default_mat()
+    for it in range(80):
+        par = dict(ol.DEFAULT_NASW)
+        par["io"] = 39 if it % 4 else 29          # mp_set_spsc adds 10 unless --spsc-keep-io (index.c:242)
+        par["sp_null_bonus"] = -7 if it % 3 else -2
+        nt, aa = ol.random_dp_problem(rng, al_max=(120, 30, 200)[[0, 1, 8].index(Ccols)], flank=60)
+        if len(nt) < 3:
+            continue
+        ss = random_spsc(rng, nt, max_sc=(par["io"] + 1) // 2 - 1 if it % 5 else 40, p_set=0.3 if it % 2 else 0.9)
+        for flag in (1, 4, 2):
+            a = ol.ref_nasw(nt, aa, flag, mat, par, ss)
+            o = ol.ora_nasw(tab, nt, aa, flag, mat, par, ss)
+            b = emu_ss(hc, nt, aa, flag, Ccols, mat, par, ss)
+            if flag == 1:
+                assert a[0] == b[0] == o[0] and a[3] == b[3] == o[3], (it, flag, len(nt), len(aa), a, b)
+            else:
+                assert a[:3] == b[:3] == o[:3], (it, flag, len(nt), len(aa), a[:3], b[:3])

@@ -39,11 +39,63 @@ def test_reference_cli_on_our_library(tmp_path):
 
 
 @need_bins
+def test_splice_score_file(tmp_path):
+    """--spsc: the reference's own CLI reads the score file through our mp_set_spsc / mp_ntseq_read_spsc, the scores
+    reach the DP as a dense byte table in HBM.  Output identical to the reference's, and different from a run without the file."""
+    g, p = synth.generate(synth.CONFIGS["small"], str(tmp_path))
+    sp = synth.make_spsc(g, str(tmp_path / "small.spsc"), seed=5)
+    plain = out([CLI, "-t8", g, p])
+    for args in (("--spsc", sp), ("--spsc", sp, "--spsc0=-3", "--spsc-max=10"), ("--spsc", sp, "--gff", "-j2")):
+        a, b = out([CLI, "-t8", *args, g, p]), out([ol.REF_BIN, "-t8", *args, g, p])
+        assert a == b, args
+        assert len(a) > 1000
+    assert out([CLI, "-t8", "--spsc", sp, g, p]) != plain
+    g, p = os.path.join(DATA, "DPP3-hs.gen.fa.gz"), os.path.join(DATA, "DPP3-mm.pep.fa.gz")
+    import gzip
+    fa = str(tmp_path / "dpp3.fa")
+    with gzip.open(g, "rb") as f, open(fa, "wb") as o:
+        o.write(f.read())
+    sp = synth.make_spsc(fa, str(tmp_path / "dpp3.spsc"), seed=6)
+    assert out([CLI, "-t4", "--spsc", sp, g, p]) == out([ol.REF_BIN, "-t4", "--spsc", sp, g, p])
+
+
+@need_bins
 def test_reference_example_on_our_library(tmp_path):
     g, p = synth.generate(synth.CONFIGS["tiny"], str(tmp_path))
     assert out([EX, g, p]) == out([EX_REF, g, p])
     g, p = os.path.join(DATA, "DPP3-hs.gen.fa.gz"), os.path.join(DATA, "DPP3-mm.pep.fa.gz")
     assert out([EX, g, p]) == out([EX_REF, g, p])
+
+
+def test_ns_global_gs16b_with_splice_bytes():
+    """ns_global_gs16b(.., ss, ..) (nasw.h:131): the per-base splice bytes of one problem travel with the batch of one."""
+    L = mp.lib()
+    rng = np.random.default_rng(12)
+    opt = mp.nsopt()
+    opt.io = 39
+    tab = ol.OraTab()
+    for f, sym in (("nt4", "ns_tab_nt4"), ("aa20", "ns_tab_aa20"), ("aa13", "ns_tab_aa13"), ("codon", "ns_tab_codon"), ("codon13", "ns_tab_codon13")):
+        setattr(tab, f, C.addressof(C.c_uint8.in_dll(L, sym)))
+    par = dict(go=opt.go, ge=opt.ge, io=opt.io, fs=opt.fs, xdrop=opt.xdrop, end_bonus=opt.end_bonus, sp=tuple(opt.sp), sp_null_bonus=opt.sp_null_bonus, ie_coef=opt.ie_coef)
+    f = L.ns_global_gs16b
+    f.restype = None
+    for it in range(12):
+        for flag in (1, 2, 4):
+            nt, aa = ol.random_dp_problem(rng, al_max=(70, 300)[it & 1], flank=50)
+            while len(nt) < 3:
+                nt, aa = ol.random_dp_problem(rng, al_max=70, flank=50)
+            ss = np.full(len(nt), 0xff, dtype=np.uint8)
+            k = rng.random(len(nt)) < 0.4
+            ss[k] = ((rng.integers(-14, 15, int(k.sum())) + 64) << 1 | rng.integers(0, 2, int(k.sum()))).astype(np.uint8)
+            opt.flag = flag
+            r = NsRst()
+            f(None, nt.ctypes.data_as(C.c_char_p), C.c_int32(len(nt)), aa, C.c_int32(len(aa)), C.byref(opt), ss.ctypes.data_as(C.c_void_p), C.byref(r))
+            w = ol.ora_nasw(tab, nt, aa, flag, opt._mat_keepalive, par, ss)
+            if flag == 1:
+                assert w[0] == r.score and w[3] == [r.cigar[k] for k in range(r.n_cigar)], (it, flag)
+                L.mpb_free(r.cigar)
+            else:
+                assert w[:3] == (r.score, r.nt_len, r.aa_len), (it, flag)
 
 
 class NsRst(C.Structure):  # ns_rst_t (nasw.h:73-78)

@@ -92,3 +92,33 @@ def test_no_gpu_means_loud_failure(L):
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError):
         mp.Context(0)
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="needs oracle/_ref")
+def test_splice_score_reader_equals_reference(L, tmp_path):
+    """mp_set_spsc / mp_ntseq_read_spsc (index.c:239-248, ntseq.c:234-296): option side effects and the sorted per-strand arrays."""
+    from miniprot_b200 import synth
+    r = ol.ref()
+    g, _ = synth.generate(synth.CONFIGS["tiny"], str(tmp_path))
+    sp = synth.make_spsc(g, str(tmp_path / "t.spsc"), seed=3, p_site=0.2, p_noise=0.001)
+
+    class Spsc(C.Structure):
+        _fields_ = [("n", C.c_uint32), ("m", C.c_uint32), ("a", C.POINTER(C.c_uint64))]
+
+    io = mp.idxopt()
+    for fn in (L.mp_idx_load, r.ref_mp_idx_load):
+        fn.restype = C.POINTER(mp.Idx)
+    a, b = L.mp_idx_load(g.encode(), C.byref(io), 4), r.ref_mp_idx_load(g.encode(), C.byref(io), 4)
+    for keep_io in (0, 1):
+        mo, ro = mp.mapopt(), mp.mapopt()
+        L.mp_set_spsc(sp.encode(), a, C.byref(mo), keep_io), r.ref_mp_set_spsc(sp.encode(), b, C.byref(ro), keep_io)
+        assert (mo.io, mo.io_end) == (ro.io, ro.io_end) == ((29, 19) if keep_io else (39, 29))
+        n_ctg = a.contents.nt.contents.n_ctg
+        sa, sb = C.cast(a.contents.nt.contents.spsc, C.POINTER(Spsc)), C.cast(b.contents.nt.contents.spsc, C.POINTER(Spsc))
+        tot = 0
+        for j in range(2 * n_ctg):
+            assert sa[j].n == sb[j].n, j
+            assert [sa[j].a[k] for k in range(sa[j].n)] == [sb[j].a[k] for k in range(sb[j].n)], j
+            tot += sa[j].n
+        assert tot > 1000
+    L.mp_idx_destroy(a)
