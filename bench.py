@@ -411,7 +411,7 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
 
     # ---- rooflines.  Kernel times are CUDA events on the stream each class is launched on.
-    CLS = ["v3<1>", "v3<2>", "v3<4>", "v3<8>", "cols<1>", "cols<2>", "cols<4>", "cols<8>", "cols<8,multi>", "pair<1>", "pair<2>", "pair<4>", "pair<8>", "", "", ""]
+    CLS = ["v3<1>", "v3<2>", "v3<4>", "v3<8>", "cols<1>", "cols<2>", "cols<4>", "cols<8>", "cols<8,multi>", "pair<1>", "v3<4> x 2 column passes", "", "", "", "", ""]
 
     def cls_rows(b):
         rows = []

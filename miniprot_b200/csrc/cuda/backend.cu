@@ -322,6 +322,25 @@ int mpb_idx_upload(mpb_ctx_t *c, const mp_idx_t *mi)
 	return 0;
 }
 
+// FASTA -> index with the k-mer tables built on the device (idx_build.cu); called by mp_idx_load through g_idx_build_hook once the
+// genome is packed.  The tables stay resident in the default context, so the mapping calls that follow find the index uploaded.
+// Returns non-zero when there is no device or the options are outside what the device scan covers: the caller then builds on the host.
+static int build_index_on_device(mp_idx_t *mi)
+{
+	if (const char *e = getenv("MPB_IDX_BUILD")) if (strcmp(e, "host") == 0) return -1;
+	int n_dev = 0;
+	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) { cudaGetLastError(); return -1; }
+	mpb_ctx_t *c = mpb_ctx_default();
+	const double t0 = mp_realtime();
+	if (idx_build_device(c, mi) != 0) return -1;
+	c->d_ki = c->own_ki.as<int64_t>(), c->d_kb = c->own_kb.as<uint32_t>(), c->d_seq = c->own_seq.as<uint8_t>();
+	upload_meta(c, mi);
+	c->mi = mi, c->own_index = true;
+	if (mp_verbose >= 3) fprintf(stderr, "[M::%s@%.3f] built the k-mer tables on the device in %.3f s: %ld kmer-block pairs\n", __func__, mp_realtime(), mp_realtime() - t0, (long)mi->n_kb);
+	return 0;
+}
+namespace { struct IdxBuildHook { IdxBuildHook() { mpb::g_idx_build_hook = build_index_on_device; } } g_idx_build_hook_init; }
+
 // .mpi file -> HBM: the k-mer tables ki / kb -- 85-90 % of the file, needed on the device only -- never get a
 // host copy: the file is read in 32 MB pieces into two pinned buffers and each piece leaves for the device while the next
 // one is being read.  The genome section is kept on the host as well (statistics, cs tags, output formats read it).  The

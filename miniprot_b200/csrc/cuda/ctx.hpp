@@ -51,6 +51,7 @@ namespace cuda {
 
 // One nasw wave over device-resident sequences.  `packed` is the nibble array the jobs' g_start refer to,
 // `d_aa` the residue buffer their aa_off refer to.  jobs[].{g_start,dir,comp,nl,al,aa_off,flag,io} must be set.
+int idx_build_device(mpb_ctx_s *c, mp_idx_t *mi); // idx_build.cu: ki / kb of mi from its packed genome, resident in c->own_ki / own_kb
 void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_ss, const char *d_aa, const ns_opt_t *base, std::vector<DpDev> &jobs, DpSet &out);
 
 int nasw_check_ie_coef(float ie_coef); // 0 if the extension length penalty fits the kernels' step table

@@ -44,7 +44,9 @@ static inline bool use_v3(int al, int nl)
 // instead: per row a two-warp CTA is the faster one (152 against 240 cycles), but the publishing fence, the carry traffic and
 // above all the start-up lag of each further pass (short global alignments!) cost more than that gains -- C2 step 45 ms against
 // 34 ms (profiles/README.md) -- so CTAs of up to 8 warps stay the default.
+constexpr int NCLS_ = 13;
 static int g_pass_warps = 8;
+static bool g_split_long = true; // MPB_NASW_SPLIT=0: long wide extensions stay on one 8-warp CTA (A/B)
 static inline int v3_warps(int al)
 {
 	const int nw = ((al + 7) / 8 * 8 + 31) / 32;
@@ -116,10 +118,10 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_
 	const double t_in = mp_realtime();
 	int64_t rw_tot = 0, tb_tot = 0, cig_tot = 0, carry_tot = 0;
 	std::vector<PrepChunk> chunks, pchunks; // row-record chunks of the 32-bit families, pair-record chunks of the pair-lane family
-	bool wide3[2][4] = { { false, false, false, false }, { false, false, false, false } }; // does a block-wide class hold problems of more than one pass?
+	bool wide3[2][NCLS_] = { { false } }; // does a block-wide class hold problems of more than one pass?
 	std::vector<int> unsupported;
 	const PairLimits plim = pair_limits(nso);
-	constexpr int NCLS = 13;
+	constexpr int NCLS = NCLS_;
 	std::vector<int> order[2][NCLS]; // [is_tb][class]: 0..3 block-wide wavefront with 1/2/4/8 warps; 4..7 column passes C = 1/2/4/8; 8 multi-pass; 9 pair-lane kernels (one warp per problem)
 	for (int k = 0; k < n; ++k) {
 		DpDev &j = jobs[lo + k];
@@ -148,7 +150,11 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_
 			continue;
 		}
 		const bool v3 = use_v3(j.al, j.nl);
-		const int nw = v3_warps(j.al);
+		int nw = v3_warps(j.al);
+		// A long extension of 129..256 columns is the pole of its wave on one 8-warp CTA (240 cycles per row: eight warps at one barrier);
+		// as two concurrent column passes of four warps (181 cycles per row, linked by the carry row) it is not.  Class 10.
+		const bool split = g_split_long && v3 && !is_tb && nw == 8 && j.nl >= 32768 && (j.al + 7) / 8 * 8 <= 256 && (j.al + 7) / 8 * 8 > 128;
+		if (split) nw = 4;
 		j.C = v3 ? 0 : pick_C(j.al);
 		j.pad_ = v3 ? 32 * nw : 0;
 		const int Wp = v3 ? 32 * nw : 32 * j.C, W8 = (j.al + 7) / 8 * 8, n_pass = (W8 + Wp - 1) / Wp;
@@ -165,8 +171,9 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_
 		}
 		if (n_pass > 1) j.carry_off = carry_tot, carry_tot += ((int64_t)j.nl + 2) * 4; // four ints per row
 		for (int r = 0; r < rec_rows; r += PREP_ROWS) chunks.push_back(PrepChunk{ k, r, std::min(PREP_ROWS, rec_rows - r), 0 });
-		if (v3 && n_pass > 1) wide3[is_tb][nw == 1 ? 0 : nw == 2 ? 1 : nw == 4 ? 2 : 3] = true;
-		order[is_tb][v3 ? (nw == 1 ? 0 : nw == 2 ? 1 : nw == 4 ? 2 : 3) : n_pass > 1 ? 8 : j.C == 1 ? 4 : j.C == 2 ? 5 : j.C == 4 ? 6 : 7].push_back(k);
+		const int cls = split ? 10 : v3 ? (nw == 1 ? 0 : nw == 2 ? 1 : nw == 4 ? 2 : 3) : n_pass > 1 ? 8 : j.C == 1 ? 4 : j.C == 2 ? 5 : j.C == 4 ? 6 : 7;
+		if (v3 && n_pass > 1) wide3[is_tb][cls] = true;
+		order[is_tb][cls].push_back(k);
 		(is_tb ? ctx->stats.dp_cells_tb : ctx->stats.dp_cells_ext) += (int64_t)j.nl * j.al;
 		(is_tb ? ctx->stats.n_dp_tb : ctx->stats.n_dp_ext) += 1;
 	}
@@ -181,14 +188,14 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_
 		}
 	// units of the multi-pass launches: (slot in the class's order list, pass), passes of a problem consecutive
 	std::vector<int2> units;
-	int unit_first[2][4] = { { 0 } }, unit_count[2][4] = { { 0 } }, n_units_tot = 0;
+	int unit_first[2][NCLS] = { { 0 } }, unit_count[2][NCLS] = { { 0 } }, n_units_tot = 0;
 	for (int b = 0; b < 2; ++b)
-		for (int c = 0; c < 4; ++c) {
+		for (int c = 0; c < NCLS; ++c) {
 			unit_first[b][c] = (int)units.size();
 			if (wide3[b][c])
 				for (size_t s = 0; s < count[b][c]; ++s) {
 					const DpDev &jj = jobs[lo + flat[first[b][c] + s]];
-					const int Wp = 32 << c, np = ((jj.al + 7) / 8 * 8 + Wp - 1) / Wp;
+					const int Wp = jj.pad_, np = ((jj.al + 7) / 8 * 8 + Wp - 1) / Wp;
 					for (int q = 0; q < np; ++q) units.push_back(make_int2((int)s, q));
 				}
 			unit_count[b][c] = (int)units.size() - unit_first[b][c];
@@ -248,7 +255,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_
 				nasw_launch_bt(ss, dj, ord, cnt, ctx->b_tb.as<uint16_t>(), ctx->b_cigar.as<uint32_t>(), ctx->b_out.as<int4>());
 				ctx->stats.kernel_launches += 1;
 			}
-		} else if (c < 4) {
+		} else if (c < 4 || c == 10) {
 			const bool multi = wide3[b][c];
 			const int2 *d_units = 0;
 			int *d_prog = 0, n_launch = cnt;
@@ -256,7 +263,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_
 				d_units = ctx->b_units.as<int2>() + unit_first[b][c], d_prog = (int*)(ctx->b_units.as<int2>() + n_units_tot) + unit_first[b][c];
 				n_launch = unit_count[b][c];
 			}
-			nasw_launch_v3(ss, Cs[c], b == 1, dj, ord, n_launch, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>(),
+			nasw_launch_v3(ss, c == 10 ? 4 : Cs[c], b == 1, dj, ord, n_launch, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>(),
 			               wsm_env > 0 ? wsm_env : 0, ctx->b_carry.as<int>(), multi, d_units, d_prog);
 			ctx->stats.kernel_launches += 1;
 			MPB_CUDA_OK(cudaEventRecord(ctx->ev_km[g.sid], ss));
@@ -366,6 +373,7 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_ss, const 
 		const char *e = getenv("MPB_NASW_KERNEL");
 		const char *pw = getenv("MPB_NASW_PASS_WARPS");
 		g_pass_warps = pw && atoi(pw) == 2 ? 2 : 8;
+		if (const char *sp = getenv("MPB_NASW_SPLIT")) g_split_long = atoi(sp) != 0; else g_split_long = true;
 		g_forced_family = !e ? 0 : strcmp(e, "cols") == 0 ? 1 : strcmp(e, "v3") == 0 ? 2 : strcmp(e, "pair") == 0 ? 3 : 0;
 	}
 	NaswConst cst;

@@ -605,7 +605,10 @@ void nasw_launch_v3(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, cons
 		if (multi) launch_v3<2, true, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry, units, progress);
 		else launch_v3<2, true, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
 		break;
-	case 8: launch_v3<4, false, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
+	case 8:
+		if (multi) launch_v3<4, false, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry, units, progress);
+		else launch_v3<4, false, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
+		break;
 	case 9: launch_v3<4, true, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
 	case 16:
 		if (multi) launch_v3<8, false, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry, units, progress);

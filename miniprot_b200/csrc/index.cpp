@@ -4,8 +4,8 @@
 //   bo[c*2+s]   first block id of strand s of contig c; a block is 1<<bbit bases; bo[2*n_ctg] = n_block
 //   ki[h]       start of bucket h in kb[], h in [0, 2^(4k-mod_bit)); no sentinel: the last bucket ends at n_kb
 //   kb[]        block ids; inside a bucket grouped by contig*2+strand in ascending order, ascending within a group
-// Index construction is out of the accelerated path in this round: it runs on host threads,
-// one task per contig strand like the reference (index.c:52-69,123), and must produce identical ki/kb.
+// Index construction: the FASTA is read and packed here; ki / kb are built on the GPU (cuda/idx_build.cu) or,
+// without a device, on host threads, one task per contig strand like the reference (index.c:52-69,123).  Identical ki/kb either way.
 #include <stdio.h>
 #include <algorithm>
 #include <atomic>
@@ -15,6 +15,7 @@
 namespace mpb {
 
 void (*g_idx_destroy_hook)(const mp_idx_t *) = 0;
+int (*g_idx_build_hook)(mp_idx_t *) = 0; // the device builder (cuda/idx_build.cu), set when the CUDA backend is linked in
 
 uint32_t hash32_mask(uint32_t x, uint32_t mask) // invertible mixer on 4k-bit keys (sketch.c:7-16)
 {
@@ -111,6 +112,9 @@ static mp_idx_t *idx_build(const char *fn, const mp_idxopt_t *io, int32_t n_thre
 	mp_idx_t *mi = (mp_idx_t*)calloc(1, sizeof(mp_idx_t));
 	mi->opt = *io, mi->nt = nt;
 	mi->bo = block_offsets(nt, io->bbit, &mi->n_block);
+	// the k-mer tables are built on the GPU when there is one; the host threads below serve boxes without a device
+	// (preparing a .mpi file on a login node) and MPB_IDX_BUILD=host
+	if (g_idx_build_hook && g_idx_build_hook(mi) == 0) return mi;
 	const int32_t n_task = nt->n_ctg * 2;
 	std::vector<std::vector<uint64_t>> sk((size_t)n_task);
 	std::atomic<int32_t> next(0);

@@ -35,6 +35,7 @@ static inline uint8_t nt_at_v(const mp_ntdb_t *db, uint32_t vid, int64_t pos) //
 
 // ---------------------------------------------------------------- index (index.cpp)
 extern void (*g_idx_destroy_hook)(const mp_idx_t *);                           // set by the CUDA backend
+extern int (*g_idx_build_hook)(mp_idx_t *);                                    // device index builder; non-zero return = build on the host
 int32_t idx_block2vid(const mp_idx_t *mi, uint32_t block);                  // index.c:41
 mp_idx_t *idx_restore_head(FILE *fp);                                        // .mpi up to (not including) ki / kb
 static inline uint32_t idx_n_bucket(const mp_idxopt_t *io) { return 1U << (io->kmer * 4 - io->mod_bit); }

@@ -39,6 +39,36 @@ def test_reference_cli_on_our_library(tmp_path):
 
 
 @need_bins
+def test_index_built_on_device(tmp_path):
+    """mp_idx_load on a FASTA builds ki / kb on the GPU (cuda/idx_build.cu).  The dumped .mpi must equal, byte for byte,
+    the one of the reference and the one of our host builder -- on a synthetic genome, on DPP3, and on a FASTA of awkward contigs
+    (shorter than a codon, shorter than an ORF, runs of N, lower case, a 300 kb ORF-rich stretch without stop codons)."""
+    rng = np.random.default_rng(3)
+    odd = str(tmp_path / "odd.fa")
+    with open(odd, "w") as f:
+        for i, n in enumerate((1, 2, 3, 5, 89, 90, 91, 92, 93, 2047, 2048, 2049, 4096 + 91, 70000)):
+            s = "".join("ACGT"[x] for x in rng.integers(0, 4, n))
+            if n > 100:
+                k = int(rng.integers(0, n - 50))
+                s = s[:k] + "N" * int(rng.integers(1, 40)) + s[k:].lower()
+            f.write(f">c{i} some text\n{s}\n")
+        no_stop = [c for c in (a + b + c for a in "ACGT" for b in "ACGT" for c in "ACGT") if c not in ("TAA", "TAG", "TGA")]
+        f.write(">orf\n" + "".join(no_stop[x] for x in rng.integers(0, len(no_stop), 100000)) + "\n")
+        f.write(">polyA\n" + "A" * 50000 + "\n")
+    gs, _ = synth.generate(synth.CONFIGS["small"], str(tmp_path))
+    for tag, g in (("odd", odd), ("dpp3", os.path.join(DATA, "DPP3-hs.gen.fa.gz")), ("small", gs)):
+        dev, host, ref = (str(tmp_path / f"{tag}.{x}.mpi") for x in ("dev", "host", "ref"))
+        r = subprocess.run([CLI, "-t8", "-d", dev, g], check=True, capture_output=True, timeout=300)
+        assert b"built the k-mer tables on the device" in r.stderr, r.stderr[-500:]
+        r = subprocess.run([CLI, "-t8", "-d", host, g], check=True, capture_output=True, timeout=300, env=dict(os.environ, MPB_IDX_BUILD="host"))
+        assert b"on the device" not in r.stderr
+        subprocess.run([ol.REF_BIN, "-t8", "-d", ref, g], check=True, capture_output=True, timeout=300)
+        a, b, c = (open(x, "rb").read() for x in (dev, host, ref))
+        assert len(a) == len(c) and a == c, tag
+        assert b == c, tag
+
+
+@need_bins
 def test_splice_score_file(tmp_path):
     """--spsc: the reference's own CLI reads the score file through our mp_set_spsc / mp_ntseq_read_spsc, the scores
     reach the DP as a dense byte table in HBM.  Output identical to the reference's, and different from a run without the file."""

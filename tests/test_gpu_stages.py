@@ -101,6 +101,26 @@ def test_nasw_extension_wider_than_4095_columns(ctx):
         assert ol.ora_nasw(tab, nt, aa, flag, mat, _par(opt))[:3] == g[:3], (flag, len(nt), len(aa))
 
 
+def test_nasw_long_wide_extension_as_two_passes(ctx):
+    """Extensions of 129..256 columns over >= 32768 rows run as two concurrent 4-warp column passes linked by the carry row
+    (nasw_host.cu, class 10).  A protein tail that never aligns keeps the extension going over the whole window, like the
+    100 k-row end extensions of a real run."""
+    rng = np.random.default_rng(99)
+    opt = mp.nsopt()
+    tab, mat = product_tables(), opt._mat_keepalive
+    probs = []
+    for flag, al, tail in ((4, 140, 34000), (2, 200, 33000), (4, 256, 40000), (2, 129, 36000), (4, 136, 32768 - 400)):
+        nt, aa = ol.random_dp_problem(rng, al_max=al, flank=40, intron_max=300, p_sub=0.25)
+        while len(aa) < al - 8 or len(aa) > al:
+            nt, aa = ol.random_dp_problem(rng, al_max=al, flank=40, intron_max=300, p_sub=0.25)
+        junk = rng.integers(0, 4, size=tail).astype(np.uint8)
+        nt = np.concatenate([junk, nt]) if flag == 2 else np.concatenate([nt, junk])
+        probs.append((nt, aa, flag, opt.io))
+    got = mp.nasw_batch(ctx, opt, probs)
+    for (nt, aa, flag, io), g in zip(probs, got):
+        assert ol.ora_nasw(tab, nt, aa, flag, mat, _par(opt))[:3] == g[:3], (flag, len(nt), len(aa))
+
+
 @pytest.mark.parametrize("mode", ["pre", "main", "refine"])
 def test_chain_batch_matches_oracle(ctx, mode):
     rng = np.random.default_rng({"pre": 31, "main": 32, "refine": 33}[mode])
