@@ -80,7 +80,13 @@ void ns_opt_init(ns_opt_t *opt);
 void ns_opt_set_sp(ns_opt_t *opt, int32_t model);
 void ns_set_stop_sc(int32_t asize, int8_t *mat, int8_t score);
 
-/* One DP problem; dispatched to the GPU as a batch of one (use mpb_nasw_batch for real batches). */
+/* One DP problem; dispatched to the GPU as a batch of one (use mpb_nasw_batch for real batches).
+ * Memory contract: the reference allocates r->cigar from the kalloc arena `km` and its callers kfree(km, r->cigar) (nasw.h:77,
+ * align.c:77).  Here `km` is accepted and IGNORED: r->cigar is always malloc'ed and is released with free() (or mpb_free()).
+ * That is what kfree(0, ptr) does in the reference, so callers that pass km = NULL -- example code, tests -- need no change;
+ * a caller that passes a real arena must switch the release to free().
+ * ss: per-base splice-score bytes of the slice (--spsc, ntseq.c:130-156; NULL = none), applied like nasw-sse.c:138-152,189-203.
+ * ns_global_gs32 / ns_global_gs32b (reference nasw.h:129,132; never called by miniprot) are NOT exported: see DESIGN.md section 8. */
 void ns_global_gs16(void *km, const char *ns, int32_t nl, const char *as, int32_t al, const ns_opt_t *opt, ns_rst_t *r);
 void ns_global_gs16b(void *km, const char *ns, int32_t nl, const char *as, int32_t al, const ns_opt_t *opt, const uint8_t *ss, ns_rst_t *r);
 
