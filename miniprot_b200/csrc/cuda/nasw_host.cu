@@ -46,7 +46,7 @@ static inline bool use_v3(int al, int nl)
 // 34 ms (profiles/README.md) -- so CTAs of up to 8 warps stay the default.
 constexpr int NCLS_ = 13;
 static int g_pass_warps = 8;
-static bool g_split_long = true; // MPB_NASW_SPLIT=0: long wide extensions stay on one 8-warp CTA (A/B)
+static bool g_split_long = false; // MPB_NASW_SPLIT=1: long extensions of 129..256 columns as two 4-warp column passes (measured slower, see below)
 static inline int v3_warps(int al)
 {
 	const int nw = ((al + 7) / 8 * 8 + 31) / 32;
@@ -151,8 +151,10 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_
 		}
 		const bool v3 = use_v3(j.al, j.nl);
 		int nw = v3_warps(j.al);
-		// A long extension of 129..256 columns is the pole of its wave on one 8-warp CTA (240 cycles per row: eight warps at one barrier);
-		// as two concurrent column passes of four warps (181 cycles per row, linked by the carry row) it is not.  Class 10.
+		// A long extension of 129..256 columns is a pole of its wave on one 8-warp CTA (240 cycles per row: eight warps at one barrier).
+		// Two concurrent column passes of four warps (181 cycles per row each, linked by the carry row; class 10) looked like the way out
+		// and are NOT: measured on C2, the four such problems of a step take 25 ms as pass pairs against 12.4 ms on one CTA (the
+		// pass pipeline costs about twice the rows of a lone CTA, as it does for the 350-column problems that need it).  Opt-in only.
 		const bool split = g_split_long && v3 && !is_tb && nw == 8 && j.nl >= 32768 && (j.al + 7) / 8 * 8 <= 256 && (j.al + 7) / 8 * 8 > 128;
 		if (split) nw = 4;
 		j.C = v3 ? 0 : pick_C(j.al);
@@ -247,7 +249,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_
 		const int *ord = dord + g.first;
 		MPB_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
 		MPB_CUDA_OK(cudaEventRecord(ctx->ev_k0[g.sid], ss));
-		if (c >= 9) {
+		if (c == 9) {
 			nasw_launch_pair(ss, b == 1, dj, ord, cnt, ctx->b_rw.as<int4>(), d_aa, cst, ctx->b_out.as<int4>(), ctx->b_tb.as<uint16_t>());
 			ctx->stats.kernel_launches += 1;
 			MPB_CUDA_OK(cudaEventRecord(ctx->ev_km[g.sid], ss));
@@ -373,7 +375,7 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_ss, const 
 		const char *e = getenv("MPB_NASW_KERNEL");
 		const char *pw = getenv("MPB_NASW_PASS_WARPS");
 		g_pass_warps = pw && atoi(pw) == 2 ? 2 : 8;
-		if (const char *sp = getenv("MPB_NASW_SPLIT")) g_split_long = atoi(sp) != 0; else g_split_long = true;
+		if (const char *sp = getenv("MPB_NASW_SPLIT")) g_split_long = atoi(sp) != 0; else g_split_long = false;
 		g_forced_family = !e ? 0 : strcmp(e, "cols") == 0 ? 1 : strcmp(e, "v3") == 0 ? 2 : strcmp(e, "pair") == 0 ? 3 : 0;
 	}
 	NaswConst cst;

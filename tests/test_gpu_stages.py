@@ -101,10 +101,12 @@ def test_nasw_extension_wider_than_4095_columns(ctx):
         assert ol.ora_nasw(tab, nt, aa, flag, mat, _par(opt))[:3] == g[:3], (flag, len(nt), len(aa))
 
 
-def test_nasw_long_wide_extension_as_two_passes(ctx):
-    """Extensions of 129..256 columns over >= 32768 rows run as two concurrent 4-warp column passes linked by the carry row
-    (nasw_host.cu, class 10).  A protein tail that never aligns keeps the extension going over the whole window, like the
-    100 k-row end extensions of a real run."""
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_nasw_long_wide_extension(ctx, split, monkeypatch):
+    """Extensions of 129..256 columns over >= 32768 rows: on one 8-warp CTA (default) and as two concurrent 4-warp column passes
+    linked by the carry row (MPB_NASW_SPLIT=1, nasw_host.cu class 10).  A protein tail that never aligns keeps the extension going
+    over the whole window, like the 100 k-row end extensions of a real run."""
+    monkeypatch.setenv("MPB_NASW_SPLIT", split)
     rng = np.random.default_rng(99)
     opt = mp.nsopt()
     tab, mat = product_tables(), opt._mat_keepalive
