@@ -46,11 +46,15 @@ static inline bool use_v3(int al, int nl)
 // 34 ms (profiles/README.md) -- so CTAs of up to 8 warps stay the default.
 constexpr int NCLS_ = 13;
 static int g_pass_warps = 8;
+static int g_wide_warps = 4; // passes of a problem wider than 256 columns: 128 columns each (MPB_NASW_WIDE_WARPS=8: 256)
 static bool g_split_long = false; // MPB_NASW_SPLIT=1: long extensions of 129..256 columns as two 4-warp column passes (measured slower, see below)
 static inline int v3_warps(int al)
 {
 	const int nw = ((al + 7) / 8 * 8 + 31) / 32;
 	const int r = nw <= 1 ? 1 : nw <= 2 ? 2 : nw <= 4 ? 4 : 8;
+	// wider than one CTA anyway: passes of 128 columns (four warps meet at the barrier of a macro-step instead of eight; measured on
+	// 350 columns x 100 k rows: three 4-warp passes 12.5 ms, two 8-warp passes 16.6 ms, against 11.7 ms for ONE 8-warp CTA on 200 columns)
+	if (nw > 8 && g_wide_warps < 8) return g_wide_warps;
 	return r < g_pass_warps ? r : g_pass_warps;
 }
 
@@ -171,7 +175,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_
 			j.cig_cap = j.nl + j.al + 4;
 			j.cig_off = cig_tot, cig_tot += j.cig_cap;
 		}
-		if (n_pass > 1) j.carry_off = carry_tot, carry_tot += ((int64_t)j.nl + 2) * 4; // four ints per row
+		if (n_pass > 1) j.carry_off = carry_tot, carry_tot += ((int64_t)j.nl + 3 * Wp + 64) * 4; // four ints per row; slack: the feeder of a later pass reads ahead of the rows it needs, past the last row during the ramp-down
 		for (int r = 0; r < rec_rows; r += PREP_ROWS) chunks.push_back(PrepChunk{ k, r, std::min(PREP_ROWS, rec_rows - r), 0 });
 		const int cls = split ? 10 : v3 ? (nw == 1 ? 0 : nw == 2 ? 1 : nw == 4 ? 2 : 3) : n_pass > 1 ? 8 : j.C == 1 ? 4 : j.C == 2 ? 5 : j.C == 4 ? 6 : 7;
 		if (v3 && n_pass > 1) wide3[is_tb][cls] = true;
@@ -375,6 +379,7 @@ void nasw_run(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_ss, const 
 		const char *e = getenv("MPB_NASW_KERNEL");
 		const char *pw = getenv("MPB_NASW_PASS_WARPS");
 		g_pass_warps = pw && atoi(pw) == 2 ? 2 : 8;
+		{ const char *ww = getenv("MPB_NASW_WIDE_WARPS"); g_wide_warps = ww && atoi(ww) == 8 ? 8 : 4; }
 		if (const char *sp = getenv("MPB_NASW_SPLIT")) g_split_long = atoi(sp) != 0; else g_split_long = false;
 		g_forced_family = !e ? 0 : strcmp(e, "cols") == 0 ? 1 : strcmp(e, "v3") == 0 ? 2 : strcmp(e, "pair") == 0 ? 3 : 0;
 	}

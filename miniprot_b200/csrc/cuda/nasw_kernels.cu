@@ -319,7 +319,9 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 	trk.init(code_bits(job.al));
 	int tb_score = NEG;
 	for (int pass = unit_pass; pass <= unit_pass; ++pass) {
-	const bool last_pass = pass == n_pass - 1, carry_in = MP && pass > 0 && x == 0, carry_out = MP && !last_pass && x == Wp - 1;
+	// carry_out: the last column of a pass that has a successor writes its outputs to the carry row array; feeder: in a later pass, one
+	// thread off the first column's warp (lane 1 of warp 1) brings the carry rows in
+	const bool last_pass = pass == n_pass - 1, carry_out = MP && !last_pass && x == Wp - 1, feeder = MP && pass > 0 && x == 33;
 	Geo3 g;
 	g.x = x, g.col = pass * Wp + x, g.nl = job.nl, g.al = job.al, g.W8 = W8all, g.live = g.col < g.W8, g.first = g.col == 0;
 	// profile: 22 x Wp, column x of row a at smem[a * Wp + x]
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 		for (int a = 0; a < 22; ++a) smem[a * Wp + x] = rcode >= 0 ? cst.mat[a * 22 + rcode] : NEG;
 	}
 	if (x == 0) stop_flag[0] = stop_flag[1] = 0;
-	if (x < 24) xchg[x / 12][0][x % 12] = (!TB && x % 12 >= 6 && x % 12 < 9) ? INT32_MIN : NEG;
+	if (x < 24 && !(MP && pass > 0)) xchg[x / 12][0][x % 12] = (!TB && x % 12 >= 6 && x % 12 < 9) ? INT32_MIN : NEG; // (a later pass: slot 0 is fed from the carry rows)
 	__syncthreads();
 	const uint32_t xr[2] = { smem_addr(&xchg[0][warp][0]), smem_addr(&xchg[1][warp][0]) };         // what lane 0 receives from
 	const uint32_t xw[2] = { smem_addr(&xchg[0][warp + (warp < NW - 1)][0]), smem_addr(&xchg[1][warp + (warp < NW - 1)][0]) }; // what lane 31 sends to
@@ -339,19 +341,40 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 	env.rec = rec + job.rw_off * 2, env.M = v3_triples(g.nl), env.prof = smem + x, env.Wp = Wp, env.cur = env.rec;
 	Lane3<TB> L;
 	L.init(g, cst.end_bonus, par.fs, env);
-	// carry rows of the first column, fetched two macro-steps ahead: cb[T & 1][r] = row 3 T + 2 + r
-	int4 cb[2][3];
-	int prog_seen = 0; // what the first column last read from the previous pass's counter
-	auto carry_fetch = [&](int Tm, int4 *dst) {
-		if (carry_in) {
-			const int need = min(3 * Tm + 5, g.nl); // rows below `need` must have left the previous pass
-			if (prog_seen < need) {
-				while ((prog_seen = *prog_in) < need) __nanosleep(200);
-				__threadfence(); // the rows were written before the counter moved
-			}
-#pragma unroll
-			for (int r = 0; r < 3; ++r) { const int i = 3 * Tm + 2 + r; dst[r] = __ldcg(carry + (i < g.nl ? i : g.nl)); }
+	// A later pass: what its first column needs from the left -- the outputs of the previous pass's last column, three rows per
+	// macro-step -- reaches it exactly like the left neighbour's outputs reach the first lane of any other warp: through exchange slot 0,
+	// so the receive path and the steady loop are the same code as in a single-pass problem.  The feeder thread brings the carry rows
+	// in with asynchronous 16-byte copies global -> shared (a ring of 16 macro-steps), EIGHT macro-steps ahead: the rows were written by
+	// another SM a moment ago and come from the far side of L2 -- about 2000 cycles, four macro-steps; fetched into registers two or three
+	// steps ahead they set the pace of the whole pass (measured: 17 ms per 100 k rows against 8 ms for the same CTA without a carry).
+	// At step T it repacks the rows of step T + 1 from the ring into slot 0 of this step's parity, before the barrier.  Every 32 steps
+	// it makes sure the previous pass has published what the next 32 issues will read.
+	// (Predicated accesses: every thread runs them, one thread's predicate is set -- no divergence region in the steady loop.)
+	__shared__ __align__(16) int4 cring[MP ? 16 * 3 : 1];
+	const uint32_t cring_a = smem_addr(cring);
+	int prog_seen = 0; // what the feeder last read from the previous pass's counter
+	const uint32_t xs0[2] = { smem_addr(&xchg[0][0][0]), smem_addr(&xchg[1][0][0]) };
+	auto feed_wait = [&](int Tm) {
+		const int need = min(3 * Tm + 5, g.nl); // rows below `need` must have left the previous pass
+		if (prog_seen < need) {
+			while ((prog_seen = *prog_in) < need) __nanosleep(200);
+			__threadfence(); // the rows were written before the counter moved
 		}
+	};
+	const int4 *cr = carry + 2;      // feeder: first carry row of the macro-step whose rows are requested next (row 3 Tm + 2) ...
+	int cslot = 0;                   // ... and its ring slot, Tm & 15
+	int4 *cw = carry + (2 - 3 * (Wp - 1)); // last column: where its rows of macro-step T go (row 3 (T - (Wp - 1)) + 2), before the array while T < Wp - 1
+	auto feed_issue = [&]() { // past the last row the array has slack (nasw_host.cu) and the rows are masked
+#pragma unroll
+		for (int r = 0; r < 3; ++r) cp_async16_if(feeder, cring_a + (uint32_t)(cslot * 3 + r) * 16, cr + r);
+		cp_async_commit();
+		cr += 3, cslot = (cslot + 1) & 15;
+	};
+	auto feed_repack = [&](uint32_t slot, int Tm) { // ring rows (H, I, X, S) x 3 -> slot layout H[3], I[3], X[3], S[3]
+		const uint32_t a = cring_a + (uint32_t)((Tm & 15) * 3) * 16;
+		const int4 v0 = lds128(a), v1 = lds128(a + 16), v2 = lds128(a + 32);
+		sts128_if(feeder, slot, make_int4(v0.x, v1.x, v2.x, v0.y)), sts128_if(feeder, slot + 16, make_int4(v1.y, v2.y, v0.z, v1.z));
+		sts128_if(feeder, slot + 32, make_int4(v2.z, v0.w, v1.w, v2.w));
 	};
 	// the last column of a pass that has a successor: every 32nd macro-step (and at the end) it publishes the number of finished rows
 	// (the fence is not free, and a lag of a hundred rows is nothing against the tens of thousands of a long problem)
@@ -359,7 +382,13 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 		__threadfence();
 		*prog_out = rows_done;
 	};
-	if (MP) carry_fetch(0, cb[0]), carry_fetch(1, cb[1]);
+	if (MP) {
+		if (feeder) feed_wait(41);
+		for (int k = 0; k < 8; ++k) feed_issue(); // macro-steps 0..7
+		cp_async_wait<0>();
+		feed_repack(xs0[1], 0); // macro-step 0 reads the slot of parity 1
+		__syncthreads();
+	}
 	const int n_macro = g.nl > 2 ? (g.nl - 2 + 2) / 3 + Wp : 0; // rows 2..nl-1 in triples, plus the skew of the last column
 	uint16_t *tbp = TB ? tb + job.tb_off + (int64_t)pass * (3 * (n_macro + 2)) * Wp + x : 0;
 	// (T is even at every loop head, so the parity of macro-step T + PH is PH: all exchange slots are static)
@@ -369,19 +398,19 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 			RH[r] = __shfl_up_sync(0xffffffffu, L.oH[r], 1), rI[r] = __shfl_up_sync(0xffffffffu, L.oI[r], 1), rX[r] = __shfl_up_sync(0xffffffffu, L.oX[r], 1); \
 			rS[r] = TB ? __shfl_up_sync(0xffffffffu, L.oS[r], 1) : 0; \
 		} \
-		if (lane == 0) { /* the column to my left lives in the previous warp; slot 0 holds the constant left boundary */ \
+		if (lane == 0) { /* the column to my left lives in the previous warp; slot 0: the constant left boundary, or the previous pass's last column */ \
 			const int4 b0 = lds128(xr[PH ^ 1]), b1 = lds128(xr[PH ^ 1] + 16), b2 = lds128(xr[PH ^ 1] + 32); \
 			RH[0] = b0.x, RH[1] = b0.y, RH[2] = b0.z, rI[0] = b0.w, rI[1] = b1.x, rI[2] = b1.y, rX[0] = b1.z, rX[1] = b1.w, rX[2] = b2.x; \
 			if (TB) rS[0] = b2.y, rS[1] = b2.z, rS[2] = b2.w; \
-		} \
-		if (MP) { /* first column of a later pass: the column to its left was the last column of the previous pass */ \
-			if (carry_in) { \
-				_Pragma("unroll") for (int r = 0; r < 3; ++r) { RH[r] = cb[PH][r].x, rI[r] = cb[PH][r].y, rX[r] = cb[PH][r].z; if (TB) rS[r] = cb[PH][r].w; } \
-			} \
-			carry_fetch(T + PH + 2, cb[PH]); \
 		}
 #define NSW_V3_SEND(PH) \
 		if (NW > 1) { \
+			if (MP) { /* carry rows of the next macro-step into slot 0, those of the step after the next two on their way */ \
+				if (((T + PH) & 31) == 0 && feeder) feed_wait(T + PH + 41); \
+				feed_issue(); /* macro-step T + PH + 8 */ \
+				cp_async_wait<6>(); /* everything up to macro-step T + PH + 2 has landed */ \
+				feed_repack(xs0[PH], T + PH + 1); \
+			} \
 			if (lane == 31 && warp < NW - 1) { \
 				sts128(xw[PH], make_int4(L.oH[0], L.oH[1], L.oH[2], L.oI[0])), sts128(xw[PH] + 16, make_int4(L.oI[1], L.oI[2], L.oX[0], L.oX[1])); \
 				sts128(xw[PH] + 32, make_int4(L.oX[2], TB ? L.oS[0] : 0, TB ? L.oS[1] : 0, TB ? L.oS[2] : 0)); \
@@ -395,10 +424,10 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 		uint32_t wd[3]; \
 		const uint32_t done = L.template macro<PH>(g, par, T + PH, rH, rI, rX, rS, env, wd); \
 		if (TB) { _Pragma("unroll") for (int r = 0; r < 3; ++r) if (done >> r & 1) tbp[(int64_t)(3 * (T + PH) + r) * Wp] = (uint16_t)wd[r]; } \
-		if (MP && carry_out) { \
-			_Pragma("unroll") for (int r = 0; r < 3; ++r) if (done >> r & 1) \
-				carry[Lane3<TB>::row_of(g, T + PH, r)] = make_int4(L.oH[r], L.oI[r], L.oX[r], TB ? L.oS[r] : 0); \
-			if (done) carry_publish(min(Lane3<TB>::row_of(g, T + PH, 0) + 3, g.nl)); \
+		if (MP) { \
+			_Pragma("unroll") for (int r = 0; r < 3; ++r) stg128_if(carry_out && (done >> r & 1), cw + r, make_int4(L.oH[r], L.oI[r], L.oX[r], TB ? L.oS[r] : 0)); \
+			cw += 3; \
+			if (carry_out && done) carry_publish(min(Lane3<TB>::row_of(g, T + PH, 0) + 3, g.nl)); \
 		} \
 		if (!TB && warp == NW - 1 && last_pass) { /* the last column sees the complete row maxima; its rows are real when 2 <= i < nl */ \
 			(void)done; \
@@ -413,9 +442,10 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 		uint32_t wd[3]; \
 		L.template macro_steady<PH>(g, par, hb[PH ^ 1], hb[PH], rI, rX, rS, env, wd); \
 		if (TB) { if (g.live) { _Pragma("unroll") for (int r = 0; r < 3; ++r) tbs[r * Wp] = (uint16_t)wd[r]; } tbs += 3 * Wp; } \
-		if (MP && carry_out) { \
-			_Pragma("unroll") for (int r = 0; r < 3; ++r) carry[Lane3<TB>::row_of(g, T + PH, r)] = make_int4(L.oH[r], L.oI[r], L.oX[r], TB ? L.oS[r] : 0); \
-			if (((T + PH) & 31) == 31) carry_publish(Lane3<TB>::row_of(g, T + PH, 0) + 3); \
+		if (MP) { \
+			_Pragma("unroll") for (int r = 0; r < 3; ++r) stg128_if(carry_out, cw + r, make_int4(L.oH[r], L.oI[r], L.oX[r], TB ? L.oS[r] : 0)); \
+			cw += 3; \
+			if (((T + PH) & 127) == 127 && carry_out) carry_publish(Lane3<TB>::row_of(g, T + PH, 0) + 3); /* the fence waits for the stores to reach L2: rarely */ \
 		} \
 		if (!TB && warp == NW - 1 && last_pass) { \
 			_Pragma("unroll") for (int r = 0; r < 3; ++r) sts32(ring_w + (trk.n_ring + r) * 128, L.oX[r]); \
@@ -609,7 +639,10 @@ void nasw_launch_v3(cudaStream_t st, int nw, bool is_tb, const DpDev *jobs, cons
 		if (multi) launch_v3<4, false, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry, units, progress);
 		else launch_v3<4, false, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
 		break;
-	case 9: launch_v3<4, true, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry); break;
+	case 9:
+		if (multi) launch_v3<4, true, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry, units, progress);
+		else launch_v3<4, true, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);
+		break;
 	case 16:
 		if (multi) launch_v3<8, false, true>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry, units, progress);
 		else launch_v3<8, false, false>(st, jobs, order, n, rec, aa, cst, out, tb, warps_per_sm, carry);

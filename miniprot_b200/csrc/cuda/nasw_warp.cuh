@@ -28,6 +28,29 @@ __device__ __forceinline__ int4 lds128(uint32_t a)
 	return v;
 }
 
+// Predicated 16-byte accesses: one thread of a block has something to do, nobody branches (a branch that one lane takes costs the
+// whole warp a divergence region on the critical path of every macro-step; the column passes of a wide problem use these).
+__device__ __forceinline__ void stg128_if(bool p, const void *a, int4 v)
+{
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q st.global.v4.b32 [%1], {%2, %3, %4, %5};\n\t}" :: "r"((int)p), "l"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void ldcg128_if(bool p, const void *a, int4 &v) // v keeps its value when p is false
+{
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %4, 0;\n\t@q ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%5];\n\t}" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "r"((int)p), "l"(a));
+}
+__device__ __forceinline__ void sts128_if(bool p, uint32_t a, int4 v)
+{
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q st.shared.v4.b32 [%1], {%2, %3, %4, %5};\n\t}" :: "r"((int)p), "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 16 bytes global -> shared, asynchronously (LDGSTS through L2), predicated; groups are committed and awaited per thread
+__device__ __forceinline__ void cp_async16_if(bool p, uint32_t smem, const void *g)
+{
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q cp.async.cg.shared.global [%1], [%2], 16;\n\t}" :: "r"((int)p), "r"(smem), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 // Extension bookkeeping of the block-wide kernel, 30 rows at a time.  ExtTracker::row (nasw_core.cuh) is the specification: a
 // running maximum of (row best - length penalty) with first-occurrence ties, and a stop at the first row that falls more than
 // xdrop below it.  Fed row by row it costs the warp that owns the last column ~15 divergent instructions per row on the
