@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 		sts128_if(feeder, slot, make_int4(v0.x, v1.x, v2.x, v0.y)), sts128_if(feeder, slot + 16, make_int4(v1.y, v2.y, v0.z, v1.z));
 		sts128_if(feeder, slot + 32, make_int4(v2.z, v0.w, v1.w, v2.w));
 	};
-	// the last column of a pass that has a successor: every 32nd macro-step (and at the end) it publishes the number of finished rows
+	// the last column of a pass that has a successor: every 128th macro-step (and at the end) it publishes the number of finished rows
 	// (the fence is not free, and a lag of a hundred rows is nothing against the tens of thousands of a long problem)
 	auto carry_publish = [&](int rows_done) {
 		__threadfence();
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(NW * 32) nasw_v3_kernel(const DpDev *jobs, con
 		if (MP) { \
 			_Pragma("unroll") for (int r = 0; r < 3; ++r) stg128_if(carry_out && (done >> r & 1), cw + r, make_int4(L.oH[r], L.oI[r], L.oX[r], TB ? L.oS[r] : 0)); \
 			cw += 3; \
-			if (carry_out && done) carry_publish(min(Lane3<TB>::row_of(g, T + PH, 0) + 3, g.nl)); \
+			if (carry_out && done && ((T + PH) & 7) == 7) carry_publish(min(Lane3<TB>::row_of(g, T + PH, 0) + 3, g.nl)); /* ramps: every 8th step */ \
 		} \
 		if (!TB && warp == NW - 1 && last_pass) { /* the last column sees the complete row maxima; its rows are real when 2 <= i < nl */ \
 			(void)done; \
