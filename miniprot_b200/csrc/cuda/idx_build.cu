@@ -242,6 +242,8 @@ int idx_build_device(mpb_ctx_s *c, mp_idx_t *mi)
 	if (n_kb) MPB_CUDA_OK(cudaMemcpyAsync(mi->kb, c->own_kb.p, sizeof(uint32_t) * (size_t)n_kb, cudaMemcpyDeviceToHost, st));
 	MPB_CUDA_OK(cudaStreamSynchronize(st));
 	c->stats.h2d_bytes += (int64_t)seq_bytes, c->stats.d2h_bytes += (int64_t)(sizeof(int64_t) * n_bucket + sizeof(uint32_t) * (size_t)n_kb);
+	// the build's scratch (24 B per pair: 45 GB for a 3 Gbp genome) is not an arena of the mapping stages: give it back
+	for (int k : { 2, 4, 5, 6, 7 }) c->b_c[k].release();
 	return 0;
 }
 
