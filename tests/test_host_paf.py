@@ -62,3 +62,30 @@ def test_other_output_formats_golden(hc, tmp_path, fmt, monkeypatch):
     if os.path.exists(os.path.join(DATA, "DPP3-hs.gen.fa.gz")):
         got = run(hc, os.path.join(DATA, "DPP3-hs.gen.fa.gz"), os.path.join(DATA, "DPP3-mm.pep.fa.gz"), str(tmp_path / "d.txt"), flag=flag)
         assert got == open(os.path.join(GOLD, f"DPP3_{fmt}.txt"), "rb").read()
+
+
+@pytest.mark.parametrize("extra", [0, 1, 2, 3, 4])
+def test_hit_abutting_the_contig_end(hc, tmp_path, extra, capfd):
+    """A gene whose coding sequence stops `extra` bases before the contig end while the protein goes on: with fewer than 3 bases left
+    there is nothing to extend into (the reference stops at an assertion there, nasw-sse.c:443); the hit must simply end at its last
+    pinned anchor -- no right extension planned, no `inconsistent CIGAR` drop (align.cpp plan(): has_right)."""
+    import numpy as np
+
+    rng = np.random.default_rng(17 + extra)
+    aa2cod = {}
+    std = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
+    for i, a in enumerate(std):
+        aa2cod.setdefault(a, []).append("TCAG"[i >> 4] + "TCAG"[(i >> 2) & 3] + "TCAG"[i & 3])
+    prot = "".join("ARNDCQEGHILKMFPSTWYV"[x] for x in rng.integers(0, 20, 160))
+    cds = "".join(aa2cod[a][int(rng.integers(0, len(aa2cod[a])))] for a in prot[:120])  # the genome encodes residues 0..119 only
+    ctg = "".join("ACGT"[x] for x in rng.integers(0, 4, 5000)) + cds + "".join("ACGT"[x] for x in rng.integers(0, 4, extra))
+    g, p = str(tmp_path / "g.fa"), str(tmp_path / "p.faa")
+    open(g, "w").write(">ctg\n" + ctg + "\n")
+    open(p, "w").write(">prot\n" + prot + "\n")
+    paf = run(hc, g, p, str(tmp_path / "o.paf")).decode()
+    err = capfd.readouterr().err
+    assert "inconsistent CIGAR" not in err, err
+    rows = [l.split("\t") for l in paf.splitlines()]
+    assert len(rows) >= 1 and rows[0][0] == "prot" and rows[0][5] == "ctg"
+    assert int(rows[0][8]) <= len(ctg) and int(rows[0][8]) >= len(ctg) - extra - 30  # the hit reaches the end of the coding sequence
+    assert int(rows[0][3]) >= 110 and int(rows[0][3]) <= 121                         # ... and covers the encoded residues only
