@@ -15,6 +15,10 @@
 #include <stdio.h>
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include "internal.hpp"
 #include "align.hpp"
 #include "fastx.hpp"
@@ -240,39 +244,129 @@ static void write_batch(FILE *out, const mp_idx_t *mi, const mp_mapopt_t *opt, c
 	}
 }
 
+// One mini-batch of the query file with everything that must live from the reader to the writer.
+struct FileBatch {
+	std::vector<std::string> names, seqs;
+	std::vector<const char*> sp, np;
+	std::vector<int32_t> len, n_reg;
+	std::vector<mp_reg1_t*> reg;
+	Batch view() const
+	{
+		Batch b;
+		b.n = (int32_t)seqs.size(), b.seq = sp.data(), b.len = len.data(), b.name = np.data();
+		return b;
+	}
+	void release() // hits are libc-allocated like the reference's (map.c:314-318)
+	{
+		for (size_t i = 0; i < reg.size(); ++i) {
+			for (int32_t j = 0; j < n_reg[i]; ++j) free(reg[i][j].feat), free(reg[i][j].p);
+			free(reg[i]);
+		}
+		reg.clear();
+	}
+};
+
+// bseq.c:53-74: records until the batch holds mini_batch_size residues; null at the end of the input
+static std::unique_ptr<FileBatch> read_batch(FastxReader &rd, int64_t mini_batch_size, bool &more)
+{
+	std::unique_ptr<FileBatch> fb(new FileBatch);
+	std::string name, seq;
+	int64_t residues = 0;
+	while (residues < mini_batch_size && (more = rd.next(name, seq))) {
+		residues += (int64_t)seq.size();
+		fb->names.push_back(name), fb->seqs.push_back(seq);
+	}
+	if (fb->seqs.empty()) return nullptr;
+	const size_t n = fb->seqs.size();
+	fb->sp.resize(n), fb->np.resize(n), fb->len.resize(n), fb->n_reg.assign(n, 0), fb->reg.assign(n, (mp_reg1_t*)0);
+	for (size_t i = 0; i < n; ++i) fb->sp[i] = fb->seqs[i].c_str(), fb->np[i] = fb->names[i].c_str(), fb->len[i] = (int32_t)fb->seqs[i].size();
+	return fb;
+}
+
+// A one-slot hand-over between two steps of the file pipeline: put() waits while the slot is taken, take() returns null once
+// the producer has closed an empty slot.
+class Handoff {
+public:
+	void put(std::unique_ptr<FileBatch> fb)
+	{
+		std::unique_lock<std::mutex> lk(mu_);
+		cv_.wait(lk, [&] { return !slot_; });
+		slot_ = std::move(fb);
+		cv_.notify_all();
+	}
+	void close()
+	{
+		std::lock_guard<std::mutex> lk(mu_);
+		closed_ = true;
+		cv_.notify_all();
+	}
+	std::unique_ptr<FileBatch> take()
+	{
+		std::unique_lock<std::mutex> lk(mu_);
+		cv_.wait(lk, [&] { return slot_ || closed_; });
+		std::unique_ptr<FileBatch> fb = std::move(slot_);
+		cv_.notify_all();
+		return fb;
+	}
+
+private:
+	std::mutex mu_;
+	std::condition_variable cv_;
+	std::unique_ptr<FileBatch> slot_;
+	bool closed_ = false;
+};
+
+// map.c:273-343 (worker_pipeline under kt_pipeline with three steps): step 0 reads and parses the next mini-batch, step 1 maps
+// it (the GPU batch dispatcher above), step 2 formats and writes the hits -- in the order of the input, by one thread, which
+// also owns the hit counter.  As in the reference, step 0 of batch n+1 and step 2 of batch n-1 run while batch n is mapped:
+// one reader thread, the calling thread as the mapper (it owns the device), one writer thread, a one-slot hand-over between
+// neighbours.  MPB_FILE_PIPELINE=0 runs the three steps one after another on the calling thread (A/B, debugging).
 int32_t map_file(Stages *st, const mp_idx_t *mi, const char *fn, const mp_mapopt_t *opt, FILE *out)
 {
 	FastxReader rd(fn);
 	if (!rd.fp) return -1;
-	std::vector<std::string> names, seqs;
-	std::string name, seq;
-	bool more = true;
-	int64_t n_done = 0, id_counter = 0;
+	int64_t id_counter = 0;
 	if (opt->flag & MP_F_GFF) fputs("##gff-version 3\n", out); // map.c:338
-	while (more) {
-		int64_t residues = 0;
-		names.clear(), seqs.clear();
-		while (residues < opt->mini_batch_size && (more = rd.next(name, seq))) { // bseq.c:53-74
-			names.push_back(name), seqs.push_back(seq);
-			residues += (int64_t)seq.size();
+	auto map_step = [&](FileBatch &fb) {
+		map_batch(st, mi, opt, fb.view(), fb.n_reg.data(), fb.reg.data());
+		if (mp_verbose >= 3)
+			fprintf(stderr, "[M::%s::%.3f*%.2f] mapped %d sequences\n", "map_file", mp_realtime(), mp_cputime() / mp_realtime(), (int)fb.seqs.size());
+	};
+	auto write_step = [&](FileBatch &fb) {
+		write_batch(out, mi, opt, fb.view(), fb.n_reg.data(), fb.reg.data(), &id_counter);
+		fb.release();
+	};
+	const char *e = getenv("MPB_FILE_PIPELINE");
+	if (e && atoi(e) == 0) {
+		bool more = true;
+		while (more) {
+			std::unique_ptr<FileBatch> fb = read_batch(rd, opt->mini_batch_size, more);
+			if (!fb) break;
+			map_step(*fb);
+			write_step(*fb);
 		}
-		if (seqs.empty()) break;
-		const int32_t n = (int32_t)seqs.size();
-		std::vector<const char*> sp((size_t)n), np((size_t)n);
-		std::vector<int32_t> len((size_t)n), n_reg((size_t)n);
-		std::vector<mp_reg1_t*> reg((size_t)n);
-		for (int32_t i = 0; i < n; ++i) sp[(size_t)i] = seqs[(size_t)i].c_str(), np[(size_t)i] = names[(size_t)i].c_str(), len[(size_t)i] = (int32_t)seqs[(size_t)i].size();
-		Batch b;
-		b.n = n, b.seq = sp.data(), b.len = len.data(), b.name = np.data();
-		map_batch(st, mi, opt, b, n_reg.data(), reg.data());
-		write_batch(out, mi, opt, b, n_reg.data(), reg.data(), &id_counter);
-		for (int32_t i = 0; i < n; ++i) {
-			for (int32_t j = 0; j < n_reg[(size_t)i]; ++j) free(reg[(size_t)i][j].feat), free(reg[(size_t)i][j].p);
-			free(reg[(size_t)i]);
-		}
-		n_done += n;
-		if (mp_verbose >= 3) fprintf(stderr, "[M::%s::%.3f*%.2f] mapped %d sequences\n", __func__, mp_realtime(), mp_cputime() / mp_realtime(), n);
+		return 0;
 	}
+	Handoff to_map, to_write;
+	std::thread reader([&] {
+		bool more = true;
+		while (more) {
+			std::unique_ptr<FileBatch> fb = read_batch(rd, opt->mini_batch_size, more);
+			if (!fb) break;
+			to_map.put(std::move(fb));
+		}
+		to_map.close();
+	});
+	std::thread writer([&] {
+		while (std::unique_ptr<FileBatch> fb = to_write.take()) write_step(*fb);
+	});
+	while (std::unique_ptr<FileBatch> fb = to_map.take()) {
+		map_step(*fb);
+		to_write.put(std::move(fb));
+	}
+	to_write.close();
+	reader.join();
+	writer.join();
 	return 0;
 }
 

@@ -34,12 +34,18 @@ def test_dpp3_golden(hc, tmp_path, name, kw):
 
 
 @pytest.mark.parametrize("cfg", ["tiny", "tiny5"])
-def test_synthetic_golden(hc, tmp_path, cfg):
+def test_synthetic_golden(hc, tmp_path, cfg, monkeypatch):
     g, p = synth.generate(synth.CONFIGS[cfg], str(tmp_path))
     want = open(os.path.join(GOLD, cfg + ".paf"), "rb").read()
     assert run(hc, g, p, str(tmp_path / "o.paf")) == want
     # batch boundaries must not matter (SURVEY 8b determinism contract): 3 proteins per mini-batch
     assert run(hc, g, p, str(tmp_path / "o2.paf"), mini_batch=1200) == want
+    # ... nor whether the three steps of the file driver (read / map / write, map.c:273-343) overlap or run one after another
+    monkeypatch.setenv("MPB_FILE_PIPELINE", "0")
+    assert run(hc, g, p, str(tmp_path / "o3.paf"), mini_batch=1200) == want
+    assert run(hc, g, p, str(tmp_path / "o4.paf"), mini_batch=1) == want  # one protein per mini-batch
+    monkeypatch.delenv("MPB_FILE_PIPELINE")
+    assert run(hc, g, p, str(tmp_path / "o5.paf"), mini_batch=1) == want
 
 
 FORMATS = {"gff": (0x8, None), "gtf": (0x20, None), "aln": (0x80, None), "trans": (0x100 | 0x4, None), "gff_only": (0x8 | 0x10, "#")}
