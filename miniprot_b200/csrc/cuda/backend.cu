@@ -147,9 +147,19 @@ struct CudaStages : Stages {
 	}
 };
 
-// nasw-sse.c:426 is served from a step table; refuse (loudly) a coefficient whose steps do not fit it
-bool bad_ie_coef(float ie_coef)
+// Scoring parameters the kernels cannot reproduce bit for bit are refused (loudly) instead of mapped approximately:
+//  * gap open 0 (-O 0).  The reference's lazy-F loop ends when "I - ge <= max(H, I) - go - ge" holds in every SIMD lane
+//    (nasw-sse.c:411, :530).  With go > 0 that is only true where the insertion did not raise H, so stopping loses nothing and
+//    the result is the textbook recurrence, which is what the kernels compute.  With go == 0 it is true at once: only the
+//    first column of each of the eight stripe segments ever sees the insertion carried over from the segment before, and the
+//    scores depend on the SSE layout (found by tools/fuzz_emu.py: reference and recurrence differ on ~1 % of random problems).
+//  * nasw-sse.c:426 is served from a step table; a coefficient whose steps do not fit it.
+bool bad_scoring(int go, float ie_coef)
 {
+	if (go < 1) {
+		fprintf(stderr, "[miniprot_b200] gap open penalty %d: values below 1 are not supported (with -O 0 the reference's result depends on its SIMD stripe layout)\n", go);
+		return true;
+	}
 	if (nasw_check_ie_coef(ie_coef) == 0) return false;
 	fprintf(stderr, "[miniprot_b200] ie_coef = %g: the extension length penalty has more than %d steps and is not supported\n", (double)ie_coef, nsw::PEN_STEPS);
 	return true;
@@ -424,7 +434,7 @@ int mpb_map_batch(mpb_ctx_t *c, const mp_idx_t *mi, const mp_mapopt_t *opt, int3
                   const char *const *names, int32_t *n_reg_out, mp_reg1_t **reg_out)
 {
 	if (!c) return -1;
-	if (bad_ie_coef(opt->ie_coef)) return -3;
+	if (bad_scoring(opt->go, opt->ie_coef)) return -3;
 	MPB_CUDA_OK(cudaSetDevice(c->device));
 	Batch b;
 	b.n = n_seq, b.seq = seqs, b.len = lens, b.name = names;
@@ -435,7 +445,7 @@ int mpb_map_batch(mpb_ctx_t *c, const mp_idx_t *mi, const mp_mapopt_t *opt, int3
 int32_t mpb_map_file(mpb_ctx_t *c, const mp_idx_t *mi, const char *fn, const mp_mapopt_t *opt, FILE *out)
 {
 	if (!c) return -1;
-	if (bad_ie_coef(opt->ie_coef)) return -3;
+	if (bad_scoring(opt->go, opt->ie_coef)) return -3;
 	MPB_CUDA_OK(cudaSetDevice(c->device));
 	return map_file(c->stages, mi, fn, opt, out);
 }
@@ -476,7 +486,7 @@ int64_t mpb_format_paf(const mp_idx_t *mi, const mp_mapopt_t *opt, const char *q
 int mpb_nasw_batch(mpb_ctx_t *c, const ns_opt_t *opt, int32_t n, const mpb_dp_problem_t *prob, mpb_dp_result_t *rst)
 {
 	if (!c) return -1;
-	if (bad_ie_coef(opt->ie_coef)) return -3;
+	if (bad_scoring(opt->go, opt->ie_coef)) return -3;
 	MPB_CUDA_OK(cudaSetDevice(c->device));
 	// pack the host sequences the way the genome is stored, so that the same kernels serve both paths
 	int64_t nt_tot = 0, aa_tot = 0;

@@ -60,25 +60,13 @@ static inline int v3_warps(int al)
 
 // Pair-lane kernels (nasw_pair.cuh: two columns per thread as packed int16x2) serve every problem whose scores provably stay
 // inside their value domain and whose padded width fits 8 warps; MPB_NASW_KERNEL=v3|cols keeps them out (A/B measurements).
-struct PairLimits { int smin, smax, dmax, amax; };
-static PairLimits pair_limits(const ns_opt_t *o)
-{
-	PairLimits l;
-	l.smin = 127, l.smax = -128;
-	for (int a = 0; a < 22; ++a)
-		for (int b = 0; b < 22; ++b) { const int v = o->sc[a * 22 + b]; l.smin = std::min(l.smin, v), l.smax = std::max(l.smax, v); }
-	l.dmax = std::max({ o->sp[0], o->sp[1], o->sp[2], o->sp[3], o->sp[4], 0 });            // nasw-sse.c:120-127
-	l.amax = std::max({ o->sp[0] + 3 * std::max(o->sp[5], 0), o->sp[2], o->sp[3], 0 });   // nasw-sse.c:128-137
-	int dmin = std::min({ o->sp[0], o->sp[1], o->sp[2], o->sp[3], o->sp[4], o->sp[5] });
-	if (dmin < 0) l.dmax = 1 << 20; // negative splice penalties: not a case the value-domain argument covers
-	return l;
-}
+static nsw::PairLimits pair_limits(const ns_opt_t *o) { return nsw::pair_limits(o->sc, o->sp); }
 // Which problems they serve by default is a measured choice (profiles/README.md; tools/dp_bench.py and bench.py A/B on B200): global
 // alignments of up to 64 padded columns, where one warp of the pair-lane kernel replaces one or two warps of the block-wide kernel at
 // 1.25-1.4x its speed.  Score-only extensions stay on the block-wide kernels: there the pair-lane form needs 172-189 cycles per row
 // against 137 (<= 32 columns) / 152 (33..64 columns, two warps) -- its 64 columns per warp do not pay for the 32-bit row-maximum
 // bookkeeping that an extension carries per cell.  MPB_NASW_KERNEL=pair sends every problem of up to 64 columns to them (tests, A/B).
-static inline bool use_pair(const DpDev &j, const ns_opt_t *o, const PairLimits &l)
+static inline bool use_pair(const DpDev &j, const ns_opt_t *o, const nsw::PairLimits &l)
 {
 	if (g_forced_family == 1 || g_forced_family == 2) return false;
 	const int W8 = (j.al + 7) / 8 * 8;
@@ -124,7 +112,7 @@ static void run_subwave(mpb_ctx_s *ctx, const uint8_t *packed, const uint8_t *d_
 	std::vector<PrepChunk> chunks, pchunks; // row-record chunks of the 32-bit families, pair-record chunks of the pair-lane family
 	bool wide3[2][NCLS_] = { { false } }; // does a block-wide class hold problems of more than one pass?
 	std::vector<int> unsupported;
-	const PairLimits plim = pair_limits(nso);
+	const nsw::PairLimits plim = pair_limits(nso);
 	constexpr int NCLS = NCLS_;
 	std::vector<int> order[2][NCLS]; // [is_tb][class]: 0..3 block-wide wavefront with 1/2/4/8 warps; 4..7 column passes C = 1/2/4/8; 8 multi-pass; 9 pair-lane kernels (one warp per problem)
 	for (int k = 0; k < n; ++k) {

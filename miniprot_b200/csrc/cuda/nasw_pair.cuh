@@ -111,6 +111,22 @@ inline bool pair_eligible(int al, int go, int ge, int io, int fs, int end_bonus,
 	return junk_hi < legit_lo && legit_hi < 32767 - PAIR_BIAS;
 }
 
+// The extremes pair_eligible() wants, from the scoring matrix (22 x 22) and the six splice-model penalties as the kernels see them.
+struct PairLimits { int smin, smax, dmax, amax; };
+inline PairLimits pair_limits(const int8_t *mat, const int32_t *sp)
+{
+	PairLimits l;
+	l.smin = 127, l.smax = -128;
+	for (int k = 0; k < 484; ++k) l.smin = mat[k] < l.smin ? mat[k] : l.smin, l.smax = mat[k] > l.smax ? mat[k] : l.smax;
+	auto mx = [](int a, int b) { return a > b ? a : b; };
+	l.dmax = mx(mx(mx(sp[0], sp[1]), mx(sp[2], sp[3])), mx(sp[4], 0));          // nasw-sse.c:120-127
+	l.amax = mx(mx(sp[0] + 3 * mx(sp[5], 0), sp[2]), mx(sp[3], 0));              // nasw-sse.c:128-137
+	int dmin = sp[0];
+	for (int k = 1; k < 6; ++k) dmin = sp[k] < dmin ? sp[k] : dmin;
+	if (dmin < 0) l.dmax = 1 << 20; // negative splice penalties: not a case the value-domain argument covers
+	return l;
+}
+
 // ---- row records -------------------------------------------------------------------------------------------------------------
 // One record per TRIPLE of rows m (rows i0 = 3m+2 .. i0+2), holding what a thread needs at the macro-step in which its low half
 // is on triple m and its high half on triple m-1: every entry is a pair (low half: row of triple m, high half: the row three

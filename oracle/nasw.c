@@ -10,7 +10,12 @@
  *   - the first pass restarts the insertion chain at each of the 8 segment starts
  *     (column % slen == 0), which decides the state nibble and bit 4 of the traceback word;
  *   - the lazy-F loop (nasw-sse.c:408-422 / 521-537) is equivalent to one left-to-right pass
- *     over logical columns that raises H and sets bit 9.
+ *     over logical columns that raises H and sets bit 9.  PRECONDITION: gap
+ *     open go >= 1.  The loop stops when "I - ge <= max(H, I) - go - ge" holds in all lanes; with
+ *     go > 0 that is only true where I did not raise H, so the stop loses nothing.  With go == 0
+ *     it is true at once and the reference's scores depend on the stripe layout (only the first
+ *     column of each segment sees the carried-over insertion): not restated here, refused by the
+ *     product (backend.cu bad_scoring); tests/test_oracle_pin.py pins both facts.
  * Cell recurrences: nasw-sse.c:15-22.  Backtrack: nasw-sse.c:40-89.  Sequence preparation:
  * nasw-sse.c:91-210.  Extension bookkeeping: nasw-sse.c:423-443.
  */

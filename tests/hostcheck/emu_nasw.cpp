@@ -509,3 +509,11 @@ extern "C" int emu_pen_check(float ie_coef, int xmax)
 	}
 	return bad;
 }
+
+// would the dispatcher send this problem to the pair-lane kernels? (nasw_host.cu use_pair: value-domain check + width; no --spsc)
+extern "C" int emu_pair_eligible(const int8_t *mat, const int32_t *sp, int go, int ge, int io, int fs, int end_bonus, int nl, int al)
+{
+	const PairLimits l = pair_limits(mat, sp);
+	if ((al + 7) / 8 * 8 > PAIR_MAX_W8 || nl < 3) return 0;
+	return pair_eligible(al, go, ge, io, fs, end_bonus, l.smin, l.smax, l.dmax, l.amax) ? 1 : 0;
+}

@@ -158,3 +158,17 @@ def test_emu_with_splice_scores_matches_reference(hc, Ccols):
                 assert a[0] == b[0] == o[0] and a[3] == b[3] == o[3], (it, flag, len(nt), len(aa), a, b)
             else:
                 assert a[:3] == b[:3] == o[:3], (it, flag, len(nt), len(aa), a[:3], b[:3])
+
+
+def test_emu_random_scoring_parameters():
+    """Random problems x random scoring parameters (-O >= 1, -E, -J, -F, -B, -C, splice models, x-drop, ie_coef, --spsc bytes)
+    through every kernel family -- the pair-lane family where the dispatcher's value-domain check admits the problem -- against
+    the reference's ns_global_gs16b and the oracle.  A fixed-seed slice of tools/fuzz_emu.py (which runs open-ended)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_emu
+
+    n_cmp, n_pair, n_bad = fuzz_emu.fuzz(20260924, 80)
+    assert n_bad == 0 and n_cmp > 400 and n_pair > 50

@@ -306,3 +306,40 @@ def test_segmented_sort(ctx):
     L.mpb_sort_segments.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     assert L.mpb_sort_segments(ctx.h, len(sizes), off.ctypes.data, keys.ctypes.data) == 0
     assert (keys == want).all()
+
+
+def test_nasw_batch_random_scoring_parameters(ctx):
+    """Ten batches, each with its own random scoring parameters (-O >= 1, -E, -J, -F, -B, splice penalties, x-drop, ie_coef) and
+    stop-codon score: every kernel family the dispatcher picks (incl. the pair-lane kernels where the value-domain check admits
+    the problem) against the oracle.  The CPU twin of this test is tests/test_emu_nasw.py::test_emu_random_scoring_parameters."""
+    rng = np.random.default_rng(31337)
+    tab = product_tables()
+    for batch in range(10):
+        over = dict(go=int(rng.integers(1, 31)), ge=int(rng.integers(0, 6)), io=int(rng.integers(3, 61)), fs=int(rng.integers(1, 61)),
+                    end_bonus=int(rng.integers(0, 21)), xdrop=int(rng.choice([5, 30, 100, 400])), ie_coef=float(rng.choice([0.0, 0.25, 0.5, 1.0, 2.5])))
+        if batch % 2:
+            over["sp"] = tuple(int(x) for x in rng.integers(0, 40, size=4)) + (int(rng.integers(0, 8)), int(rng.integers(0, 8)))
+        opt = mp.nsopt(**over)
+        mat = opt._mat_keepalive
+        if batch % 3 == 0:
+            mp.lib().ns_set_stop_sc(22, mat.ctypes.data_as(C.c_void_p), int(rng.integers(1, 60)))
+        probs = []
+        for it in range(120):
+            nt, aa = ol.random_dp_problem(rng, al_max=(12, 64, 140, 300)[it % 4], flank=(0, 3, 60)[it % 3], intron_max=(0, 60, 400)[it % 3],
+                                          p_sub=(0.05, 0.2, 0.5)[it % 3])
+            if len(nt) >= 3:
+                probs.append((nt, aa, (1, 4, 2)[it % 3], opt.io))
+        got = mp.nasw_batch(ctx, opt, probs)
+        par = _par(opt)
+        for (nt, aa, flag, io), g in zip(probs, got):
+            w = ol.ora_nasw(tab, nt, aa, flag, mat, par)
+            assert (w[0] == g[0] and w[3] == g[3]) if flag == 1 else (w[:3] == g[:3]), (batch, over, flag, len(nt), len(aa), w[:3], g[:3])
+
+
+def test_unsupported_scoring_is_refused(ctx):
+    """Gap open 0 (the reference's result then depends on its SSE stripe layout, backend.cu bad_scoring) and an ie_coef beyond the
+    penalty table are refused with -3 instead of being mapped approximately."""
+    nt, aa = ol.random_dp_problem(np.random.default_rng(5), al_max=40)
+    for over in (dict(go=0), dict(ie_coef=40.0)):
+        with pytest.raises(RuntimeError, match="-3"):
+            mp.nasw_batch(ctx, mp.nsopt(**over), [(nt, aa, 1, 29)])

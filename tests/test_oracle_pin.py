@@ -158,3 +158,52 @@ def test_chain(mode):
         assert len(ua) == len(ub) and (ua == ub).all() and (ba == bb).all(), (mode, it, n)
         n_nonempty += len(ua) > 0
     assert n_nonempty > 30
+
+
+def _random_scoring(rng, go_min=1):
+    """Scoring parameters over the range the CLI reaches (-O -E -J -F -B, splice models, x-drop, ie_coef)."""
+    par = dict(ol.DEFAULT_NASW)
+    par.update(go=int(rng.integers(go_min, 31)), ge=int(rng.integers(0, 6)), io=int(rng.integers(3, 61)), fs=int(rng.integers(1, 61)),
+               end_bonus=int(rng.integers(0, 21)), xdrop=int(rng.choice([5, 30, 100, 400])), ie_coef=float(rng.choice([0.0, 0.25, 0.5, 1.0, 2.5])))
+    if rng.random() < 0.5:
+        par["sp"] = tuple(int(x) for x in rng.integers(0, 40, size=4)) + (int(rng.integers(0, 8)), int(rng.integers(0, 8)))
+    return par
+
+
+def test_nasw_random_scoring_parameters(tab):
+    """The restatement equals the reference for every gap-open penalty >= 1 together with random other penalties, stop-codon
+    scores (-C, options.c:87-88) and problem shapes (tools/fuzz_emu.py runs the same comparison open-ended)."""
+    rng = np.random.default_rng(909)
+    for it in range(150):
+        par = _random_scoring(rng)
+        m = ol.default_mat()
+        if it % 3 == 0:
+            ol.ref().ref_ns_set_stop_sc(22, m.ctypes.data_as(C.c_void_p), int(rng.integers(1, 60)))
+        nt, aa = ol.random_dp_problem(rng, al_max=int(rng.choice([12, 64, 140, 300])), flank=int(rng.choice([0, 3, 60])),
+                                      intron_max=int(rng.choice([0, 60, 400])), p_sub=float(rng.choice([0.05, 0.2, 0.5])))
+        if len(nt) < 3:
+            continue
+        for flag in (1, 4, 2):
+            b = ol.ora_nasw(tab, nt, aa, flag, m, par)
+            if flag != 1 and b[2] == len(aa) + 1:
+                continue  # the reference stops at an assertion here (nasw-sse.c:441)
+            a = ol.ref_nasw(nt, aa, flag, m, par)
+            assert (a[0] == b[0] and a[3] == b[3]) if flag == 1 else (a[:3] == b[:3]), (it, flag, len(nt), len(aa), par, a[:3], b[:3])
+
+
+def test_nasw_gap_open_zero_is_layout_dependent_in_the_reference(tab, mat):
+    """go == 0 is outside the restatement (oracle/nasw.c header) and refused by the product: the reference's lazy-F loop
+    (nasw-sse.c:408-422) then stops after the first stripe, so its scores fall BELOW the recurrence's on some problems --
+    never above, and never for go >= 1.  Pins the reason for the precondition."""
+    rng = np.random.default_rng(4)
+    below = 0
+    for it in range(200):
+        par = _random_scoring(rng)
+        par["go"] = 0
+        nt, aa = ol.random_dp_problem(rng, al_max=80, flank=30)
+        if len(nt) < 3:
+            continue
+        a, b = ol.ref_nasw(nt, aa, 1, mat, par), ol.ora_nasw(tab, nt, aa, 1, mat, par)
+        assert a[0] <= b[0], (it, a[0], b[0])
+        below += a[0] < b[0]
+    assert below > 0
