@@ -177,7 +177,9 @@ int32_t mp_map_file(const mp_idx_t *idx, const char *fn, const mp_mapopt_t *opt,
 double mp_realtime(void);                                               /* mppriv.h:47 (sys.c:93)  */
 double mp_cputime(void);                                                /* mppriv.h:48 (sys.c:107) */
 long mp_peakrss(void);                                                  /* mppriv.h:49 (sys.c:116) */
-/* --spsc splice-score input: not served in this round; both return/leave "no scores". */
+/* --spsc splice-score input (ntseq.c:234-296, index.c:239-248): the score file is read into mi->nt->spsc
+ * (sorted per contig and strand, as the reference keeps them); the mapping context scatters it into a dense per-base table in
+ * HBM on first use and the DP prep kernels apply nasw-sse.c:138-152,189-203. */
 int32_t mp_ntseq_read_spsc(mp_ntdb_t *nt, const char *fn, int32_t max_sc);  /* miniprot.h:251 */
 void mp_set_spsc(const char *fn, mp_idx_t *mi, mp_mapopt_t *mo, int32_t keep_io); /* miniprot.h:253 */
 

@@ -85,7 +85,7 @@ struct OracleStages : Stages {
 	void nasw(const mp_idx_t *mi, const ns_opt_t *base, const Batch &b, const std::vector<DpJob> &jobs, DpSet &out) override
 	{
 		ora_tab_t tab = product_tables();
-		std::vector<uint8_t> nt;
+		std::vector<uint8_t> nt, ss;
 		out.score.clear(), out.nt_len.clear(), out.aa_len.clear(), out.cig.clear(), out.cig_off.assign(1, 0);
 		for (const DpJob &j : jobs) {
 			ora_nasw_par_t p;
@@ -97,7 +97,24 @@ struct OracleStages : Stages {
 			if (l != j.nl) { fprintf(stderr, "[hostcheck] bad slice %ld != %d\n", (long)l, j.nl); abort(); }
 			ora_nasw_rst_t r;
 			memset(&r, 0, sizeof(r));
-			ora_nasw(&tab, &p, nt.data(), j.nl, b.seq[j.qid] + j.aa_st, j.al, 0, &r);
+			// --spsc: the bytes of the slice as mp_ntseq_spsc_get() fills them for the region's window (ntseq.c:130-156): the largest
+			// byte of a position, 0xff where there is none -- and none at the window's first position, which the reference's
+			// interval search always skips
+			const uint8_t *ssp = 0;
+			if (mi->nt->spsc) {
+				ss.assign((size_t)j.nl + 1, 0xff);
+				const mp_spsc_t *sv = &mi->nt->spsc[j.vid];
+				const uint64_t *lo = std::lower_bound(sv->a, sv->a + sv->n, (uint64_t)j.nt_st << 8);
+				for (const uint64_t *e = lo; e < sv->a + sv->n && (int64_t)(*e >> 8) < j.nt_st + j.nl; ++e) {
+					const int64_t pos = (int64_t)(*e >> 8);
+					const uint8_t sc = (uint8_t)(*e & 0xff);
+					if (pos == j.win_st) continue;
+					uint8_t &x = ss[(size_t)(pos - j.nt_st)];
+					if (x == 0xff || x < sc) x = sc;
+				}
+				ssp = ss.data();
+			}
+			ora_nasw(&tab, &p, nt.data(), j.nl, b.seq[j.qid] + j.aa_st, j.al, ssp, &r);
 			out.score.push_back(r.score), out.nt_len.push_back(r.nt_len), out.aa_len.push_back(r.aa_len);
 			if (r.n_cigar) out.cig.insert(out.cig.end(), r.cigar, r.cigar + r.n_cigar);
 			out.cig_off.push_back((int64_t)out.cig.size());
@@ -144,6 +161,16 @@ int hc_map_file(const char *genome, const char *prot, const char *out_path, uint
 	fclose(fp);
 	mp_idx_destroy(mi);
 	return rc;
+}
+
+// The reference's mp_map_file() entry with the oracle stages behind it: lets the UNMODIFIED reference CLI (main.c) be linked
+// against this test library (tests/test_host_cli.py), so that the host side of the product -- option handling, index builder
+// and .mpi I/O, hit bookkeeping, alignment planner, statistics, every output format -- is compared with the reference binary
+// under arbitrary command lines, without a GPU.
+int32_t mp_map_file(const mp_idx_t *mi, const char *fn, const mp_mapopt_t *opt, int)
+{
+	OracleStages st;
+	return map_file(&st, mi, fn, opt, stdout);
 }
 
 int hc_idx_dump(const char *genome, const char *out_mpi, int32_t n_threads)
