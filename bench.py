@@ -469,7 +469,7 @@ def main():
         "e2e": {"value": e2e, "unit": "proteins/s", "h2d_bytes_per_step": st2.h2d_bytes // args.steps, "d2h_bytes_per_step": st2.d2h_bytes // args.steps,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(st.kernel_launches), "roofline": roofline, "roofline_int": roofline_int, "int_peak": int_peak, "cpu_baseline": cpu,
-        "clocks": sampler.summary()}))
+        "clocks": sampler.summary(), "build": mp.build_info()}))
     ctx.close()
     if dist:
         dist.destroy_process_group()

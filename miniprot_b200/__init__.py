@@ -19,12 +19,64 @@ NS_F_CIGAR, NS_F_EXT_LEFT, NS_F_EXT_RIGHT = 1, 2, 4
 MP_F_NO_SPLICE, MP_F_NO_ALIGN, MP_F_SHOW_UNMAP, MP_F_NO_PRE_CHAIN, MP_F_NO_CS = 0x1, 0x2, 0x4, 0x40, 0x200
 
 
+BUILD_INFO = os.path.join(_HERE, "BUILD_INFO.json")
+_SRC_GLOBS = ("csrc/Makefile", "csrc/*.cpp", "csrc/*.hpp", "csrc/cuda/*.cu", "csrc/cuda/*.cuh", "csrc/cuda/*.hpp", "../include/*.h")
+
+
+def _sha256_file(path: str) -> str:
+    import hashlib
+
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 20), b""):
+            h.update(blk)
+    return h.hexdigest()
+
+
+def source_fingerprint() -> str:
+    """sha256 over the sources the library is compiled from (paths and contents, sorted)."""
+    import glob
+    import hashlib
+
+    h = hashlib.sha256()
+    for pat in _SRC_GLOBS:
+        for path in sorted(glob.glob(os.path.join(_HERE, pat))):
+            h.update(os.path.relpath(path, _HERE).encode() + b"\0" + _sha256_file(path).encode() + b"\n")
+    return h.hexdigest()
+
+
 def build(force: bool = False) -> str:
-    """Compile the shared library in-tree with nvcc for sm_100a (no GPU needed to compile)."""
+    """Compile the shared library in-tree with nvcc for sm_100a (no GPU needed to compile) and record what it was built from
+    (BUILD_INFO.json next to the library: travels to the GPU box with it, stays out of the history like the library)."""
+    import json
+    import time
+
     if force:
         subprocess.run(["make", "-s", "-C", CSRC, "clean"], check=True)
     subprocess.run(["make", "-s", "-j8", "-C", CSRC], check=True)
+    try:
+        nvcc = subprocess.run(["nvcc", "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    except OSError:
+        nvcc = "unknown"
+    with open(BUILD_INFO, "w") as f:
+        json.dump({"source_sha256": source_fingerprint(), "so_sha256": _sha256_file(LIB_PATH), "nvcc": nvcc,
+                   "arch": "-gencode arch=compute_100a,code=sm_100a", "built_at": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())}, f)
     return LIB_PATH
+
+
+def build_info() -> dict:
+    """What build() recorded, plus whether the library that is loaded now is that build and the sources are still the ones it was
+    compiled from.  Never raises (bench.py and smoke() report it)."""
+    import json
+
+    try:
+        with open(BUILD_INFO) as f:
+            info = json.load(f)
+        info["so_is_that_build"] = _sha256_file(LIB_PATH) == info.get("so_sha256")
+        info["sources_unchanged_since"] = source_fingerprint() == info.get("source_sha256")
+        return info
+    except Exception as e:  # noqa: BLE001 -- a report, not a gate
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 class IdxOpt(C.Structure):  # mp_idxopt_t

@@ -122,3 +122,19 @@ def test_splice_score_reader_equals_reference(L, tmp_path):
             tot += sa[j].n
         assert tot > 1000
     L.mp_idx_destroy(a)
+
+
+def test_build_record_matches_the_loaded_library():
+    """build() records what the library was compiled from (BUILD_INFO.json); bench.py and smoke() report it, so a stale or foreign
+    .so would show (so_is_that_build / sources_unchanged_since false)."""
+    import os
+
+    import miniprot_b200 as mp
+
+    if not os.path.exists(mp.BUILD_INFO):
+        import pytest
+
+        pytest.skip("library was built outside miniprot_b200.build()")
+    bi = mp.build_info()
+    assert "error" not in bi and bi["so_is_that_build"] and bi["sources_unchanged_since"], bi
+    assert "compute_100a" in bi["arch"] and len(bi["source_sha256"]) == 64
