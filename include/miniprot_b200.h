@@ -213,7 +213,8 @@ int mpb_idx_attach_device(mpb_ctx_t *ctx, const mp_idx_t *mi_meta, void *d_ki, v
  * Returns 0; -1 without a context; -3 (with a message on stderr, nothing mapped) for scoring parameters whose reference
  * result cannot be reproduced bit for bit: a gap open penalty below 1 (with -O 0 the reference's lazy-F loop stops at once,
  * nasw-sse.c:411,530, and its scores depend on the SSE stripe layout) or an ie_coef whose length penalty has more steps
- * than the kernels' table (> ~5).  mpb_map_file() and mpb_nasw_batch() apply the same check. */
+ * than the kernels' table (> ~5); or an index built with a minimum ORF length (-L) above 40, which the tile halos of the
+ * window kernels do not cover.  mpb_map_file() and mpb_nasw_batch() apply the same checks. */
 int mpb_map_batch(mpb_ctx_t *ctx, const mp_idx_t *mi, const mp_mapopt_t *opt, int32_t n_seq,
                   const char *const *seqs, const int32_t *lens, const char *const *names,
                   int32_t *n_reg_out, mp_reg1_t **reg_out);

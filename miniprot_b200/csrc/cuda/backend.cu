@@ -164,6 +164,13 @@ bool bad_scoring(int go, float ie_coef)
 	fprintf(stderr, "[miniprot_b200] ie_coef = %g: the extension length penalty has more than %d steps and is not supported\n", (double)ie_coef, nsw::PEN_STEPS);
 	return true;
 }
+// ... and an index whose minimum ORF length (-L) exceeds what the halos of the window kernel's tiles cover (win_scan.cuh)
+bool bad_index(const mp_idx_t *mi)
+{
+	if (mi->opt.min_aa_len <= WIN_MAX_MIN_AA) return false;
+	fprintf(stderr, "[miniprot_b200] min ORF length %d: values above %d are not supported by the window kernels\n", mi->opt.min_aa_len, WIN_MAX_MIN_AA);
+	return true;
+}
 
 // Host threads of a rank stay on the NUMA node its GPU hangs off (pinned staging buffers, the worker pool of the host phases
 // and the driver's own threads then never cross the socket interconnect; with one rank per GPU on a two-socket box the ranks
@@ -434,7 +441,7 @@ int mpb_map_batch(mpb_ctx_t *c, const mp_idx_t *mi, const mp_mapopt_t *opt, int3
                   const char *const *names, int32_t *n_reg_out, mp_reg1_t **reg_out)
 {
 	if (!c) return -1;
-	if (bad_scoring(opt->go, opt->ie_coef)) return -3;
+	if (bad_scoring(opt->go, opt->ie_coef) || bad_index(mi)) return -3;
 	MPB_CUDA_OK(cudaSetDevice(c->device));
 	Batch b;
 	b.n = n_seq, b.seq = seqs, b.len = lens, b.name = names;
@@ -445,7 +452,7 @@ int mpb_map_batch(mpb_ctx_t *c, const mp_idx_t *mi, const mp_mapopt_t *opt, int3
 int32_t mpb_map_file(mpb_ctx_t *c, const mp_idx_t *mi, const char *fn, const mp_mapopt_t *opt, FILE *out)
 {
 	if (!c) return -1;
-	if (bad_scoring(opt->go, opt->ie_coef)) return -3;
+	if (bad_scoring(opt->go, opt->ie_coef) || bad_index(mi)) return -3;
 	MPB_CUDA_OK(cudaSetDevice(c->device));
 	return map_file(c->stages, mi, fn, opt, out);
 }
