@@ -332,9 +332,13 @@ int32_t map_file(Stages *st, const mp_idx_t *mi, const char *fn, const mp_mapopt
 		if (mp_verbose >= 3)
 			fprintf(stderr, "[M::%s::%.3f*%.2f] mapped %d sequences\n", "map_file", mp_realtime(), mp_cputime() / mp_realtime(), (int)fb.seqs.size());
 	};
+	static const bool trace = getenv("MPB_TRACE") != 0;
 	auto write_step = [&](FileBatch &fb) {
+		const double t0 = mp_realtime();
 		write_batch(out, mi, opt, fb.view(), fb.n_reg.data(), fb.reg.data(), &id_counter);
+		const double t1 = mp_realtime();
 		fb.release();
+		if (trace) fprintf(stderr, "[mpb-trace] output: %d proteins formatted + written in %.2f ms, released in %.2f ms\n", (int)fb.seqs.size(), (t1 - t0) * 1e3, (mp_realtime() - t1) * 1e3);
 	};
 	const char *e = getenv("MPB_FILE_PIPELINE");
 	if (e && atoi(e) == 0) {

@@ -41,6 +41,28 @@ def random_inputs(rng, d):
                            ctg_len=int(rng.choice([100_000, 250_000, 2_000_000])), fs_per_base=float(rng.choice([0.0, 0.0, 0.0067])),
                            min_exons=int(rng.choice([1, 3])), max_exons=int(rng.choice([3, 8])))
     g, p = synth.generate(spec, d)
+    if rng.random() < 0.6:  # paralogs: diverged copies of random segments (whole or partial genes, either strand) elsewhere in the genome
+        comp = bytes.maketrans(b"ACGT", b"TGCA")
+        recs = [r.split("\n", 1) for r in open(g).read().split(">")[1:]]
+        seqs = [bytearray(r[1].replace("\n", "").encode()) for r in recs]
+        for _ in range(int(rng.integers(2, 12))):
+            a, b = int(rng.integers(0, len(seqs))), int(rng.integers(0, len(seqs)))
+            ln = int(rng.integers(1500, 20000))
+            if len(seqs[a]) <= ln + 10 or len(seqs[b]) <= ln + 10:
+                continue
+            s0, t0 = int(rng.integers(0, len(seqs[a]) - ln)), int(rng.integers(0, len(seqs[b]) - ln))
+            seg = bytearray(seqs[a][s0:s0 + ln])
+            mut = rng.random(ln) < float(rng.choice([0.0, 0.03, 0.1]))
+            sub = rng.integers(0, 4, size=ln)
+            for i in mut.nonzero()[0]:
+                seg[i] = b"ACGT"[sub[i]]
+            if rng.random() < 0.5:
+                seg = bytearray(bytes(seg).translate(comp)[::-1])
+            seqs[b][t0:t0 + ln] = seg
+        g = g[:-3] + f".par{int(rng.integers(1 << 30))}.fa"
+        with open(g, "w") as f:
+            for r, sq in zip(recs, seqs):
+                f.write(">" + r[0] + "\n" + sq.decode() + "\n")
     # awkward query records: unmappable, very short, X / * / lower case, an empty one, a duplicate
     recs = open(p).read().split(">")[1:]
     aa = synth.AA20
