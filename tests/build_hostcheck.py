@@ -10,6 +10,8 @@ HOST_SRCS = ["tables.cpp", "ntdb.cpp", "index.cpp", "hits.cpp", "align.cpp", "pa
 
 
 def build(force=False):
+    if os.environ.get("MPB_HOSTCHECK_SO"):  # a build made elsewhere, e.g. with -fsanitize=address,undefined (run python under LD_PRELOAD=libasan)
+        return os.environ["MPB_HOSTCHECK_SO"]
     srcs = [os.path.join(CSRC, s) for s in HOST_SRCS] + [os.path.join(ROOT, "tests", "hostcheck", f) for f in ("hostcheck.cpp", "emu_nasw.cpp", "emu_chain.cpp")]
     ora = sorted(glob.glob(os.path.join(ROOT, "oracle", "*.c")))
     deps = srcs + ora + glob.glob(os.path.join(CSRC, "*.hpp")) + glob.glob(os.path.join(CSRC, "cuda", "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h")) + \

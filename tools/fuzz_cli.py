@@ -158,7 +158,7 @@ def random_options(rng, g, d):
 
 
 def fuzz(seed, n_it, workdir=None):
-    cli = build_cli()
+    cli = os.environ.get("MPB_FUZZ_CLI") or build_cli()  # MPB_FUZZ_CLI: e.g. the same program built with -fsanitize=address,undefined
     if cli is None or not os.path.exists(REF_BIN):
         print("needs the reference sources (main.c) and oracle/_ref/miniprot")
         return 0, 0
@@ -183,6 +183,7 @@ def fuzz(seed, n_it, workdir=None):
                 n_ref_abort += 1
                 continue
             same = outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+            same = same and b"Sanitizer" not in outs[1][2] and b"runtime error" not in outs[1][2]
             if use_mpi:
                 same = same and open(os.path.join(d, "i0.mpi"), "rb").read() == open(os.path.join(d, "i1.mpi"), "rb").read()
             if not same:
