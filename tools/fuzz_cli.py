@@ -150,10 +150,12 @@ def random_options(rng, g, d):
         o.extend(["--spsc", sp])
         maybe(0.3, "--spsc0", int(rng.integers(0, 15)))
         maybe(0.3, "--spsc-max", int(rng.integers(0, 15)))
-    if rng.random() < 0.08:  # index options (host index builder; the default index is what the GPU stages are built for)
+    if rng.random() < float(os.environ.get("MPB_FUZZ_P_INDEX", 0.08)):  # index options (host index builder; the default index is what the GPU stages are built for)
         maybe(0.5, "-M", int(rng.choice([0, 2])))
         maybe(0.5, "-L", int(rng.choice([10, 50])))
         maybe(0.3, "-b", int(rng.choice([7, 9])))
+        maybe(0.3, "-k", 5)
+        maybe(0.4, "-T", int(rng.choice([2, 3, 4, 5, 6, 9, 11, 12, 13, 14, 16, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 33])))
     return o
 
 
@@ -173,7 +175,7 @@ def fuzz(seed, n_it, workdir=None):
             outs = []
             mpi = [os.path.join(d, f"i{k}.mpi") for k in range(2)]
             if use_mpi:
-                idx_opts = [x for i, x in enumerate(opts) if x in ("-M", "-L", "-b") or (i and opts[i - 1] in ("-M", "-L", "-b"))]
+                idx_opts = [x for i, x in enumerate(opts) if x in ("-M", "-L", "-b", "-k", "-T") or (i and opts[i - 1] in ("-M", "-L", "-b", "-k", "-T"))]
                 for k, binary in enumerate((REF_BIN, cli)):
                     subprocess.run([binary, "-t2", "-d", mpi[k]] + idx_opts + [g], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             for k, binary in enumerate((REF_BIN, cli)):
