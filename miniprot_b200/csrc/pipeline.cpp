@@ -320,7 +320,8 @@ private:
 // it (the GPU batch dispatcher above), step 2 formats and writes the hits -- in the order of the input, by one thread, which
 // also owns the hit counter.  As in the reference, step 0 of batch n+1 and step 2 of batch n-1 run while batch n is mapped:
 // one reader thread, the calling thread as the mapper (it owns the device), one writer thread, a one-slot hand-over between
-// neighbours.  MPB_FILE_PIPELINE=0 runs the three steps one after another on the calling thread (A/B, debugging).
+// neighbours.  An input that fits one mini-batch has nothing to overlap and starts no thread; MPB_FILE_PIPELINE=0 runs the three
+// steps one after another on the calling thread for any input (A/B, debugging).
 int32_t map_file(Stages *st, const mp_idx_t *mi, const char *fn, const mp_mapopt_t *opt, FILE *out)
 {
 	FastxReader rd(fn);
@@ -341,11 +342,11 @@ int32_t map_file(Stages *st, const mp_idx_t *mi, const char *fn, const mp_mapopt
 		if (trace) fprintf(stderr, "[mpb-trace] output: %d proteins formatted + written in %.2f ms, released in %.2f ms\n", (int)fb.seqs.size(), (t1 - t0) * 1e3, (mp_realtime() - t1) * 1e3);
 	};
 	const char *e = getenv("MPB_FILE_PIPELINE");
-	if (e && atoi(e) == 0) {
-		bool more = true;
-		while (more) {
-			std::unique_ptr<FileBatch> fb = read_batch(rd, opt->mini_batch_size, more);
-			if (!fb) break;
+	bool more = true;
+	std::unique_ptr<FileBatch> first = read_batch(rd, opt->mini_batch_size, more);
+	if (!first) return 0;
+	if ((e && atoi(e) == 0) || !more) { // the whole input is one mini-batch (nothing to overlap: no threads), or the serial form was asked for
+		for (std::unique_ptr<FileBatch> fb = std::move(first); fb; fb = more ? read_batch(rd, opt->mini_batch_size, more) : std::unique_ptr<FileBatch>()) {
 			map_step(*fb);
 			write_step(*fb);
 		}
@@ -353,7 +354,6 @@ int32_t map_file(Stages *st, const mp_idx_t *mi, const char *fn, const mp_mapopt
 	}
 	Handoff to_map, to_write;
 	std::thread reader([&] {
-		bool more = true;
 		while (more) {
 			std::unique_ptr<FileBatch> fb = read_batch(rd, opt->mini_batch_size, more);
 			if (!fb) break;
@@ -364,7 +364,7 @@ int32_t map_file(Stages *st, const mp_idx_t *mi, const char *fn, const mp_mapopt
 	std::thread writer([&] {
 		while (std::unique_ptr<FileBatch> fb = to_write.take()) write_step(*fb);
 	});
-	while (std::unique_ptr<FileBatch> fb = to_map.take()) {
+	for (std::unique_ptr<FileBatch> fb = std::move(first); fb; fb = to_map.take()) {
 		map_step(*fb);
 		to_write.put(std::move(fb));
 	}
