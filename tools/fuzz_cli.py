@@ -168,6 +168,11 @@ def fuzz(seed, n_it, workdir=None):
     bad = n_ref_abort = 0
     with tempfile.TemporaryDirectory(dir=workdir) as d:
         for it in range(n_it):
+            if it and it % 100 == 0:
+                print(f"progress seed {seed}: {it} command lines, {bad} mismatches ({n_ref_abort} skipped: the reference aborted)", flush=True)
+                for f in os.listdir(d):  # inputs of earlier iterations
+                    if f not in (os.path.basename(g), os.path.basename(p)) and not f.endswith(".planted.faa"):
+                        os.remove(os.path.join(d, f))
             if it % 4 == 0:
                 g, p = random_inputs(rng, d)
             opts = random_options(rng, g, d)

@@ -43,6 +43,8 @@ def fuzz(seed, n_it):
     tab = ol.ref_tables()
     n_cmp = n_pair = n_bad = 0
     for it in range(n_it):
+        if it and it % 2000 == 0:
+            print(f"progress seed {seed}: {it} problems, {n_cmp} comparisons ({n_pair} on the pair-lane family), {n_bad} mismatches", flush=True)
         par = random_par(rng)
         mat = ol.default_mat()
         if rng.random() < 0.3:  # -C: stop-codon score scale (options.c:87-88)
@@ -74,7 +76,7 @@ def fuzz(seed, n_it):
                 if not ok:
                     n_bad += 1
                     print(f"MISMATCH seed={seed} it={it} flag={flag} family={fam} nl={len(nt)} al={len(aa)} par={par} ss={ss is not None}\n  ref={want[:3]} ora={o[:3]} emu={got[:3]}", flush=True)
-    print(f"seed {seed}: {n_cmp} comparisons ({n_pair} on the pair-lane family), {n_bad} mismatches")
+    print(f"seed {seed}: {n_cmp} comparisons ({n_pair} on the pair-lane family), {n_bad} mismatches", flush=True)
     return n_cmp, n_pair, n_bad
 
 

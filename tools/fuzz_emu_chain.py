@@ -26,6 +26,8 @@ def main():
     rng = np.random.default_rng(seed)
     bad = 0
     for it in range(n_it):
+        if it and it % 2000 == 0:
+            print(f"progress seed {seed}: {it} problems, {bad} mismatches", flush=True)
         mode = ("pre", "main", "refine")[it % 3]
         n = int(rng.integers(1, 80)) if rng.random() < 0.5 else int(rng.integers(80, 4000))
         a = ol.random_chain_problem(rng, n, mode)
