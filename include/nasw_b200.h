@@ -86,6 +86,10 @@ void ns_set_stop_sc(int32_t asize, int8_t *mat, int8_t score);
  * That is what kfree(0, ptr) does in the reference, so callers that pass km = NULL -- example code, tests -- need no change;
  * a caller that passes a real arena must switch the release to free().
  * ss: per-base splice-score bytes of the slice (--spsc, ntseq.c:130-156; NULL = none), applied like nasw-sse.c:138-152,189-203.
+ * Preconditions: opt->go >= 1 (with a gap open penalty of 0 the reference's lazy-F loop, nasw-sse.c:408-422 / 521-537, stops at
+ * once and its result depends on the SSE stripe layout) and an ie_coef whose length penalty fits the kernels'
+ * step table (<= ~5).  A call that violates them prints a message and aborts (the function has no way to report an error;
+ * mpb_nasw_batch() returns -3 instead).
  * ns_global_gs32 / ns_global_gs32b (reference nasw.h:129,132; never called by miniprot) are NOT exported: see DESIGN.md section 8. */
 void ns_global_gs16(void *km, const char *ns, int32_t nl, const char *as, int32_t al, const ns_opt_t *opt, ns_rst_t *r);
 void ns_global_gs16b(void *km, const char *ns, int32_t nl, const char *as, int32_t al, const ns_opt_t *opt, const uint8_t *ss, ns_rst_t *r);
