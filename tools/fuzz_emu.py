@@ -19,6 +19,9 @@ import oracle_lib as ol  # noqa: E402
 from test_emu_nasw import emu, emu_ss, random_spsc  # noqa: E402
 
 
+LONG = os.environ.get("MPB_FUZZ_PROFILE") == "long"
+
+
 def random_par(rng):
     par = dict(ol.DEFAULT_NASW)
     if rng.random() < 0.7:
@@ -43,18 +46,29 @@ def fuzz(seed, n_it):
     tab = ol.ref_tables()
     n_cmp = n_pair = n_bad = 0
     for it in range(n_it):
-        if it and it % 2000 == 0:
+        if it and it % (200 if LONG else 2000) == 0:
             print(f"progress seed {seed}: {it} problems, {n_cmp} comparisons ({n_pair} on the pair-lane family), {n_bad} mismatches", flush=True)
         par = random_par(rng)
         mat = ol.default_mat()
         if rng.random() < 0.3:  # -C: stop-codon score scale (options.c:87-88)
             ol.ref().ref_ns_set_stop_sc(22, mat.ctypes.data_as(C.c_void_p), int(rng.integers(1, 60)))
         shape = rng.random()
-        al_max = 12 if shape < 0.2 else 64 if shape < 0.6 else 140 if shape < 0.85 else 300 if shape < 0.97 else 600
-        nt, aa = ol.random_dp_problem(rng, al_max=al_max, flank=int(rng.choice([0, 3, 60])), intron_max=int(rng.choice([0, 60, 400])),
-                                      p_sub=float(rng.choice([0.05, 0.2, 0.5])), p_fs=float(rng.choice([0.0, 0.02, 0.1])))
-        if rng.random() < 0.1:
-            nt = nt[:int(rng.integers(0, 8))]
+        if LONG:  # MPB_FUZZ_PROFILE=long: several column passes, thousands of rows, long introns, slices cut anywhere
+            al_max = 300 if shape < 0.4 else 700 if shape < 0.8 else 1500
+            nt, aa = ol.random_dp_problem(rng, al_max=al_max, flank=int(rng.choice([0, 60, 2000])), intron_max=int(rng.choice([400, 5000])),
+                                          p_sub=float(rng.choice([0.05, 0.2, 0.5])), p_fs=float(rng.choice([0.0, 0.02, 0.1])), p_n=float(rng.choice([0.0, 0.002, 0.05])))
+            if rng.random() < 0.3 and len(nt) > 8:
+                a, b = sorted(int(x) for x in rng.integers(0, len(nt), size=2))
+                nt = nt[a:b] if b - a >= 3 else nt
+        else:
+            al_max = 12 if shape < 0.2 else 64 if shape < 0.6 else 140 if shape < 0.85 else 300 if shape < 0.97 else 600
+            nt, aa = ol.random_dp_problem(rng, al_max=al_max, flank=int(rng.choice([0, 3, 60])), intron_max=int(rng.choice([0, 60, 400])),
+                                          p_sub=float(rng.choice([0.05, 0.2, 0.5])), p_fs=float(rng.choice([0.0, 0.02, 0.1])))
+            if rng.random() < 0.1:
+                nt = nt[:int(rng.integers(0, 8))]
+            elif rng.random() < 0.1 and len(nt) > 8:
+                a, b = sorted(int(x) for x in rng.integers(0, len(nt), size=2))
+                nt = nt[a:b] if b - a >= 3 else nt
         use_ss = rng.random() < 0.15
         ss = random_spsc(rng, nt, max_sc=(par["io"] + 1) // 2 - 1 if rng.random() < 0.7 else 40) if use_ss and len(nt) else None
         sp = (C.c_int32 * 6)(*par["sp"])
