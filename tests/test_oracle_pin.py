@@ -207,3 +207,34 @@ def test_nasw_gap_open_zero_is_layout_dependent_in_the_reference(tab, mat):
         assert a[0] <= b[0], (it, a[0], b[0])
         below += a[0] < b[0]
     assert below > 0
+
+
+def test_committed_goldens_are_what_the_reference_prints(tmp_path):
+    """tests/golden/*.paf are the reference's own output (tests/golden/make_golden.py): re-run the compiled reference on the same
+    inputs and compare, so that a stale or hand-edited golden cannot pass for the reference."""
+    import hashlib
+    import os
+    import subprocess
+
+    from miniprot_b200 import synth
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    data = os.path.join(ol.ORA_DIR, "_ref", "data")
+    if not os.path.exists(ol.REF_BIN):
+        pytest.skip("reference binary not built")
+
+    def ref_out(args):
+        return subprocess.run([ol.REF_BIN, "-t4"] + args, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+
+    g, p = os.path.join(data, "DPP3-hs.gen.fa.gz"), os.path.join(data, "DPP3-mm.pep.fa.gz")
+    if os.path.exists(g):
+        out = ref_out([g, p])
+        assert hashlib.md5(out).hexdigest() == "74fd00200bda6c03380bb3062fb5178b"  # SURVEY.md App. D
+        assert out == open(os.path.join(gold, "DPP3_default.paf"), "rb").read()
+        assert ref_out(["-j2", g, p]) == open(os.path.join(gold, "DPP3_j2.paf"), "rb").read()
+        assert ref_out(["--gff", g, p]) == open(os.path.join(gold, "DPP3_gff.txt"), "rb").read()
+    for cfg in ("tiny", "tiny5"):
+        gg, pp = synth.generate(synth.CONFIGS[cfg], str(tmp_path))
+        assert ref_out([gg, pp]) == open(os.path.join(gold, cfg + ".paf"), "rb").read()
+    gg, pp = synth.generate(synth.CONFIGS["tiny5"], str(tmp_path))
+    assert ref_out(["--gtf", gg, pp]) == open(os.path.join(gold, "tiny5_gtf.txt"), "rb").read()
