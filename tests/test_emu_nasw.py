@@ -172,3 +172,17 @@ def test_emu_random_scoring_parameters():
 
     n_cmp, n_pair, n_bad = fuzz_emu.fuzz(20260924, 80)
     assert n_bad == 0 and n_cmp > 400 and n_pair > 50
+
+
+def test_emu_random_scoring_parameters_long_profile(monkeypatch):
+    """The same comparison on the fuzzer's "long" profile: problems of several column passes (up to 1500 columns), thousands of rows,
+    long introns, slices cut anywhere, runs of N."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_emu
+
+    monkeypatch.setattr(fuzz_emu, "LONG", True)
+    n_cmp, _, n_bad = fuzz_emu.fuzz(424242, 8)
+    assert n_bad == 0 and n_cmp >= 30
