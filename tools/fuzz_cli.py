@@ -20,18 +20,16 @@ from miniprot_b200 import synth  # noqa: E402
 
 REF_SRC = os.environ.get("MPB_REFERENCE", "/root/reference")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "miniprot")
-CLI = os.path.join(ROOT, "tests", "_build", "miniprot_hostcheck_cli")
+CLI = os.path.join(ROOT, "oracle", "_ref", "miniprot_hostcheck_cli")  # compiled reference source: output under oracle/_ref like the other reference builds
 
 
 def build_cli():
-    """tests/_build/miniprot_hostcheck_cli = reference main.c (compiled where it lies) + libhostcheck.so"""
-    so = build_hostcheck.build()
-    main_c = os.path.join(REF_SRC, "main.c")
-    if not os.path.exists(main_c):
+    """oracle/_ref/miniprot_hostcheck_cli = reference main.c (compiled where it lies) + tests/_build/libhostcheck.so; the recipe is
+    oracle/Makefile (target hostcheck_cli)"""
+    build_hostcheck.build()
+    if not os.path.exists(os.path.join(REF_SRC, "main.c")):
         return None
-    if not os.path.exists(CLI) or os.path.getmtime(CLI) < os.path.getmtime(so):
-        subprocess.run(["gcc", "-std=c99", "-O2", "-w", "-I" + REF_SRC, main_c, "-o", CLI, "-L" + os.path.dirname(so), "-lhostcheck",
-                        "-Wl,-rpath,$ORIGIN", "-lpthread", "-lz", "-lm"], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "hostcheck_cli", "REF=" + REF_SRC], check=True)
     return CLI
 
 
